@@ -1,0 +1,107 @@
+"""ctypes binding of libdstagnn_b200.so (the C ABI declared in include/dstagnn_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised.  The library is built in-tree by
+``__graft_entry__.build()`` (nvcc, sm_100a) so that it travels with the repo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
+ABI_VERSION = 1
+
+ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+
+
+class Axis(C.Structure):
+    _fields_ = [("s0", C.c_int64), ("s1", C.c_int64), ("d1", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Operand(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("batch", Axis), ("row", Axis), ("col", Axis)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("batch", C.c_int32),
+                ("A", Operand), ("B", Operand), ("C", Operand),
+                ("Amul", Operand), ("Cmul", Operand), ("Cadd", Operand),
+                ("alpha", C.c_float), ("relu", C.c_int32), ("accumulate", C.c_int32),
+                ("split_k", C.c_int32), ("precision", C.c_int32), ("pad_", C.c_int32)]
+
+
+_F = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
+_i32, _i64, _f32, _u64 = C.c_int32, C.c_int64, C.c_float, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/dstagnn_b200.h one to one
+SIGNATURES = {
+    "dstag_abi_version": (C.c_int, []),
+    "dstag_last_error": (C.c_char_p, []),
+    "dstag_launch_count": (_i64, []),
+    "dstag_reset_launch_count": (None, []),
+    "dstag_gemm": (C.c_int, [C.POINTER(Gemm), _F]),
+    "dstag_gemm_uses_tensor_cores": (C.c_int, [C.POINTER(Gemm)]),
+    "dstag_layernorm_fwd": (C.c_int, [_F, _i64, _i64, _i32, _i64, _F, _i32, _F, _F, _f32, _F, _F, _F,
+                                      _i32, _i32, _f32, _u64, _F]),
+    "dstag_layernorm_bwd": (C.c_int, [_F, _F, _i64, _i64, _i32, _i64, _F, _i32, _F, _F, _F, _F, _F, _F,
+                                      _i32, _i32, _f32, _u64, _F]),
+    "dstag_colsum": (C.c_int, [_F, _F, _i64, _i64, _i64, _F]),
+    "dstag_transpose": (C.c_int, [_F, _F, _i32, _i32, _i32, _F]),
+    "dstag_softmax_fwd": (C.c_int, [_F, _i64, _i32, _i32, _F]),
+    "dstag_softmax_bwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _F]),
+    "dstag_relu_bwd": (C.c_int, [_F, _F, _F, _i64, _F]),
+    "dstag_tattn_fwd": (C.c_int, [_F, _F, _i32, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_tattn_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_gtu_gate_fwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
+    "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
+    "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F]),
+    "dstag_tail_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i32, _i32, _f32,
+                                 _u64, _F]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root "
+            "(needs nvcc with sm_100a support). There is no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    ver = lib.dstag_abi_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"libdstagnn_b200.so ABI {ver} != expected {ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def stream_ptr(t):
+    """cudaStream_t of torch's current stream on t's device, as a void*."""
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().dstag_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().dstag_launch_count())
+
+
+def reset_launch_count():
+    load().dstag_reset_launch_count()

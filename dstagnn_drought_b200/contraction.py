@@ -1,0 +1,281 @@
+"""Einsum-style front end of ``dstag_gemm`` (include/dstagnn_b200.h).
+
+``contract("bftn,dtf->bnd", O, W)`` classifies every index letter by where it
+occurs -- in both inputs and the output (batch), first input and output (m),
+second input and output (n), both inputs only (k: summed) -- and hands the
+kernel the operands' *native strides*, so permuted / sliced / unfolded views are
+consumed in place: no ``.contiguous()``, no im2col buffer.  Each role may span at
+most two tensor dimensions (the C ABI's two-level axis).
+
+``contract`` is differentiable (both operands and the additive epilogue term);
+its backward is two more ``contract_raw`` calls with the roles swapped, which is
+how every weight- and input-gradient of the dense products in
+model/DSTAGNN_my.py:62-63, 92-99, 128-131, 193, 207, 221, 232, 243, 266-267 is
+produced.  ``contract_raw`` is the non-differentiable primitive used inside the
+hand-written autograd Functions of ``ops.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACC_ADD, ACC_ATOMIC, ACC_STORE, Axis, Gemm, Operand
+
+_PRECISION = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "tf32": _lib.PREC_TF32}
+_precision = _lib.PREC_TF32X3
+NUM_SMS = 148
+
+
+def set_precision(name: str):
+    """'fp32' (CUDA-core FMA), 'tf32x3' (tensor cores, fp32-grade; default) or 'tf32'."""
+    global _precision
+    _precision = _PRECISION[name]
+
+
+def get_precision() -> str:
+    return {v: k for k, v in _PRECISION.items()}[_precision]
+
+
+class Plan:
+    """Index-role classification of one contraction spec."""
+
+    def __init__(self, spec: str):
+        ins, out = spec.replace(" ", "").split("->")
+        a, b = ins.split(",")
+        for s in (a, b, out):
+            if len(set(s)) != len(s):
+                raise ValueError(f"repeated index in '{s}' of '{spec}'")
+        self.a, self.b, self.c = a, b, out
+        sa, sb, sc = set(a), set(b), set(out)
+        if not sc <= (sa | sb):
+            raise ValueError(f"output index missing from inputs in '{spec}'")
+        if (sa - sb - sc) or (sb - sa - sc):
+            raise ValueError(f"index summed over a single operand in '{spec}' is not supported")
+        self.batch = [l for l in out if l in sa and l in sb]
+        self.m = [l for l in out if l in sa and l not in sb]
+        self.n = [l for l in out if l in sb and l not in sa]
+        self.k = [l for l in a if l in sb and l not in sc]
+        for role, letters in (("batch", self.batch), ("m", self.m), ("n", self.n), ("k", self.k)):
+            if len(letters) > 2:
+                raise ValueError(f"role {role} spans {len(letters)} dims {letters} in '{spec}' (max 2); "
+                                 "merge dims with .view() first")
+
+
+_plans = {}
+
+
+def plan(spec: str) -> Plan:
+    p = _plans.get(spec)
+    if p is None:
+        p = _plans[spec] = Plan(spec)
+    return p
+
+
+def _sizes(pl: Plan, A, B, extra):
+    size = {}
+    for sub, t in ((pl.a, A), (pl.b, B)) + tuple(extra):
+        if t.dim() != len(sub):
+            raise ValueError(f"operand with subscripts '{sub}' has {t.dim()} dims {tuple(t.shape)}")
+        for l, s in zip(sub, t.shape):
+            if size.setdefault(l, s) != s:
+                raise ValueError(f"size mismatch for index '{l}': {size[l]} vs {s}")
+    return size
+
+
+def _axis(letters: Sequence[str], sub: str, t: torch.Tensor, size) -> Axis:
+    def stride(l):
+        i = sub.find(l)
+        return t.stride(i) if i >= 0 else 0
+
+    if len(letters) == 0:
+        return Axis(0, 0, 1, 0)
+    if len(letters) == 1:
+        return Axis(stride(letters[0]), 0, 1, 0)
+    hi, lo = letters
+    s_hi, s_lo, d_lo = stride(hi), stride(lo), size[lo]
+    if s_hi == s_lo * d_lo:                      # the two dims flatten into one
+        return Axis(s_lo, 0, 1, 0)
+    return Axis(s_hi, s_lo, d_lo, 0)
+
+
+def _operand(t: Optional[torch.Tensor], sub: str, batch, row, col, size) -> Operand:
+    if t is None:
+        z = Axis(0, 0, 1, 0)
+        return Operand(None, z, z, z)
+    return Operand(t.data_ptr(), _axis(batch, sub, t, size), _axis(row, sub, t, size),
+                   _axis(col, sub, t, size))
+
+
+def _prod(letters, size):
+    r = 1
+    for l in letters:
+        r *= size[l]
+    return r
+
+
+def _check(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"dstagnn_drought_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"dstagnn_drought_b200: {name} must be float32, got {t.dtype}")
+
+
+def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, alpha=1.0,
+                     relu=False, accumulate=ACC_STORE, split_k=1, precision=None) -> Gemm:
+    """Pure host logic (no CUDA call): used directly by the CPU tests."""
+    pl = plan(spec)
+    extra = [(pl.c, out)]
+    for opt in (a_mul, c_add, c_mul):
+        if opt is not None:
+            extra.append(opt)
+    size = _sizes(pl, A, B, extra)
+    if a_mul is not None and not set(a_mul[0]) <= set(pl.a):
+        raise ValueError("a_mul subscripts must be a subset of the first operand's")
+    for opt in (c_add, c_mul):
+        if opt is not None and not set(opt[0]) <= set(pl.c):
+            raise ValueError("c_add / c_mul subscripts must be a subset of the output's")
+    g = Gemm()
+    g.M, g.N, g.K, g.batch = (_prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size),
+                              _prod(pl.batch, size))
+    g.A = _operand(A, pl.a, pl.batch, pl.m, pl.k, size)
+    g.B = _operand(B, pl.b, pl.batch, pl.k, pl.n, size)
+    g.C = _operand(out, pl.c, pl.batch, pl.m, pl.n, size)
+    g.Amul = _operand(a_mul[1], a_mul[0], pl.batch, pl.m, pl.k, size) if a_mul else _operand(None, "", [], [], [], size)
+    g.Cmul = _operand(c_mul[1], c_mul[0], pl.batch, pl.m, pl.n, size) if c_mul else _operand(None, "", [], [], [], size)
+    g.Cadd = _operand(c_add[1], c_add[0], pl.batch, pl.m, pl.n, size) if c_add else _operand(None, "", [], [], [], size)
+    g.alpha, g.relu, g.accumulate, g.split_k = float(alpha), int(bool(relu)), int(accumulate), int(split_k)
+    g.precision = _precision if precision is None else precision
+    return g
+
+
+def auto_split_k(M: int, N: int, K: int, batch: int) -> int:
+    """Split the reduction when the output grid cannot fill the 148 SMs (weight gradients:
+    tiny M x N, K = batch * nodes * time)."""
+    tiles = ((M + 63) // 64) * ((N + 63) // 64) * batch
+    if tiles >= 2 * NUM_SMS or K < 2048:
+        return 1
+    return max(1, min((4 * NUM_SMS + tiles - 1) // tiles, K // 512))
+
+
+def output_shape(spec: str, A, B):
+    pl = plan(spec)
+    size = _sizes(pl, A, B, ())
+    return tuple(size[l] for l in pl.c)
+
+
+def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+                 a_mul: Optional[Tuple[str, torch.Tensor]] = None,
+                 c_add: Optional[Tuple[str, torch.Tensor]] = None,
+                 c_mul: Optional[Tuple[str, torch.Tensor]] = None, alpha: float = 1.0,
+                 relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
+                 precision=None) -> torch.Tensor:
+    """Enqueue one contraction on the current CUDA stream.  No autograd."""
+    lib = _lib.load()
+    _check(A, "A"), _check(B, "B")
+    for opt in (a_mul, c_add, c_mul):
+        if opt is not None:
+            _check(opt[1], "epilogue/prologue operand")
+    if out is None:
+        if accumulate != ACC_STORE:
+            raise ValueError("accumulating contraction needs an explicit out=")
+        out = torch.empty(output_shape(spec, A, B), device=A.device, dtype=torch.float32)
+    _check(out, "out")
+    pl = plan(spec)
+    size = _sizes(pl, A, B, ((pl.c, out),))
+    M, N, K, nb = _prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size), _prod(pl.batch, size)
+    if split_k is None:
+        split_k = 1 if relu else auto_split_k(M, N, K, nb)
+    if split_k > 1:
+        if accumulate == ACC_STORE:
+            out.zero_()
+        elif accumulate == ACC_ADD:
+            pass  # existing contents are kept; partial sums are added atomically
+        accumulate = ACC_ATOMIC
+    g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
+    _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# small helpers shared with ops.py
+# ----------------------------------------------------------------------------------------
+def colsum(t2d: torch.Tensor, rows: int, cols: int, ld: Optional[int] = None) -> torch.Tensor:
+    """sum over rows of a (rows, cols) matrix with leading dimension ld -> (cols,)."""
+    lib = _lib.load()
+    _check(t2d, "colsum input")
+    out = torch.zeros(cols, device=t2d.device, dtype=torch.float32)
+    _lib.check(lib.dstag_colsum(t2d.data_ptr(), out.data_ptr(), rows, cols, cols if ld is None else ld,
+                                _lib.stream_ptr(t2d)), "dstag_colsum")
+    return out
+
+
+def relu_bwd(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    _lib.check(lib.dstag_relu_bwd(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(),
+                                  _lib.stream_ptr(y)), "dstag_relu_bwd")
+    return dx
+
+
+def reduce_to(sub_out: str, grad: torch.Tensor, sub_keep: str) -> torch.Tensor:
+    """Sum a contiguous gradient with subscripts ``sub_out`` down to ``sub_keep`` (a subset,
+    same relative order).  The big reduction (all leading dims) runs in dstag_colsum; only a
+    tiny remainder, if any, is left to torch."""
+    assert grad.is_contiguous()
+    first = min(sub_out.index(l) for l in sub_keep)
+    lead = 1
+    for s in grad.shape[:first]:
+        lead *= s
+    tail_shape = grad.shape[first:]
+    cols = 1
+    for s in tail_shape:
+        cols *= s
+    red = colsum(grad, lead, cols).view(tail_shape) if lead > 1 else grad.reshape(tail_shape)
+    drop = [i for i, l in enumerate(sub_out[first:]) if l not in sub_keep]
+    if drop:
+        red = red.sum(dim=drop)
+    return red
+
+
+class _Contract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, cadd, amul, spec, cadd_sub, amul_sub, alpha, relu):
+        out = contract_raw(spec, A, B, a_mul=(amul_sub, amul) if amul is not None else None,
+                           c_add=(cadd_sub, cadd) if cadd is not None else None, alpha=alpha, relu=relu)
+        ctx.spec, ctx.cadd_sub, ctx.amul_sub, ctx.alpha, ctx.relu = spec, cadd_sub, amul_sub, alpha, relu
+        ctx.has_cadd = cadd is not None
+        ctx.save_for_backward(A, B, amul, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B, amul, out = ctx.saved_tensors
+        pl = plan(ctx.spec)
+        dC = dC.contiguous()
+        if ctx.relu:
+            dC = relu_bwd(out, dC)
+        dA = dB = dadd = None
+        am = (ctx.amul_sub, amul) if amul is not None else None
+        if ctx.needs_input_grad[0]:
+            dA = torch.empty(A.shape, device=A.device, dtype=torch.float32)
+            contract_raw(f"{pl.c},{pl.b}->{pl.a}", dC, B, out=dA, c_mul=am, alpha=ctx.alpha)
+        if ctx.needs_input_grad[1]:
+            dB = torch.empty(B.shape, device=B.device, dtype=torch.float32)
+            contract_raw(f"{pl.a},{pl.c}->{pl.b}", A, dC, out=dB, a_mul=am, alpha=ctx.alpha)
+        if ctx.has_cadd and ctx.needs_input_grad[2]:
+            dadd = reduce_to(pl.c, dC, ctx.cadd_sub)
+        return dA, dB, dadd, None, None, None, None, None, None
+
+
+def contract(spec: str, A: torch.Tensor, B: torch.Tensor, *, c_add=None, a_mul=None, alpha: float = 1.0,
+             relu: bool = False) -> torch.Tensor:
+    """Differentiable contraction.  ``c_add=(subscripts, tensor)`` is a differentiable additive
+    epilogue term (bias vector / bias matrix); ``a_mul=(subscripts, tensor)`` is a constant
+    Hadamard factor applied to the first operand while it is loaded."""
+    cadd_sub, cadd = c_add if c_add is not None else (None, None)
+    amul_sub, amul = a_mul if a_mul is not None else (None, None)
+    return _Contract.apply(A, B, cadd, amul, spec, cadd_sub, amul_sub, float(alpha), bool(relu))

@@ -1,0 +1,313 @@
+// HBM-bound row kernels: LayerNorm (+embedding/residual add, +dropout), row softmax,
+// column sums, batched transpose, ReLU backward.  One pass over the data each; rows are
+// staged in shared memory so every global element is read once and written once.
+#include "common.cuh"
+
+namespace dstag {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxDynSmem = 200 * 1024;
+
+// ======================================================================================
+// LayerNorm forward
+// ======================================================================================
+__global__ void __launch_bounds__(kRowThreads)
+ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a_div, long long a_sc,
+              const float* __restrict__ tab, int tab_mod, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, float* __restrict__ y,
+              float* __restrict__ mean, float* __restrict__ rstd, int rows, int L, float drop_p,
+              unsigned long long seed) {
+  extern __shared__ float sm[];
+  float* row = sm;        // L floats; slot c is only ever touched by thread (c % blockDim)
+  float* red = sm + L;    // 33 floats
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float invL = 1.f / (float)L;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* ap = a + (long long)(r / a_div) * a_s0 + (long long)(r % a_div) * a_s1;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      float v = __ldg(ap + (long long)c * a_sc);
+      if (tp) v += __ldg(tp + c);
+      row[c] = v;
+      s += v;
+    }
+    const float mu = block_sum(s, red) * invL;
+    float q = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      const float d = row[c] - mu;
+      q = fmaf(d, d, q);
+    }
+    const float rs = rsqrtf(block_sum(q, red) * invL + eps);
+    float* yp = y + (long long)r * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      float o = (row[c] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
+      if (drop_p > 0.f) o *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
+      yp[c] = o;
+    }
+    if (threadIdx.x == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+// ======================================================================================
+// LayerNorm backward: dpre = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma / dbeta are accumulated per CTA in shared memory, then one atomicAdd per column.
+// ======================================================================================
+__global__ void __launch_bounds__(kRowThreads)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, long long a_s0,
+              long long a_s1, int a_div, long long a_sc, const float* __restrict__ tab, int tab_mod,
+              const float* __restrict__ gamma, const float* __restrict__ mean,
+              const float* __restrict__ rstd, float* __restrict__ dpre, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, int rows, int L, float drop_p, unsigned long long seed) {
+  extern __shared__ float sm[];
+  float* xh = sm;            // xhat
+  float* gg = sm + L;        // dy * gamma
+  float* ag = sm + 2 * L;    // dgamma partial
+  float* ab = sm + 3 * L;    // dbeta partial
+  float* red = sm + 4 * L;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float invL = 1.f / (float)L;
+  for (int c = threadIdx.x; c < L; c += blockDim.x) { ag[c] = 0.f; ab[c] = 0.f; }
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* ap = a + (long long)(r / a_div) * a_s0 + (long long)(r % a_div) * a_s1;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
+    const float* dyp = dy + (long long)r * L;
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      float v = __ldg(ap + (long long)c * a_sc);
+      if (tp) v += __ldg(tp + c);
+      const float x = (v - mu) * rs;
+      float d = __ldg(dyp + c);
+      if (drop_p > 0.f) d *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
+      const float g = d * __ldg(gamma + c);
+      xh[c] = x;
+      gg[c] = g;
+      ag[c] = fmaf(d, x, ag[c]);
+      ab[c] += d;
+      s1 += g;
+      s2 = fmaf(g, x, s2);
+    }
+    const float m1 = block_sum(s1, red) * invL;
+    const float m2 = block_sum(s2, red) * invL;
+    float* op = dpre + (long long)r * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) op[c] = rs * (gg[c] - m1 - xh[c] * m2);
+  }
+  for (int c = threadIdx.x; c < L; c += blockDim.x) {
+    atomicAdd(dgamma + c, ag[c]);
+    atomicAdd(dbeta + c, ab[c]);
+  }
+}
+
+// ======================================================================================
+// Column sums with a 2-level (in-CTA + atomic) reduction.
+// ======================================================================================
+__global__ void __launch_bounds__(kRowThreads)
+colsum_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, long long cols,
+              long long ld, int lanes_c, long long rows_per_chunk) {
+  __shared__ float part[kRowThreads];
+  const int lc = threadIdx.x % lanes_c, lr = threadIdx.x / lanes_c, lanes_r = kRowThreads / lanes_c;
+  const long long c = (long long)blockIdx.x * lanes_c + lc;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = r0 + lr; r < r1; r += lanes_r) acc += __ldg(in + r * ld + c);
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (lr == 0 && c < cols) {
+    for (int j = 1; j < lanes_r; ++j) acc += part[j * lanes_c + lc];
+    atomicAdd(out + c, acc);
+  }
+}
+
+// ======================================================================================
+// Batched transpose through a padded shared tile.
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * R * C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = r0 + ty + j, c = c0 + tx;
+    if (r < R && c < C) tile[ty + j][tx] = __ldg(in + base + (long long)r * C + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j, r = r0 + tx;
+    if (r < R && c < C) out[base + (long long)c * R + r] = tile[tx][ty + j];
+  }
+}
+
+// ======================================================================================
+// Row softmax (in place), padded columns zeroed.
+// ======================================================================================
+__global__ void __launch_bounds__(kRowThreads)
+softmax_fwd_kernel(float* __restrict__ x, long long rows, int L, int ld) {
+  extern __shared__ float sm[];
+  float* row = sm;
+  float* red = sm + L;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float* xp = x + r * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      const float v = xp[c];
+      row[c] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      const float e = __expf(row[c] - mx);
+      row[c] = e;
+      s += e;
+    }
+    const float inv = 1.f / block_sum(s, red);
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) xp[c] = c < L ? row[c] * inv : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int L, int ld) {
+  extern __shared__ float sm[];
+  float* pr = sm;
+  float* dr = sm + L;
+  float* red = sm + 2 * L;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* pp = p + r * ld;
+    float* dpp = dp + r * ld;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      const float a = __ldg(pp + c), b = dpp[c];
+      pr[c] = a;
+      dr[c] = b;
+      s = fmaf(a, b, s);
+    }
+    s = block_sum(s, red);
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) dpp[c] = c < L ? pr[c] * (dr[c] - s) : 0.f;
+  }
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                float* __restrict__ dx, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[i] = __ldg(y + i) > 0.f ? __ldg(dy + i) : 0.f;
+}
+
+static int ensure_smem(const void* fn, size_t bytes, const char* name) {
+  if (bytes > (size_t)kMaxDynSmem) {
+    set_error("%s: row too long (%zu bytes of shared memory needed, %d available)", name, bytes,
+              kMaxDynSmem);
+    return DSTAG_ERR_SMEM;
+  }
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", name, bytes, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  return 0;
+}
+
+}  // namespace dstag
+
+using namespace dstag;
+
+extern "C" {
+
+int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
+                        const float* tab, int32_t tab_mod, const float* gamma, const float* beta,
+                        float eps, float* y, float* mean, float* rstd, int32_t rows, int32_t L,
+                        float drop_p, uint64_t seed, void* stream) {
+  DSTAG_CHECK_ARG(a && gamma && beta && y && mean && rstd, "dstag_layernorm_fwd: null pointer");
+  DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
+                  "dstag_layernorm_fwd: bad sizes rows=%d L=%d", rows, L);
+  DSTAG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dstag_layernorm_fwd: bad dropout p");
+  const size_t smem = (size_t)(L + 40) * sizeof(float);
+  int rc = ensure_smem((const void*)ln_fwd_kernel, smem, "dstag_layernorm_fwd");
+  if (rc) return rc;
+  const int grid = rows < kNumSMs * 8 ? rows : kNumSMs * 8;
+  ln_fwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
+      a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L, drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_layernorm_fwd");
+}
+
+int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
+                        int64_t a_sc, const float* tab, int32_t tab_mod, const float* gamma,
+                        const float* mean, const float* rstd, float* dpre, float* dgamma,
+                        float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
+                        void* stream) {
+  DSTAG_CHECK_ARG(dy && a && gamma && mean && rstd && dpre && dgamma && dbeta,
+                  "dstag_layernorm_bwd: null pointer");
+  DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
+                  "dstag_layernorm_bwd: bad sizes rows=%d L=%d", rows, L);
+  const size_t smem = (size_t)(4 * L + 40) * sizeof(float);
+  int rc = ensure_smem((const void*)ln_bwd_kernel, smem, "dstag_layernorm_bwd");
+  if (rc) return rc;
+  const int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
+  ln_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
+      dy, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, mean, rstd, dpre, dgamma, dbeta, rows, L,
+      drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd");
+}
+
+int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream) {
+  DSTAG_CHECK_ARG(in && out && rows > 0 && cols > 0 && ld >= cols, "dstag_colsum: bad arguments");
+  int lanes_c = 256;
+  while (lanes_c > 1 && lanes_c / 2 >= cols) lanes_c /= 2;   // smallest power of two >= cols, <= 256
+  const int lanes_r = kRowThreads / lanes_c;
+  const long long gx = (cols + lanes_c - 1) / lanes_c;
+  long long chunks = (kNumSMs * 4 + gx - 1) / gx;
+  const long long max_chunks = (rows + (long long)lanes_r * 4 - 1) / ((long long)lanes_r * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  const long long rpc = (rows + chunks - 1) / chunks;
+  const dim3 grid((unsigned)gx, (unsigned)((rows + rpc - 1) / rpc));
+  colsum_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(in, out, rows, cols, ld, lanes_c, rpc);
+  DSTAG_RETURN_LAUNCH("dstag_colsum");
+}
+
+int dstag_transpose(const float* in, float* out, int32_t batch, int32_t R, int32_t C, void* stream) {
+  DSTAG_CHECK_ARG(in && out && batch > 0 && R > 0 && C > 0, "dstag_transpose: bad arguments");
+  DSTAG_CHECK_ARG(batch <= 65535 && (R + 31) / 32 <= 65535, "dstag_transpose: grid too large");
+  const dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, R, C);
+  DSTAG_RETURN_LAUNCH("dstag_transpose");
+}
+
+int dstag_softmax_fwd(float* x, int64_t rows, int32_t L, int32_t ld, void* stream) {
+  DSTAG_CHECK_ARG(x && rows > 0 && L > 0 && ld >= L, "dstag_softmax_fwd: bad arguments");
+  const size_t smem = (size_t)(L + 40) * sizeof(float);
+  int rc = ensure_smem((const void*)softmax_fwd_kernel, smem, "dstag_softmax_fwd");
+  if (rc) return rc;
+  const int grid = (int)(rows < kNumSMs * 8 ? rows : kNumSMs * 8);
+  softmax_fwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(x, rows, L, ld);
+  DSTAG_RETURN_LAUNCH("dstag_softmax_fwd");
+}
+
+int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_t ld, void* stream) {
+  DSTAG_CHECK_ARG(p && dp && rows > 0 && L > 0 && ld >= L, "dstag_softmax_bwd: bad arguments");
+  const size_t smem = (size_t)(2 * L + 40) * sizeof(float);
+  int rc = ensure_smem((const void*)softmax_bwd_kernel, smem, "dstag_softmax_bwd");
+  if (rc) return rc;
+  const int grid = (int)(rows < kNumSMs * 8 ? rows : kNumSMs * 8);
+  softmax_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(p, dp, rows, L, ld);
+  DSTAG_RETURN_LAUNCH("dstag_softmax_bwd");
+}
+
+int dstag_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+  DSTAG_CHECK_ARG(y && dy && dx && n > 0, "dstag_relu_bwd: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  relu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+  DSTAG_RETURN_LAUNCH("dstag_relu_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// Block tail: GTU gate and the fused  dropout -> relu(tc [+ g]) -> relu(r + .) -> LayerNorm_C
+// kernel (model/DSTAGNN_my.py:194-196, 243-252).  All tensors are (X = B*N, C, T) with T
+// innermost; a CTA stages a group of nodes in shared memory with fully coalesced loads,
+// normalises every (node, t) column over the C channels out of shared memory (padded so
+// the column walk is bank-conflict free), and stores coalesced.
+#include "common.cuh"
+
+namespace dstag {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restrict__ out, long long total,
+                                    int C, int Tp, int out_ld, int out_off) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ct = C * Tp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long x = i / ct;
+    const int rem = (int)(i - x * ct);
+    const int c = rem / Tp, t = rem - c * Tp;
+    const float p = __ldg(u + x * 2 * ct + rem);
+    const float q = __ldg(u + x * 2 * ct + ct + rem);
+    out[(x * C + c) * out_ld + out_off + t] = tanhf(p) * sigmoidf_(q);
+  }
+}
+
+__global__ void gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
+                                    float* __restrict__ du, long long total, int C, int Tp, int out_ld,
+                                    int out_off) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ct = C * Tp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long x = i / ct;
+    const int rem = (int)(i - x * ct);
+    const int c = rem / Tp, t = rem - c * Tp;
+    const float p = __ldg(u + x * 2 * ct + rem);
+    const float q = __ldg(u + x * 2 * ct + ct + rem);
+    const float d = __ldg(dout + (x * C + c) * out_ld + out_off + t);
+    const float th = tanhf(p), sg = sigmoidf_(q);
+    du[x * 2 * ct + rem] = d * sg * (1.f - th * th);
+    du[x * 2 * ct + ct + rem] = d * th * sg * (1.f - sg);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tail forward
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tail_fwd_kernel(const float* __restrict__ tc, const float* __restrict__ g, const float* __restrict__ r,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, long long X,
+                int C, int T, int npc, float drop_p, unsigned long long seed) {
+  extern __shared__ float sm[];
+  const int ct = C * T, nst = ct + T;   // padded node stride: column walks hit distinct banks
+  float* V = sm;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float invC = 1.f / (float)C;
+  const long long nchunks = (X + npc - 1) / npc;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long x0 = ch * npc;
+    const int nn = (int)min((long long)npc, X - x0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nn * ct; i += blockDim.x) {
+      const int xl = i / ct, rem = i - xl * ct;
+      const long long e = (x0 + xl) * ct + rem;
+      float a = __ldg(tc + e);
+      if (drop_p > 0.f) a *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
+      if (g) a += __ldg(g + e);
+      a = fmaxf(a, 0.f);
+      V[xl * nst + rem] = fmaxf(__ldg(r + e) + a, 0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nn * T; i += blockDim.x) {
+      const int xl = i / T, t = i - xl * T;
+      float* col = V + xl * nst + t;
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += col[c * T];
+      const float mu = s * invC;
+      float q = 0.f;
+      for (int c = 0; c < C; ++c) { const float d = col[c * T] - mu; q = fmaf(d, d, q); }
+      const float rs = rsqrtf(q * invC + eps);
+      for (int c = 0; c < C; ++c) col[c * T] = (col[c * T] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
+      mean[(x0 + xl) * T + t] = mu;
+      rstd[(x0 + xl) * T + t] = rs;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nn * ct; i += blockDim.x) {
+      const int xl = i / ct, rem = i - xl * ct;
+      out[(x0 + xl) * ct + rem] = V[xl * nst + rem];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tail backward
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ tc, const float* __restrict__ g,
+                const float* __restrict__ r, const float* __restrict__ gamma,
+                const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dtc,
+                float* __restrict__ dg, float* __restrict__ dr, float* __restrict__ dgamma,
+                float* __restrict__ dbeta, long long X, int C, int T, int npc, float drop_p,
+                unsigned long long seed) {
+  extern __shared__ float sm[];
+  const int ct = C * T, nst = ct + T;
+  float* V = sm;                       // v, then unused
+  float* D = V + (size_t)npc * nst;    // dout, then dv
+  float* Fl = D + (size_t)npc * nst;   // flags: bit0 = (s1 > 0), bit1 = (s2 > 0)
+  float* Ag = Fl + (size_t)npc * nst;  // C floats: dgamma partial
+  float* Ab = Ag + C;                  // C floats: dbeta partial
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float invC = 1.f / (float)C;
+  const int lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { Ag[c] = 0.f; Ab[c] = 0.f; }
+  const long long nchunks = (X + npc - 1) / npc;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long x0 = ch * npc;
+    const int nn = (int)min((long long)npc, X - x0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nn * ct; i += blockDim.x) {
+      const int xl = i / ct, rem = i - xl * ct;
+      const long long e = (x0 + xl) * ct + rem;
+      float a = __ldg(tc + e);
+      if (drop_p > 0.f) a *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
+      if (g) a += __ldg(g + e);
+      const float s2 = __ldg(r + e) + fmaxf(a, 0.f);
+      V[xl * nst + rem] = fmaxf(s2, 0.f);
+      D[xl * nst + rem] = __ldg(dout + e);
+      Fl[xl * nst + rem] = (a > 0.f ? 1.f : 0.f) + (s2 > 0.f ? 2.f : 0.f);
+    }
+    __syncthreads();
+    const int ncol = nn * T;
+    const int ncol_pad = (ncol + 31) & ~31;   // whole warps take part in the shuffles
+    for (int i = threadIdx.x; i < ncol_pad; i += blockDim.x) {
+      const bool act = i < ncol;
+      const int xl = act ? i / T : 0, t = act ? i - xl * T : 0;
+      float* vcol = V + xl * nst + t;
+      float* dcol = D + xl * nst + t;
+      const float mu = act ? __ldg(mean + (x0 + xl) * T + t) : 0.f;
+      const float rs = act ? __ldg(rstd + (x0 + xl) * T + t) : 0.f;
+      float s1 = 0.f, s2 = 0.f;
+      if (act)
+        for (int c = 0; c < C; ++c) {
+          const float xh = (vcol[c * T] - mu) * rs;
+          const float gy = dcol[c * T] * __ldg(gamma + c);
+          s1 += gy;
+          s2 = fmaf(gy, xh, s2);
+        }
+      const float m1 = s1 * invC, m2 = s2 * invC;
+      for (int c = 0; c < C; ++c) {
+        float pa = 0.f, pb = 0.f;
+        if (act) {
+          const float xh = (vcol[c * T] - mu) * rs;
+          const float d = dcol[c * T];
+          dcol[c * T] = rs * (d * __ldg(gamma + c) - m1 - xh * m2);
+          pa = d * xh;
+          pb = d;
+        }
+        pa = warp_sum(pa);
+        pb = warp_sum(pb);
+        if (lane == 0) { atomicAdd(Ag + c, pa); atomicAdd(Ab + c, pb); }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nn * ct; i += blockDim.x) {
+      const int xl = i / ct, rem = i - xl * ct;
+      const long long e = (x0 + xl) * ct + rem;
+      const int fl = (int)Fl[xl * nst + rem];
+      const float ds2 = (fl & 2) ? D[xl * nst + rem] : 0.f;
+      const float ds1 = (fl & 1) ? ds2 : 0.f;
+      dr[e] = ds2;
+      if (dg) dg[e] = ds1;
+      float o = ds1;
+      if (drop_p > 0.f) o *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
+      dtc[e] = o;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgamma + c, Ag[c]);
+    atomicAdd(dbeta + c, Ab[c]);
+  }
+}
+
+static int pick_npc(size_t per_node_bytes, size_t extra, size_t budget, int cap) {
+  long long n = ((long long)budget - (long long)extra) / (long long)per_node_bytes;
+  if (n > cap) n = cap;
+  return (int)n;
+}
+
+static int opt_in_smem(const void* fn, size_t bytes, const char* name) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute failed: %s", name, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  return 0;
+}
+
+}  // namespace dstag
+
+using namespace dstag;
+
+extern "C" {
+
+int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t Tp, int32_t out_ld,
+                       int32_t out_off, void* stream) {
+  DSTAG_CHECK_ARG(u && out && X > 0 && C > 0 && Tp > 0 && out_off >= 0 && out_off + Tp <= out_ld,
+                  "dstag_gtu_gate_fwd: bad arguments");
+  const long long total = (long long)X * C * Tp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  gtu_gate_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, out, total, C, Tp, out_ld,
+                                                                          out_off);
+  DSTAG_RETURN_LAUNCH("dstag_gtu_gate_fwd");
+}
+
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* du, int64_t X, int32_t C, int32_t Tp,
+                       int32_t out_ld, int32_t out_off, void* stream) {
+  DSTAG_CHECK_ARG(u && dout && du && X > 0 && C > 0 && Tp > 0 && out_off >= 0 && out_off + Tp <= out_ld,
+                  "dstag_gtu_gate_bwd: bad arguments");
+  const long long total = (long long)X * C * Tp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, du, total, C, Tp,
+                                                                          out_ld, out_off);
+  DSTAG_RETURN_LAUNCH("dstag_gtu_gate_bwd");
+}
+
+int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
+                   const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
+                   int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream) {
+  DSTAG_CHECK_ARG(tc && r && gamma && beta && out && mean && rstd, "dstag_tail_fwd: null pointer");
+  DSTAG_CHECK_ARG(X > 0 && C > 0 && T > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_fwd: bad sizes");
+  const size_t per_node = (size_t)(C + 1) * T * sizeof(float);
+  const int npc = pick_npc(per_node, 0, 96 * 1024, 16);
+  if (npc < 1) { set_error("dstag_tail_fwd: C*T too large for shared memory"); return DSTAG_ERR_SMEM; }
+  const size_t smem = per_node * npc;
+  int rc = opt_in_smem((const void*)tail_fwd_kernel, smem, "dstag_tail_fwd");
+  if (rc) return rc;
+  long long chunks = (X + npc - 1) / npc;
+  const int grid = (int)(chunks < kNumSMs * 4 ? chunks : kNumSMs * 4);
+  tail_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(tc, g, r, gamma, beta, eps, out, mean, rstd,
+                                                            X, C, T, npc, drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_tail_fwd");
+}
+
+int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
+                   const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
+                   float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
+                   float drop_p, uint64_t seed, void* stream) {
+  DSTAG_CHECK_ARG(dout && tc && r && gamma && mean && rstd && dtc && dr && dgamma && dbeta,
+                  "dstag_tail_bwd: null pointer");
+  DSTAG_CHECK_ARG((g == nullptr) == (dg == nullptr), "dstag_tail_bwd: g and dg must both be given or both be null");
+  DSTAG_CHECK_ARG(X > 0 && C > 0 && T > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_bwd: bad sizes");
+  const size_t per_node = (size_t)3 * (C + 1) * T * sizeof(float);
+  const size_t extra = (size_t)2 * C * sizeof(float);
+  const int npc = pick_npc(per_node, extra, 160 * 1024, 16);
+  if (npc < 1) { set_error("dstag_tail_bwd: C*T too large for shared memory"); return DSTAG_ERR_SMEM; }
+  const size_t smem = per_node * npc + extra;
+  int rc = opt_in_smem((const void*)tail_bwd_kernel, smem, "dstag_tail_bwd");
+  if (rc) return rc;
+  long long chunks = (X + npc - 1) / npc;
+  const int grid = (int)(chunks < kNumSMs * 2 ? chunks : kNumSMs * 2);
+  tail_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dout, tc, g, r, gamma, mean, rstd, dtc, dg, dr,
+                                                            dgamma, dbeta, X, C, T, npc, drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_tail_bwd");
+}
+
+}  // extern "C"

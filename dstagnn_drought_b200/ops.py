@@ -1,0 +1,357 @@
+"""Hand-written autograd Functions over the C-ABI kernels (include/dstagnn_b200.h).
+
+Every Function's forward AND backward run only kernels of libdstagnn_b200.so
+(plus torch allocation / views).  Citations are to the reference's
+model/DSTAGNN_my.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACC_ATOMIC
+from .contraction import _check, colsum, contract_raw
+
+_VP = C.c_void_p
+
+
+def _stream(t: torch.Tensor):
+    return _lib.stream_ptr(t)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------
+# dropout seeds: one fresh 64-bit Philox key per dropout site per forward call, derived
+# from torch's seed so that torch.manual_seed() makes runs reproducible.
+# ----------------------------------------------------------------------------------------
+_seed_counter = 0
+
+
+def next_seed() -> int:
+    global _seed_counter
+    _seed_counter += 1
+    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+
+
+# ----------------------------------------------------------------------------------------
+# transpose
+# ----------------------------------------------------------------------------------------
+def transpose_raw(x3: torch.Tensor) -> torch.Tensor:
+    """(b, R, C) contiguous -> (b, C, R) contiguous."""
+    lib = _lib.load()
+    _check(x3, "transpose input")
+    assert x3.is_contiguous() and x3.dim() == 3
+    b, R, Cc = x3.shape
+    out = torch.empty((b, Cc, R), device=x3.device, dtype=torch.float32)
+    _lib.check(lib.dstag_transpose(x3.data_ptr(), out.data_ptr(), b, R, Cc, _stream(x3)), "dstag_transpose")
+    return out
+
+
+class Transpose(torch.autograd.Function):
+    """x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 materialised ((B,N,FT) -> (B,FT,N))."""
+
+    @staticmethod
+    def forward(ctx, x3):
+        return transpose_raw(x3)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return transpose_raw(dy.contiguous())
+
+
+# ----------------------------------------------------------------------------------------
+# LayerNorm(a + table/residual) [+ dropout]
+# ----------------------------------------------------------------------------------------
+class LayerNormAdd(torch.autograd.Function):
+    """y = dropout(LN(a + tab[row % tab_mod])) -- Embedding.forward (lines 172-182) for
+    both embedding types, the residual LayerNorm of MultiHeadAttention (line 100) and the
+    dropout of line 234.
+
+    ``a`` is either a contiguous (rows, L) matrix (gather=False) or the block input
+    x (B, N, F*T) read as rows (b, f*t) x columns n (gather=True; EmbedT path).
+    ``tab`` is (tab_mod, L): an embedding table, or a full (rows, L) residual.
+    """
+
+    @staticmethod
+    def forward(ctx, a, tab, gamma, beta, gather, drop_p, seed):
+        lib = _lib.load()
+        for t, n in ((a, "a"), (tab, "tab"), (gamma, "gamma"), (beta, "beta")):
+            _check(t, n)
+        a = a.contiguous()
+        tab = tab.contiguous()
+        if gather:
+            Bz, N, FT = a.shape
+            rows, L = Bz * FT, N
+            lay = (N * FT, 1, FT, FT)            # a_s0, a_s1, a_div, a_sc
+        else:
+            rows, L = a.shape
+            lay = (L, 0, 1, 1)
+        tab_mod = tab.numel() // L
+        assert tab.numel() == tab_mod * L and rows % tab_mod == 0 and gamma.numel() == L
+        y = torch.empty((rows, L), device=a.device, dtype=torch.float32)
+        mean = torch.empty(rows, device=a.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=a.device, dtype=torch.float32)
+        _lib.check(lib.dstag_layernorm_fwd(a.data_ptr(), lay[0], lay[1], lay[2], lay[3], tab.data_ptr(),
+                                           tab_mod, gamma.data_ptr(), beta.data_ptr(), 1e-5, y.data_ptr(),
+                                           mean.data_ptr(), rstd.data_ptr(), rows, L, float(drop_p),
+                                           int(seed), _stream(a)), "dstag_layernorm_fwd")
+        ctx.save_for_backward(a, tab, gamma, mean, rstd)
+        ctx.meta = (lay, tab_mod, rows, L, gather, float(drop_p), int(seed))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        a, tab, gamma, mean, rstd = ctx.saved_tensors
+        lay, tab_mod, rows, L, gather, drop_p, seed = ctx.meta
+        dy = dy.contiguous()
+        dpre = torch.empty((rows, L), device=a.device, dtype=torch.float32)
+        dgamma = torch.zeros(L, device=a.device, dtype=torch.float32)
+        dbeta = torch.zeros(L, device=a.device, dtype=torch.float32)
+        _lib.check(lib.dstag_layernorm_bwd(dy.data_ptr(), a.data_ptr(), lay[0], lay[1], lay[2], lay[3],
+                                           tab.data_ptr(), tab_mod, gamma.data_ptr(), mean.data_ptr(),
+                                           rstd.data_ptr(), dpre.data_ptr(), dgamma.data_ptr(),
+                                           dbeta.data_ptr(), rows, L, drop_p, seed, _stream(a)),
+                   "dstag_layernorm_bwd")
+        da = dtab = None
+        if ctx.needs_input_grad[0]:
+            if gather:
+                Bz, N, FT = a.shape
+                da = transpose_raw(dpre.view(Bz, FT, N))
+            else:
+                da = dpre
+        if ctx.needs_input_grad[1]:
+            if tab_mod == rows:
+                dtab = dpre.view(tab.shape)
+            else:
+                dtab = colsum(dpre, rows // tab_mod, tab_mod * L).view(tab.shape)
+        return da, dtab, dgamma, dbeta, None, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# temporal attention core
+# ----------------------------------------------------------------------------------------
+class TemporalAttention(torch.autograd.Function):
+    """ScaledDotProductAttention (lines 30-42): returns (context (B,F,T,H*dk), logits (B,F,H,T,T))."""
+
+    @staticmethod
+    def forward(ctx, qkv, res, B, F, H, T, dk):
+        lib = _lib.load()
+        _check(qkv, "qkv")
+        qkv = qkv.contiguous()
+        res_F = 0
+        if res is not None:
+            _check(res, "res_att")
+            res = res.contiguous()
+            res_F = res.shape[1]
+            assert res.shape == (B, res_F, H, T, T) and res_F in (1, F)
+        scores = torch.empty((B, F, H, T, T), device=qkv.device, dtype=torch.float32)
+        out = torch.empty((B, F, T, H * dk), device=qkv.device, dtype=torch.float32)
+        _lib.check(lib.dstag_tattn_fwd(qkv.data_ptr(), _p(res), res_F, scores.data_ptr(), out.data_ptr(),
+                                       B, F, H, T, dk, _stream(qkv)), "dstag_tattn_fwd")
+        ctx.save_for_backward(qkv, scores)
+        ctx.meta = (B, F, H, T, dk, res_F)
+        ctx.set_materialize_grads(False)
+        return out, scores
+
+    @staticmethod
+    def backward(ctx, dctx, dscores):
+        lib = _lib.load()
+        qkv, scores = ctx.saved_tensors
+        B, F, H, T, dk, res_F = ctx.meta
+        if dctx is None:
+            dctx = torch.zeros((B, F, T, H * dk), device=qkv.device, dtype=torch.float32)
+        dctx = dctx.contiguous()
+        if dscores is not None:
+            dscores = dscores.contiguous()
+        dqkv = torch.empty_like(qkv)
+        ds = torch.empty_like(scores)
+        _lib.check(lib.dstag_tattn_bwd(qkv.data_ptr(), scores.data_ptr(), dctx.data_ptr(), _p(dscores),
+                                       dqkv.data_ptr(), ds.data_ptr(), B, F, H, T, dk, _stream(qkv)),
+                   "dstag_tattn_bwd")
+        dres = None
+        if res_F and ctx.needs_input_grad[1]:
+            # broadcast over F in the forward => reduce over F here (tiny: B*F*H*T*T floats)
+            dres = ds if res_F == F else sum_over_f(ds, B, F)
+        return dqkv, dres, None, None, None, None, None
+
+
+def sum_over_f(ds: torch.Tensor, B: int, F: int) -> torch.Tensor:
+    """(B,F,H,T,T) -> (B,1,H,T,T): gradient of a res_att that was broadcast over F."""
+    ones = torch.ones(F, device=ds.device, dtype=torch.float32)
+    out = contract_raw("bfi,f->bi", ds.view(B, F, -1), ones, split_k=1)
+    return out.view(B, 1, *ds.shape[2:])
+
+
+# ----------------------------------------------------------------------------------------
+# spatial attention -> softmax -> Chebyshev contraction
+# ----------------------------------------------------------------------------------------
+def _pad_ld(n: int) -> int:
+    return (n + 31) // 32 * 32      # 128-byte rows: aligned vector / TMA access to the N x N maps
+
+
+class SpatialChebConv(torch.autograd.Function):
+    """SMultiHeadAttention scores (lines 62-66, 19) + the attention-masked Chebyshev product
+    of cheb_conv_withSAt (lines 126-130), per Chebyshev order k:
+
+        P_k[b, j, i] = softmax_i( Qs[b,i,k,:].Ks[b,j,k,:] / sqrt(dk) + (adj_pa . mask_k)[i, j] )
+        Z[k, b, j, :] = sum_i T_k[i, j] * P_k[b, j, i] * X[b, i, :]
+
+    The maps are kept TRANSPOSED (row = output node j, contiguous over i) so the reference's
+    dim=1 softmax (line 127) is a contiguous row softmax and the contraction reads K-major
+    rows.  It is computed once per (b,k), not once per time step as in the reference's loop.
+    qk: (B,N,2,K,dk) packed [W_Q | W_K] projections; biasT, tkT: (K,N,ld) transposed, padded.
+    """
+
+    @staticmethod
+    def forward(ctx, qk, biasT, tkT, x3):
+        lib = _lib.load()
+        for t, n in ((qk, "qk"), (biasT, "biasT"), (tkT, "tkT"), (x3, "x")):
+            _check(t, n)
+        qk, x3 = qk.contiguous(), x3.contiguous()
+        B, N, _, K, dk = qk.shape
+        ld = biasT.shape[-1]
+        FT = x3.shape[-1]
+        Qs, Ks = qk[:, :, 0], qk[:, :, 1]                      # (B,N,K,dk) views
+        P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
+        contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
+                     c_add=("kji", biasT[..., :N]))
+        _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+        Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
+        contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]))
+        ctx.save_for_backward(qk, P, tkT, x3)
+        return Z
+
+    @staticmethod
+    def backward(ctx, dZ):
+        lib = _lib.load()
+        qk, P, tkT, x3 = ctx.saved_tensors
+        B, N, _, K, dk = qk.shape
+        ld = P.shape[-1]
+        dZ = dZ.contiguous()
+        Qs, Ks = qk[:, :, 0], qk[:, :, 1]
+        Pv, Tv = P[..., :N], tkT[..., :N]
+        dx = None
+        if ctx.needs_input_grad[3]:
+            dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv))
+        dS = torch.empty_like(P)
+        contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], c_mul=("kji", Tv))
+        _lib.check(lib.dstag_softmax_bwd(P.data_ptr(), dS.data_ptr(), B * K * N, N, ld, _stream(P)),
+                   "dstag_softmax_bwd")
+        dSv = dS[..., :N]
+        dqk = torch.empty_like(qk)
+        alpha = 1.0 / math.sqrt(dk)
+        contract_raw("bkji,bjkd->bikd", dSv, Ks, out=dqk[:, :, 0], alpha=alpha)
+        contract_raw("bkji,bikd->bjkd", dSv, Qs, out=dqk[:, :, 1], alpha=alpha)
+        dbias = None
+        if ctx.needs_input_grad[1]:
+            dbias = colsum(dS, B, K * N * ld).view(K, N, ld)
+        return dqk, dbias, None, dx
+
+
+# ----------------------------------------------------------------------------------------
+# GTU 3/5/7: Conv2d(C -> 2C, (1,k)) over time + tanh * sigmoid gate, concatenated over time
+# ----------------------------------------------------------------------------------------
+class GtuStack(torch.autograd.Function):
+    """gtu3/gtu5/gtu7 + torch.cat (lines 192-197, 238-242).  g: (X, C, T) -> (X, C, 3T-12).
+
+    The convolution is a contraction over an *unfolded view* of g (window index folded into
+    the strides; no im2col buffer); its input gradient scatters back through the same view
+    with atomic accumulation."""
+
+    @staticmethod
+    def forward(ctx, g, w3, b3, w5, b5, w7, b7):
+        lib = _lib.load()
+        _check(g, "g")
+        g = g.contiguous()
+        X, Cc, T = g.shape
+        widths = [T - ks + 1 for ks in (3, 5, 7)]
+        total = sum(widths)
+        out = torch.empty((X, Cc, total), device=g.device, dtype=torch.float32)
+        us, off = [], 0
+        for ks, w, b, tp in zip((3, 5, 7), (w3, w5, w7), (b3, b5, b7), widths):
+            gu = g.unfold(2, ks, 1)                                    # (X, C, T', ks) view
+            u = contract_raw("xctd,ocd->xot", gu, w.view(2 * Cc, Cc, ks), c_add=("o", b))
+            _lib.check(lib.dstag_gtu_gate_fwd(u.data_ptr(), out.data_ptr(), X, Cc, tp, total, off,
+                                              _stream(g)), "dstag_gtu_gate_fwd")
+            us.append(u)
+            off += tp
+        ctx.save_for_backward(g, w3, w5, w7, *us)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        g, w3, w5, w7, u3, u5, u7 = ctx.saved_tensors
+        X, Cc, T = g.shape
+        dout = dout.contiguous()
+        total = dout.shape[-1]
+        dg = torch.zeros_like(g) if ctx.needs_input_grad[0] else None
+        grads, off = [], 0
+        for ks, w, u in zip((3, 5, 7), (w3, w5, w7), (u3, u5, u7)):
+            tp = T - ks + 1
+            du = torch.empty_like(u)
+            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), du.data_ptr(), X, Cc, tp,
+                                              total, off, _stream(g)), "dstag_gtu_gate_bwd")
+            gu = g.unfold(2, ks, 1)
+            dw = contract_raw("xot,xctd->ocd", du, gu).view(w.shape)
+            db = colsum(du, X, 2 * Cc * tp).view(2 * Cc, tp).sum(dim=1)
+            if dg is not None:
+                contract_raw("xot,ocd->xctd", du, w.view(2 * Cc, Cc, ks), out=dg.unfold(2, ks, 1),
+                             accumulate=ACC_ATOMIC, split_k=1)
+            grads += [dw, db]
+            off += tp
+        return (dg, *grads)
+
+
+# ----------------------------------------------------------------------------------------
+# block tail
+# ----------------------------------------------------------------------------------------
+class BlockTail(torch.autograd.Function):
+    """out = LN_C(relu(r + relu(dropout(tc) [+ g])))  (lines 243-252); all (X, C, T)."""
+
+    @staticmethod
+    def forward(ctx, tc, g, r, gamma, beta, drop_p, seed):
+        lib = _lib.load()
+        for t, n in ((tc, "tc"), (r, "r"), (gamma, "gamma"), (beta, "beta")):
+            _check(t, n)
+        tc, r = tc.contiguous(), r.contiguous()
+        if g is not None:
+            g = g.contiguous()
+        X, Cc, T = tc.shape
+        out = torch.empty_like(tc)
+        mean = torch.empty((X, T), device=tc.device, dtype=torch.float32)
+        rstd = torch.empty((X, T), device=tc.device, dtype=torch.float32)
+        _lib.check(lib.dstag_tail_fwd(tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                      1e-5, out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), X, Cc, T,
+                                      float(drop_p), int(seed), _stream(tc)), "dstag_tail_fwd")
+        ctx.save_for_backward(tc, g, r, gamma, mean, rstd)
+        ctx.meta = (float(drop_p), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        tc, g, r, gamma, mean, rstd = ctx.saved_tensors
+        drop_p, seed = ctx.meta
+        X, Cc, T = tc.shape
+        dout = dout.contiguous()
+        dtc = torch.empty_like(tc)
+        dr = torch.empty_like(tc)
+        dg = torch.empty_like(tc) if g is not None else None
+        dgamma = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
+        dbeta = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
+        _lib.check(lib.dstag_tail_bwd(dout.data_ptr(), tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(),
+                                      mean.data_ptr(), rstd.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
+                                      dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
+                                      _stream(tc)), "dstag_tail_bwd")
+        return dtc, dg, dr, dgamma, dbeta, None, None

@@ -1,0 +1,175 @@
+/*
+ * dstagnn_b200.h -- C ABI of libdstagnn_b200.so (hand-written sm_100a kernels for the
+ * DSTAGNN block forward/backward path).
+ *
+ * The reference (Ghoul-tn/DSTAGNN_Drought) has no FFI: every operation of the hot path
+ * is a stock PyTorch call inside model/DSTAGNN_my.py.  Each entry point below therefore
+ * cites the reference lines whose arithmetic it replaces.  Conventions:
+ *   - all tensors are fp32 device pointers owned by the caller, borrowed for the
+ *     duration of the enqueue; nothing is allocated inside the library;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; work is stream-ordered and
+ *     the calls are re-entrant per stream (CUDA-graph capturable);
+ *   - return value 0 = enqueued, negative = DSTAG_ERR_* (no kernel launched),
+ *     positive = cudaError_t of the failed launch.
+ *   - there is no CPU path: every function requires device pointers.
+ */
+#ifndef DSTAGNN_B200_H
+#define DSTAGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSTAG_ERR_BAD_ARG (-1)
+#define DSTAG_ERR_UNSUPPORTED (-2)
+#define DSTAG_ERR_SMEM (-3)
+
+/* ABI version, bumped whenever a signature below changes. */
+int dstag_abi_version(void);
+/* Last error text of the calling thread ("" if none). */
+const char* dstag_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset
+ * (process-wide counter; used by bench.py for "gpu_launches"). */
+int64_t dstag_launch_count(void);
+void dstag_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Strided tensor contraction  C[b,m,n] (+)= alpha * sum_k (A*Amul)[b,m,k] * B[b,k,n]
+ *                             then  (+ Cadd) (* Cmul) (relu)
+ *
+ * Each logical index (batch, m, n, k) may be the flattening of up to TWO tensor
+ * dimensions: idx -> (idx / d1) * s0 + (idx % d1) * s1  (element strides; d1 == 1 means a
+ * single dimension).  This one primitive covers every dense product of the block:
+ *   TAt W_Q/W_K/W_V/fc       model/DSTAGNN_my.py:92-99     (x permuted view, no copy)
+ *   pre_conv, final_conv     model/DSTAGNN_my.py:232,278   (Conv2d == per-node Linear)
+ *   SAt W_Q/W_K, Q K^T       model/DSTAGNN_my.py:62-63,19
+ *   cheb: (T_k . A)^T x      model/DSTAGNN_my.py:128-131   (Amul = T_k fused into operand load)
+ *   Theta_k mix, fcmy        model/DSTAGNN_my.py:131,243
+ *   GTU Conv2d(1,k)          model/DSTAGNN_my.py:193       (im2col folded into the strides)
+ * and, by swapping operand roles, all of their input/weight gradients.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t s0;   /* stride of the outer sub-index (elements) */
+  int64_t s1;   /* stride of the inner sub-index (elements); ignored when d1 == 1 */
+  int32_t d1;   /* extent of the inner sub-index; 1 = not split */
+  int32_t pad_;
+} dstag_axis_t;
+
+typedef struct {
+  const void* ptr;       /* fp32 device pointer; NULL = operand absent (Amul/Cmul/Cadd) */
+  dstag_axis_t batch;
+  dstag_axis_t row;      /* A: m   B: k   C/Cmul/Cadd: m   Amul: m */
+  dstag_axis_t col;      /* A: k   B: n   C/Cmul/Cadd: n   Amul: k */
+} dstag_operand_t;
+
+enum { DSTAG_ACC_STORE = 0, DSTAG_ACC_ADD = 1, DSTAG_ACC_ATOMIC = 2 };
+enum {
+  DSTAG_PREC_FP32 = 0,     /* fp32 FMA on CUDA cores (exact fp32 semantics) */
+  DSTAG_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-pass split: fp32-grade accuracy */
+  DSTAG_PREC_TF32 = 2      /* tcgen05 kind::tf32 single pass (reported separately) */
+};
+
+typedef struct {
+  int32_t M, N, K, batch;
+  dstag_operand_t A, B, C, Amul, Cmul, Cadd;
+  float alpha;
+  int32_t relu;          /* apply max(.,0) last */
+  int32_t accumulate;    /* DSTAG_ACC_*; ATOMIC required when split_k > 1 or C aliases over batch */
+  int32_t split_k;       /* >= 1 */
+  int32_t precision;     /* DSTAG_PREC_* */
+  int32_t pad_;
+} dstag_gemm_t;
+
+int dstag_gemm(const dstag_gemm_t* g, void* stream);
+/* 1 if this shape/precision is served by the tcgen05 engine, 0 if by the SIMT kernel. */
+int dstag_gemm_uses_tensor_cores(const dstag_gemm_t* g);
+
+/* ------------------------------------------------------------------------------------
+ * Row LayerNorm with fused pre-add:  y[r,:] = LN(a[r,:] + tab[r % tab_mod,:]) * gamma + beta
+ * followed by optional inverted dropout (Philox, keyed by seed; p == 0 disables).
+ *   a is gathered as a[(r / a_div) * a_s0 + (r % a_div) * a_s1 + c * a_sc].
+ * Replaces Embedding.forward (model/DSTAGNN_my.py:172-182: pos_embed + LayerNorm, both
+ * 'T' and 'S' types, tab = the embedding table), the residual LayerNorm of
+ * MultiHeadAttention (line 100: tab = residual, tab_mod = rows) and the dropout of
+ * line 234.  mean/rstd (rows each) are saved for the backward.
+ * ---------------------------------------------------------------------------------- */
+int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
+                        const float* tab, int32_t tab_mod, const float* gamma, const float* beta,
+                        float eps, float* y, float* mean, float* rstd, int32_t rows, int32_t L,
+                        float drop_p, uint64_t seed, void* stream);
+/* dpre[r,:] = d(loss)/d(a + tab) (contiguous rows x L); dgamma/dbeta are ACCUMULATED
+ * (atomicAdd) into caller-zeroed buffers. */
+int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
+                        int64_t a_sc, const float* tab, int32_t tab_mod, const float* gamma,
+                        const float* mean, const float* rstd, float* dpre, float* dgamma,
+                        float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
+                        void* stream);
+
+/* out[c] (+)= sum_r in[r * ld + c], r < rows, c < cols.  Bias / embedding-table /
+ * mask gradients (autograd of model/DSTAGNN_my.py:127,175,180,193,207,221).  `out` must be
+ * zeroed by the caller (partial sums are combined with atomicAdd). */
+int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);
+
+/* out[b, c, r] = in[b, r, c]  (x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 made contiguous,
+ * and the transposes of the N x N mask / Chebyshev matrices). */
+int dstag_transpose(const float* in, float* out, int32_t batch, int32_t R, int32_t C, void* stream);
+
+/* In-place row softmax over L entries of rows with leading dimension ld; entries
+ * [L, ld) are set to 0.  F.softmax(..., dim=1) of model/DSTAGNN_my.py:127 on the
+ * transposed map layout (row = output node j, column = i). */
+int dstag_softmax_fwd(float* x, int64_t rows, int32_t L, int32_t ld, void* stream);
+/* In place on dp: dp <- p * (dp - sum(p * dp)). */
+int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_t ld, void* stream);
+
+/* dx = dy * (y > 0)  (backward of the ReLUs at model/DSTAGNN_my.py:133,245-247). */
+int dstag_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Temporal attention core (ScaledDotProductAttention, model/DSTAGNN_my.py:30-42), one
+ * CTA per (b, f, h):  S = Q K^T / sqrt(dk) + res ; P = softmax over the QUERY index
+ * (dim=3 of (B,F,H,Tq,Tk)) ; ctx = P V.
+ *   qkv    (B,F,T,3,H,dk)   packed projections
+ *   res    (B,res_F,H,T,T)  res_F in {0 (absent), 1 (broadcast over F), F}
+ *   scores (B,F,H,T,T)      returned logits (line 42)
+ *   ctx    (B,F,T,H,dk)     == context.transpose(2,3).reshape(...) of line 98
+ * ---------------------------------------------------------------------------------- */
+int dstag_tattn_fwd(const float* qkv, const float* res, int32_t res_F, float* scores, float* ctx,
+                    int32_t B, int32_t F, int32_t H, int32_t T, int32_t dk, void* stream);
+/* dscores_ext (nullable): gradient arriving through the returned logits (next block's
+ * res_att).  dscores_out (B,F,H,T,T): total gradient w.r.t. the logits (= grad of res). */
+int dstag_tattn_bwd(const float* qkv, const float* scores, const float* dctx,
+                    const float* dscores_ext, float* dqkv, float* dscores_out, int32_t B, int32_t F,
+                    int32_t H, int32_t T, int32_t dk, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GTU gate (model/DSTAGNN_my.py:194-196): out[x, c, off + t] = tanh(u[x, c, t]) * sigmoid(u[x, C + c, t])
+ *   u (X, 2C, Tp) contiguous; out rows have leading dimension out_ld (the concatenated
+ *   time axis 3T-12 of line 242).
+ * ---------------------------------------------------------------------------------- */
+int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t Tp, int32_t out_ld,
+                       int32_t out_off, void* stream);
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* du, int64_t X, int32_t C, int32_t Tp,
+                       int32_t out_ld, int32_t out_off, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Block tail (model/DSTAGNN_my.py:243-252):
+ *   tc' = dropout(tc) ; tco = relu(tc' [+ g]) ; out = LN_C(relu(r + tco)) over the channel axis
+ *   tc, g, r, out: (X, C, T) with X = B*N ; g == NULL in block 0 (line 245).
+ *   mean/rstd: (X, T) saved statistics.
+ * ---------------------------------------------------------------------------------- */
+int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
+                   const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
+                   int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
+/* dtc, dr always written; dg written when g != NULL (dg == d tco).  dgamma/dbeta accumulated
+ * atomically into caller-zeroed buffers. */
+int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
+                   const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
+                   float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
+                   float drop_p, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSTAGNN_B200_H */

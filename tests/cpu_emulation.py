@@ -1,0 +1,266 @@
+"""TEST INFRASTRUCTURE ONLY: a numpy emulation of the C ABI in include/dstagnn_b200.h.
+
+It lets the CPU test-suite drive the *host-side wiring* (einsum specs, argument order of
+every ctypes call, the hand-written backward formulas, the res_att gradient chain) end to end
+against the golden fixtures without a GPU.  It is installed by monkeypatching
+``dstagnn_drought_b200._lib.load`` inside a pytest fixture; the product package never imports
+this file and has no CPU path of its own.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+
+def _arr(ptr, n):
+    return np.ctypeslib.as_array((C.c_float * int(n)).from_address(int(ptr)))
+
+
+def _axoff(ax, idx):
+    idx = np.asarray(idx, dtype=np.int64)
+    if ax.d1 == 1:
+        return idx * ax.s0
+    return (idx // ax.d1) * ax.s0 + (idx % ax.d1) * ax.s1
+
+
+def _offsets(op, nb, nr, nc):
+    return (_axoff(op.batch, np.arange(nb))[:, None, None] + _axoff(op.row, np.arange(nr))[None, :, None]
+            + _axoff(op.col, np.arange(nc))[None, None, :])
+
+
+def _read(op, nb, nr, nc):
+    off = _offsets(op, nb, nr, nc)
+    lo, hi = int(off.min()), int(off.max())
+    base = _arr(op.ptr + 4 * lo, hi - lo + 1) if lo >= 0 else None
+    if base is None:
+        raise ValueError("negative offset")
+    return base[off - lo]
+
+
+class FakeLib:
+    def __init__(self):
+        self.launches = 0
+        self.err = b""
+
+    # ---- plumbing ----
+    def dstag_abi_version(self):
+        return 1
+
+    def dstag_last_error(self):
+        return self.err
+
+    def dstag_launch_count(self):
+        return self.launches
+
+    def dstag_reset_launch_count(self):
+        self.launches = 0
+
+    def dstag_gemm_uses_tensor_cores(self, gref):
+        return 0
+
+    # ---- contraction ----
+    def dstag_gemm(self, gref, stream):
+        g = gref._obj
+        self.launches += 1
+        A = _read(g.A, g.batch, g.M, g.K).astype(np.float64)
+        if g.Amul.ptr:
+            A = A * _read(g.Amul, g.batch, g.M, g.K)
+        B = _read(g.B, g.batch, g.K, g.N).astype(np.float64)
+        R = g.alpha * np.einsum("bmk,bkn->bmn", A, B)
+        if g.Cadd.ptr:
+            R = R + _read(g.Cadd, g.batch, g.M, g.N)
+        if g.Cmul.ptr:
+            R = R * _read(g.Cmul, g.batch, g.M, g.N)
+        if g.relu:
+            R = np.maximum(R, 0)
+        off = _offsets(g.C, g.batch, g.M, g.N)
+        lo, hi = int(off.min()), int(off.max())
+        out = _arr(g.C.ptr + 4 * lo, hi - lo + 1)
+        if g.accumulate == 0:
+            assert len(np.unique(off)) == off.size, "store-mode output aliases"
+            out[off - lo] = R
+        else:
+            np.add.at(out, (off - lo).ravel(), R.ravel().astype(np.float32))
+        return 0
+
+    # ---- row kernels ----
+    @staticmethod
+    def _ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L):
+        r = np.arange(rows, dtype=np.int64)
+        off = ((r // a_div) * a_s0 + (r % a_div) * a_s1)[:, None] + (np.arange(L, dtype=np.int64) * a_sc)[None, :]
+        pre = _arr(a, off.max() + 1)[off].astype(np.float64)
+        if tab:
+            pre = pre + _arr(tab, tab_mod * L).reshape(tab_mod, L)[r % tab_mod]
+        return pre
+
+    def dstag_layernorm_fwd(self, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, beta, eps, y, mean, rstd,
+                            rows, L, drop_p, seed, stream):
+        assert drop_p == 0.0, "emulation has no dropout"
+        self.launches += 1
+        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L)
+        mu = pre.mean(1)
+        rs = 1.0 / np.sqrt(pre.var(1) + eps)
+        _arr(y, rows * L).reshape(rows, L)[:] = (pre - mu[:, None]) * rs[:, None] * _arr(gamma, L) + _arr(beta, L)
+        _arr(mean, rows)[:] = mu
+        _arr(rstd, rows)[:] = rs
+        return 0
+
+    def dstag_layernorm_bwd(self, dy, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, mean, rstd, dpre, dgamma,
+                            dbeta, rows, L, drop_p, seed, stream):
+        assert drop_p == 0.0
+        self.launches += 1
+        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L)
+        mu = _arr(mean, rows).astype(np.float64)[:, None]
+        rs = _arr(rstd, rows).astype(np.float64)[:, None]
+        xh = (pre - mu) * rs
+        d = _arr(dy, rows * L).reshape(rows, L).astype(np.float64)
+        g = d * _arr(gamma, L)
+        _arr(dpre, rows * L).reshape(rows, L)[:] = rs * (g - g.mean(1, keepdims=True)
+                                                        - xh * (g * xh).mean(1, keepdims=True))
+        _arr(dgamma, L)[:] += (d * xh).sum(0)
+        _arr(dbeta, L)[:] += d.sum(0)
+        return 0
+
+    def dstag_colsum(self, inp, out, rows, cols, ld, stream):
+        self.launches += 1
+        m = _arr(inp, (rows - 1) * ld + cols)
+        acc = np.zeros(cols)
+        for r in range(rows):
+            acc += m[r * ld:r * ld + cols]
+        _arr(out, cols)[:] += acc
+        return 0
+
+    def dstag_transpose(self, inp, out, batch, R, Cc, stream):
+        self.launches += 1
+        _arr(out, batch * R * Cc).reshape(batch, Cc, R)[:] = _arr(inp, batch * R * Cc).reshape(batch, R, Cc).transpose(0, 2, 1)
+        return 0
+
+    def dstag_softmax_fwd(self, x, rows, L, ld, stream):
+        self.launches += 1
+        m = _arr(x, rows * ld).reshape(rows, ld)
+        s = m[:, :L].astype(np.float64)
+        e = np.exp(s - s.max(1, keepdims=True))
+        m[:, :L] = e / e.sum(1, keepdims=True)
+        m[:, L:] = 0
+        return 0
+
+    def dstag_softmax_bwd(self, p, dp, rows, L, ld, stream):
+        self.launches += 1
+        P = _arr(p, rows * ld).reshape(rows, ld)[:, :L].astype(np.float64)
+        D = _arr(dp, rows * ld).reshape(rows, ld)
+        d = D[:, :L].astype(np.float64)
+        D[:, :L] = P * (d - (P * d).sum(1, keepdims=True))
+        D[:, L:] = 0
+        return 0
+
+    def dstag_relu_bwd(self, y, dy, dx, n, stream):
+        self.launches += 1
+        _arr(dx, n)[:] = np.where(_arr(y, n) > 0, _arr(dy, n), 0)
+        return 0
+
+    # ---- temporal attention ----
+    def dstag_tattn_fwd(self, qkv, res, res_F, scores, ctx, B, F, H, T, dk, stream):
+        self.launches += 1
+        q = _arr(qkv, B * F * T * 3 * H * dk).reshape(B, F, T, 3, H, dk).astype(np.float64)
+        Q, K, V = (q[:, :, :, i].transpose(0, 1, 3, 2, 4) for i in range(3))            # (B,F,H,T,dk)
+        S = Q @ K.transpose(0, 1, 2, 4, 3) / math.sqrt(dk)
+        if res_F:
+            S = S + _arr(res, B * res_F * H * T * T).reshape(B, res_F, H, T, T)
+        _arr(scores, B * F * H * T * T).reshape(B, F, H, T, T)[:] = S
+        e = np.exp(S - S.max(3, keepdims=True))
+        P = e / e.sum(3, keepdims=True)                                                  # over the QUERY axis
+        _arr(ctx, B * F * T * H * dk).reshape(B, F, T, H, dk)[:] = (P @ V).transpose(0, 1, 3, 2, 4)
+        return 0
+
+    def dstag_tattn_bwd(self, qkv, scores, dctx, dsext, dqkv, dsout, B, F, H, T, dk, stream):
+        self.launches += 1
+        q = _arr(qkv, B * F * T * 3 * H * dk).reshape(B, F, T, 3, H, dk).astype(np.float64)
+        Q, K, V = (q[:, :, :, i].transpose(0, 1, 3, 2, 4) for i in range(3))
+        S = _arr(scores, B * F * H * T * T).reshape(B, F, H, T, T).astype(np.float64)
+        e = np.exp(S - S.max(3, keepdims=True))
+        P = e / e.sum(3, keepdims=True)
+        dC = _arr(dctx, B * F * T * H * dk).reshape(B, F, T, H, dk).transpose(0, 1, 3, 2, 4).astype(np.float64)
+        dV = P.transpose(0, 1, 2, 4, 3) @ dC
+        dP = dC @ V.transpose(0, 1, 2, 4, 3)
+        dS = P * (dP - (P * dP).sum(3, keepdims=True))
+        if dsext:
+            dS = dS + _arr(dsext, B * F * H * T * T).reshape(B, F, H, T, T)
+        _arr(dsout, B * F * H * T * T).reshape(B, F, H, T, T)[:] = dS
+        dQ = dS @ K / math.sqrt(dk)
+        dK = dS.transpose(0, 1, 2, 4, 3) @ Q / math.sqrt(dk)
+        out = _arr(dqkv, B * F * T * 3 * H * dk).reshape(B, F, T, 3, H, dk)
+        for i, t in enumerate((dQ, dK, dV)):
+            out[:, :, :, i] = t.transpose(0, 1, 3, 2, 4)
+        return 0
+
+    # ---- GTU gate + tail ----
+    def dstag_gtu_gate_fwd(self, u, out, X, Cc, Tp, out_ld, out_off, stream):
+        self.launches += 1
+        U = _arr(u, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp).astype(np.float64)
+        O = _arr(out, X * Cc * out_ld).reshape(X, Cc, out_ld)
+        O[:, :, out_off:out_off + Tp] = np.tanh(U[:, :Cc]) / (1 + np.exp(-U[:, Cc:]))
+        return 0
+
+    def dstag_gtu_gate_bwd(self, u, dout, du, X, Cc, Tp, out_ld, out_off, stream):
+        self.launches += 1
+        U = _arr(u, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp).astype(np.float64)
+        d = _arr(dout, X * Cc * out_ld).reshape(X, Cc, out_ld)[:, :, out_off:out_off + Tp].astype(np.float64)
+        th, sg = np.tanh(U[:, :Cc]), 1 / (1 + np.exp(-U[:, Cc:]))
+        D = _arr(du, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp)
+        D[:, :Cc] = d * sg * (1 - th * th)
+        D[:, Cc:] = d * th * sg * (1 - sg)
+        return 0
+
+    def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, stream):
+        assert drop_p == 0.0
+        self.launches += 1
+        n = X * Cc * T
+        s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
+        if g:
+            s1 = s1 + _arr(g, n).reshape(X, Cc, T)
+        v = np.maximum(_arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0), 0)
+        mu = v.mean(1)
+        rs = 1 / np.sqrt(v.var(1) + eps)
+        ga, be = _arr(gamma, Cc)[None, :, None], _arr(beta, Cc)[None, :, None]
+        _arr(out, n).reshape(X, Cc, T)[:] = (v - mu[:, None]) * rs[:, None] * ga + be
+        _arr(mean, X * T).reshape(X, T)[:] = mu
+        _arr(rstd, X * T).reshape(X, T)[:] = rs
+        return 0
+
+    def dstag_tail_bwd(self, dout, tc, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma, dbeta, X, Cc, T, drop_p,
+                       seed, stream):
+        assert drop_p == 0.0
+        self.launches += 1
+        n = X * Cc * T
+        s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
+        if g:
+            s1 = s1 + _arr(g, n).reshape(X, Cc, T)
+        s2 = _arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0)
+        v = np.maximum(s2, 0)
+        mu = _arr(mean, X * T).reshape(X, 1, T).astype(np.float64)
+        rs = _arr(rstd, X * T).reshape(X, 1, T).astype(np.float64)
+        xh = (v - mu) * rs
+        d = _arr(dout, n).reshape(X, Cc, T).astype(np.float64)
+        gy = d * _arr(gamma, Cc)[None, :, None]
+        dv = rs * (gy - gy.mean(1, keepdims=True) - xh * (gy * xh).mean(1, keepdims=True))
+        ds2 = dv * (s2 > 0)
+        ds1 = ds2 * (s1 > 0)
+        _arr(dr, n).reshape(X, Cc, T)[:] = ds2
+        _arr(dtc, n).reshape(X, Cc, T)[:] = ds1
+        if dg:
+            _arr(dg, n).reshape(X, Cc, T)[:] = ds1
+        _arr(dgamma, Cc)[:] += (d * xh).sum((0, 2))
+        _arr(dbeta, Cc)[:] += d.sum((0, 2))
+        return 0
+
+
+def install(monkeypatch):
+    """Route the package's ctypes calls to the emulation (CPU tensors)."""
+    from dstagnn_drought_b200 import _lib, contraction, modules, ops
+    fake = FakeLib()
+    monkeypatch.setattr(modules, "_require_cuda", lambda x: None)
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda t: None)
+    monkeypatch.setattr(contraction, "_check", lambda t, name: None)
+    monkeypatch.setattr(ops, "_check", lambda t, name: None)
+    return fake

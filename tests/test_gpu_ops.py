@@ -1,0 +1,289 @@
+"""GPU unit tests: every C-ABI kernel against a plain PyTorch (fp64) evaluation of the same
+formula, forward and backward, incl. ragged sizes.  Tolerances are relative to max|ref|."""
+import math
+
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5   # fp32 kernels vs fp64 evaluation
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["fp32", "tf32x3"])
+def precision(request):
+    import dstagnn_drought_b200 as D
+    old = D.get_precision()
+    D.set_precision(request.param)
+    yield request.param
+    D.set_precision(old)
+
+
+def _grads(fn, inputs, dout):
+    xs = [t.detach().clone().requires_grad_(True) for t in inputs]
+    out = fn(*xs)
+    out.backward(dout.to(out.dtype))
+    return out.detach(), [x.grad for x in xs]
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 7, 3), (3, 70, 65, 33), (2, 129, 64, 130), (1, 300, 33, 1000)])
+def test_contract_matmul_fwd_bwd(dev, precision, shape):
+    from dstagnn_drought_b200 import contract
+    b, m, n, k = shape
+    torch.manual_seed(0)
+    A = torch.randn(b, m, k, device=dev)
+    B = torch.randn(b, n, k, device=dev)
+    bias = torch.randn(n, device=dev)
+    dout = torch.randn(b, m, n, device=dev)
+    out, (dA, dB, db) = _grads(lambda a, bb, c: contract("bmk,bnk->bmn", a, bb, c_add=("n", c), alpha=0.5),
+                               [A, B, bias], dout)
+    ref, (rA, rB, rb) = _grads(lambda a, bb, c: 0.5 * torch.einsum("bmk,bnk->bmn", a, bb) + c,
+                               [A.double(), B.double(), bias.double()], dout.double())
+    for got, want in ((out, ref), (dA, rA), (dB, rB), (db, rb)):
+        assert rel_err(got, want) < TOL
+
+
+def test_contract_weight_grad_split_k_and_relu(dev, precision):
+    from dstagnn_drought_b200 import contract
+    torch.manual_seed(1)
+    X = torch.randn(9000, 48, device=dev)
+    W = torch.randn(40, 48, device=dev)
+    dout = torch.randn(9000, 40, device=dev)
+    out, (dX, dW) = _grads(lambda x, w: contract("xk,ok->xo", x, w, relu=True), [X, W], dout)
+    ref, (rX, rW) = _grads(lambda x, w: torch.relu(x @ w.t()), [X.double(), W.double()], dout.double())
+    assert rel_err(out, ref) < TOL and rel_err(dX, rX) < TOL and rel_err(dW, rW) < TOL
+
+
+def test_contract_permuted_and_two_level_axes(dev, precision):
+    from dstagnn_drought_b200 import contract
+    torch.manual_seed(2)
+    Bz, F, T, N, Dm = 3, 4, 12, 37, 24
+    O = torch.randn(Bz, F, T, N, device=dev)
+    W = torch.randn(Dm, T, 1, F, device=dev)
+    bias = torch.randn(Dm, device=dev)
+    dout = torch.randn(Bz, N, Dm, device=dev)
+    out, (dO, dW, db) = _grads(lambda o, w, c: contract("bftn,dtf->bnd", o, w[:, :, 0, :], c_add=("d", c)),
+                               [O, W, bias], dout)
+    ref, (rO, rW, rb) = _grads(lambda o, w, c: torch.einsum("bftn,dtf->bnd", o, w[:, :, 0, :]) + c,
+                               [O.double(), W.double(), bias.double()], dout.double())
+    for got, want in ((out, ref), (dO, rO), (dW, rW), (db, rb)):
+        assert rel_err(got, want) < TOL
+
+
+@pytest.mark.parametrize("rows,L,tab_mod", [(7, 5, 7), (24, 33, 12), (300, 883, 300), (1766, 512, 883)])
+def test_layernorm_add(dev, rows, L, tab_mod):
+    from dstagnn_drought_b200.ops import LayerNormAdd
+    torch.manual_seed(3)
+    a = torch.randn(rows, L, device=dev)
+    tab = torch.randn(tab_mod, L, device=dev)
+    gam, bet = torch.rand(L, device=dev), torch.rand(L, device=dev)
+    dout = torch.randn(rows, L, device=dev)
+
+    def ref_fn(a_, t_, g_, b_):
+        pre = a_ + t_.repeat(rows // tab_mod, 1)
+        return torch.nn.functional.layer_norm(pre, (L,), g_, b_, 1e-5)
+
+    out, gr = _grads(lambda *xs: LayerNormAdd.apply(*xs, False, 0.0, 0), [a, tab, gam, bet], dout)
+    ref, rr = _grads(ref_fn, [t.double() for t in (a, tab, gam, bet)], dout.double())
+    assert rel_err(out, ref) < TOL
+    for got, want in zip(gr, rr):
+        assert rel_err(got, want) < 5e-5
+
+
+def test_layernorm_gather_embedT(dev):
+    from dstagnn_drought_b200.ops import LayerNormAdd
+    torch.manual_seed(4)
+    Bz, N, T = 3, 41, 12
+    x3 = torch.randn(Bz, N, T, device=dev)
+    tab = torch.randn(T, N, device=dev)
+    gam, bet = torch.rand(N, device=dev), torch.rand(N, device=dev)
+    dout = torch.randn(Bz * T, N, device=dev)
+
+    def ref_fn(x_, t_, g_, b_):
+        pre = x_.permute(0, 2, 1) + t_
+        return torch.nn.functional.layer_norm(pre, (N,), g_, b_, 1e-5).reshape(Bz * T, N)
+
+    out, gr = _grads(lambda *xs: LayerNormAdd.apply(*xs, True, 0.0, 0), [x3, tab, gam, bet], dout)
+    ref, rr = _grads(ref_fn, [t.double() for t in (x3, tab, gam, bet)], dout.double())
+    assert rel_err(out, ref) < TOL
+    for got, want in zip(gr, rr):
+        assert rel_err(got, want) < 5e-5
+
+
+def test_layernorm_dropout_statistics_and_backward_mask(dev):
+    from dstagnn_drought_b200.ops import LayerNormAdd
+    torch.manual_seed(5)
+    rows, L, p = 2000, 512, 0.05
+    a = torch.randn(rows, L, device=dev, requires_grad=True)
+    tab = torch.zeros(rows, L, device=dev)
+    gam, bet = torch.ones(L, device=dev), torch.full((L,), 3.0, device=dev)
+    y = LayerNormAdd.apply(a, tab, gam, bet, False, p, 1234)
+    y0 = LayerNormAdd.apply(a, tab, gam, bet, False, 0.0, 0)
+    dropped = (y == 0)
+    frac = dropped.float().mean().item()
+    assert abs(frac - p) < 0.003
+    assert torch.allclose(y[~dropped], y0[~dropped] / (1 - p), rtol=1e-5, atol=1e-5)
+    y2 = LayerNormAdd.apply(a, tab, gam, bet, False, p, 1234)
+    assert torch.equal(y, y2)                                    # same seed -> same mask
+    # backward uses the same mask: d/d(beta) = sum over kept rows of 1/(1-p)
+    gb = torch.zeros(L, device=dev, requires_grad=True)
+    yb = LayerNormAdd.apply(a.detach(), tab, gam, bet + gb, False, p, 1234)
+    yb.sum().backward()
+    want = (~dropped).float().sum(0) / (1 - p)
+    assert torch.allclose(gb.grad, want, rtol=1e-4)
+
+
+@pytest.mark.parametrize("cfg", [(2, 1, 2, 12, None), (2, 5, 3, 12, 1), (2, 5, 3, 12, 5), (1, 3, 2, 40, 3)])
+def test_temporal_attention(dev, cfg):
+    from dstagnn_drought_b200.ops import TemporalAttention
+    Bz, F, H, T, res_F = cfg
+    dk = 32
+    torch.manual_seed(6)
+    qkv = torch.randn(Bz, F, T, 3, H, dk, device=dev)
+    res = torch.randn(Bz, res_F, H, T, T, device=dev) if res_F else None
+    dctx = torch.randn(Bz, F, T, H * dk, device=dev)
+    dlog = torch.randn(Bz, F, H, T, T, device=dev)
+
+    def ref_fn(qkv_, res_):
+        q, k, v = (qkv_[:, :, :, i].transpose(2, 3) for i in range(3))       # (B,F,H,T,dk)
+        s = q @ k.transpose(-1, -2) / math.sqrt(dk)
+        if res_ is not None:
+            s = s + res_
+        ctx = (torch.softmax(s, dim=3) @ v).transpose(2, 3).reshape(Bz, F, T, H * dk)
+        return ctx, s
+
+    xs = [qkv.clone().requires_grad_(True)] + ([res.clone().requires_grad_(True)] if res_F else [])
+    ctx, log = TemporalAttention.apply(xs[0], xs[1] if res_F else None, Bz, F, H, T, dk)
+    torch.autograd.backward([ctx, log], [dctx, dlog])
+    rs = [qkv.double().requires_grad_(True)] + ([res.double().requires_grad_(True)] if res_F else [])
+    rctx, rlog = ref_fn(rs[0], rs[1] if res_F else None)
+    torch.autograd.backward([rctx, rlog], [dctx.double(), dlog.double()])
+    assert rel_err(ctx, rctx) < TOL and rel_err(log, rlog) < TOL
+    for a, b in zip(xs, rs):
+        assert rel_err(a.grad, b.grad) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [(2, 9, 3, 1), (2, 70, 3, 12), (1, 200, 2, 40)])
+def test_spatial_cheb_conv(dev, precision, cfg):
+    from dstagnn_drought_b200.ops import SpatialChebConv, _pad_ld
+    Bz, N, K, FT = cfg
+    dk = 32
+    ld = _pad_ld(N)
+    torch.manual_seed(7)
+    qk = torch.randn(Bz, N, 2, K, dk, device=dev)
+    bias = torch.zeros(K, N, ld, device=dev)
+    bias[..., :N] = torch.randn(K, N, N, device=dev)
+    tk = torch.zeros(K, N, ld, device=dev)
+    tk[..., :N] = torch.randn(K, N, N, device=dev) * (torch.rand(K, N, N, device=dev) < 0.3)
+    x3 = torch.randn(Bz, N, FT, device=dev)
+    dZ = torch.randn(K, Bz, N, FT, device=dev)
+
+    def ref_fn(qk_, bias_, x_):
+        s = torch.einsum("bjkd,bikd->bkji", qk_[:, :, 1], qk_[:, :, 0]) / math.sqrt(dk) + bias_[..., :N]
+        a = torch.softmax(s, dim=-1) * tk[..., :N].to(s.dtype)
+        return torch.einsum("bkji,bie->kbje", a, x_)
+
+    out, gr = _grads(lambda a, b, c: SpatialChebConv.apply(a, b, tk, c), [qk, bias, x3], dZ)
+    ref, rr = _grads(ref_fn, [qk.double(), bias.double(), x3.double()], dZ.double())
+    assert rel_err(out, ref) < TOL
+    assert rel_err(gr[0], rr[0]) < 5e-5 and rel_err(gr[2], rr[2]) < TOL
+    assert rel_err(gr[1][..., :N], rr[1][..., :N]) < 5e-5
+    assert float(gr[1][..., N:].abs().max()) == 0.0 if ld > N else True
+
+
+@pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144)])
+def test_gtu_stack(dev, precision, cfg):
+    from dstagnn_drought_b200.ops import GtuStack
+    X, Cc, T = cfg
+    torch.manual_seed(8)
+    g = torch.randn(X, Cc, T, device=dev)
+    ws = [torch.randn(2 * Cc, Cc, 1, ks, device=dev) * 0.2 for ks in (3, 5, 7)]
+    bs = [torch.randn(2 * Cc, device=dev) for _ in range(3)]
+    dout = torch.randn(X, Cc, 3 * T - 12, device=dev)
+
+    def ref_fn(g_, w3, b3, w5, b5, w7, b7):
+        xc = g_.permute(1, 0, 2).unsqueeze(0)                                 # (1, C, X, T)
+        outs = []
+        for w, b in ((w3, b3), (w5, b5), (w7, b7)):
+            u = torch.nn.functional.conv2d(xc, w, b)
+            outs.append(torch.tanh(u[:, :Cc]) * torch.sigmoid(u[:, -Cc:]))
+        return torch.cat(outs, dim=-1)[0].permute(1, 0, 2)
+
+    args = [g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2]]
+    out, gr = _grads(lambda *xs: GtuStack.apply(*xs), args, dout)
+    ref, rr = _grads(ref_fn, [a.double() for a in args], dout.double())
+    assert rel_err(out, ref) < TOL
+    for got, want in zip(gr, rr):
+        assert rel_err(got, want) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [(3, 32, 12, True), (500, 32, 12, False), (37, 32, 12, True), (9, 32, 144, True),
+                                 (5, 16, 20, False)])
+def test_block_tail(dev, cfg):
+    from dstagnn_drought_b200.ops import BlockTail
+    X, Cc, T, with_g = cfg
+    torch.manual_seed(9)
+    tc, g, r = (torch.randn(X, Cc, T, device=dev) for _ in range(3))
+    gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
+    dout = torch.randn(X, Cc, T, device=dev)
+
+    def ref_fn(tc_, g_, r_, ga_, be_):
+        tco = torch.relu(tc_ + g_) if with_g else torch.relu(tc_)
+        v = torch.relu(r_ + tco).permute(0, 2, 1)
+        return torch.nn.functional.layer_norm(v, (Cc,), ga_, be_, 1e-5).permute(0, 2, 1)
+
+    def fn(tc_, g_, r_, ga_, be_):
+        return BlockTail.apply(tc_, g_ if with_g else None, r_, ga_, be_, 0.0, 0)
+
+    out, gr = _grads(fn, [tc, g, r, gam, bet], dout)
+    ref, rr = _grads(ref_fn, [t.double() for t in (tc, g, r, gam, bet)], dout.double())
+    assert rel_err(out, ref) < TOL
+    for i, (got, want) in enumerate(zip(gr, rr)):
+        if i == 1 and not with_g:
+            continue
+        assert rel_err(got, want) < 5e-5, i
+
+
+def test_block_tail_dropout_is_consistent(dev):
+    from dstagnn_drought_b200.ops import BlockTail
+    torch.manual_seed(10)
+    X, Cc, T, p = 4000, 32, 12, 0.05
+    tc = (torch.rand(X, Cc, T, device=dev) + 0.5).requires_grad_(True)      # strictly positive
+    r = torch.full((X, Cc, T), -100.0, device=dev)                          # second relu sees tco only
+    gam, bet = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+    out = BlockTail.apply(tc, None, r + 100.0, gam, bet, p, 77)
+    out.sum().backward()
+    # LN output sums to zero per column, so instead check the mask through the gradient pattern:
+    out2 = BlockTail.apply(tc, None, r + 100.0, gam, bet, p, 77)
+    assert torch.equal(out, out2)
+    out3 = BlockTail.apply(tc, None, r + 100.0, gam, bet, p, 78)
+    assert not torch.equal(out, out3)
+
+
+def test_transpose_softmax_colsum_relu(dev):
+    import ctypes as C
+    from dstagnn_drought_b200 import _lib
+    from dstagnn_drought_b200.contraction import colsum, relu_bwd
+    from dstagnn_drought_b200.ops import transpose_raw
+    lib = _lib.load()
+    torch.manual_seed(11)
+    x = torch.randn(3, 45, 70, device=dev)
+    assert torch.equal(transpose_raw(x), x.transpose(1, 2).contiguous())
+    for rows, cols in ((7, 1), (1000, 64), (64, 5000), (33, 130)):
+        m = torch.randn(rows, cols, device=dev)
+        assert rel_err(colsum(m, rows, cols), m.double().sum(0)) < TOL
+    S = torch.randn(50, 40, device=dev)
+    P = S.clone()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), 50, 33, 40, st), "softmax")
+    assert rel_err(P[:, :33], torch.softmax(S[:, :33].double(), -1)) < TOL
+    assert float(P[:, 33:].abs().max()) == 0.0
+    y, dy = torch.randn(1001, device=dev), torch.randn(1001, device=dev)
+    assert torch.equal(relu_bwd(y, dy), dy * (y > 0))

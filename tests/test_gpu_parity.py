@@ -1,0 +1,111 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the committed golden
+fixtures of the reference and against the CPU oracle, whole-net forward + backward.
+
+Tolerance (north star: fp32, max rel err <= 1e-4): per tensor, max|err| / max|ref| against the
+fp64 result; predictions and block outputs must be < 1e-4; gradients < 1e-4 or 3x the
+reference's own fp32 error on that tensor, whichever is larger (the tiny
+spatial-path gradients of the reference itself are only good to 3-5e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_PRED = 1e-4
+TOL_GRAD = 1e-4
+
+
+def _build(cfg, d, dev):
+    from dstagnn_drought_b200 import make_model
+    return make_model(dev, 1, cfg["nb"], 1, cfg["K"], 32, 32, 1, torch.from_numpy(d["adj_tmd"]),
+                      torch.from_numpy(d["adj_pa"]), torch.from_numpy(d["adj_tmd"]), cfg["P"], cfg["T"],
+                      cfg["N"], cfg["D"], 32, 32, cfg["H"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("name", GOLDEN)
+def test_net_matches_reference_golden(name, precision):
+    import dstagnn_drought_b200 as D
+    D.set_precision(precision)
+    dev = torch.device("cuda:0")
+    d, cfg, w, g, cheb = load_golden(name)
+    net = _build(cfg, d, dev)
+    net.load_state_dict(w)
+    net.eval()
+    blocks, atts = [], []
+    for b in net.BlockList:
+        b.register_forward_hook(lambda m, i, o: (blocks.append(o[0].detach()), atts.append(o[1].detach()), None)[2])
+    x = torch.from_numpy(d["x"]).to(dev)
+    y = net(x)
+    assert y.shape == d["y64"].shape
+    assert rel_err(y.detach(), d["y64"]) < TOL_PRED
+    for i in range(cfg["nb"]):
+        assert rel_err(blocks[i], d[f"blk64.{i}"]) < TOL_PRED, f"block {i} output"
+        assert rel_err(atts[i], d[f"att64.{i}"]) < TOL_PRED, f"block {i} logits"
+    loss = torch.nn.SmoothL1Loss()(y, torch.from_numpy(d["target"]).to(dev))
+    assert abs(loss.item() - float(d["loss64"])) < 1e-5
+    loss.backward()
+    ref_err = dict(zip((str(k) for k in d["ref_fp32_grad_err_keys"]), d["ref_fp32_grad_err"]))
+    dead = set(str(k) for k in d["dead"])
+    worst = {}
+    for k, p in net.named_parameters():
+        if k in dead:
+            assert p.grad is None, f"{k} must stay a dead parameter (grad None)"
+            continue
+        assert p.grad is not None, k
+        e = rel_err(p.grad, g[k])
+        worst[k] = e
+        assert e < max(TOL_GRAD, 3 * ref_err[k]), f"{k}: {e:.3e} (reference fp32 itself: {ref_err[k]:.3e})"
+    print(name, precision, "pred", rel_err(y.detach(), d["y64"]), "worst grad", max(worst.values()))
+    D.set_precision("tf32x3")
+
+
+@pytest.mark.parametrize("shape", [dict(N=170, T=12, K=3, H=3, D=64, nb=2, B=3),
+                                   dict(N=307, T=12, K=3, H=3, D=128, nb=2, B=2),
+                                   dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2)])
+def test_net_matches_oracle_at_config_shapes(shape):
+    """Ragged PEMS08 / PEMS04 node counts and a longer horizon, against the fp64 CPU oracle."""
+    from oracle import dstagnn_oracle as O
+    dev = torch.device("cuda:0")
+    N, T, K, H, Dm, nb, B = (shape[k] for k in ("N", "T", "K", "H", "D", "nb", "B"))
+    onet = O.build_oracle(N, T, K, H, Dm, nb, dtype=torch.float64, faithful=False)
+    tmd, pa = O.synthetic_graph(N, 0)
+    from dstagnn_drought_b200 import make_model
+    net = make_model(dev, 1, nb, 1, K, 32, 32, 1, torch.from_numpy(tmd), torch.from_numpy(pa),
+                     torch.from_numpy(tmd), 12, T, N, Dm, 32, 32, H)
+    net.load_state_dict({k: v.detach().float() for k, v in onet.named().items()})
+    net.eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, 1, T, generator=g)
+    tgt = torch.randn(B, N, 12, generator=g)
+    y_ref = onet(x.double())
+    torch.nn.SmoothL1Loss()(y_ref, tgt.double()).backward()
+    y = net(x.to(dev))
+    torch.nn.SmoothL1Loss()(y, tgt.to(dev)).backward()
+    assert rel_err(y.detach(), y_ref.detach()) < TOL_PRED
+    ograds = {k: v.grad for k, v in onet.named().items()}
+    for k, p in net.named_parameters():
+        if ograds[k] is None:
+            assert p.grad is None, k
+        else:
+            assert rel_err(p.grad, ograds[k]) < 5e-4, k
+
+
+def test_train_mode_runs_and_dropout_is_active():
+    dev = torch.device("cuda:0")
+    d, cfg, w, g, cheb = load_golden("g_n20")
+    net = _build(cfg, d, dev)
+    net.load_state_dict(w)
+    x = torch.from_numpy(d["x"]).to(dev)
+    net.train()
+    torch.manual_seed(0)
+    y1 = net(x)
+    y2 = net(x)
+    net.eval()
+    y0 = net(x)
+    assert not torch.equal(y1, y2)                       # fresh masks per call
+    assert rel_err(y1.detach(), y0.detach()) < 0.5       # but the same function in expectation
+    y1.sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
