@@ -93,6 +93,45 @@ def stream_ptr(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+# ---- optional per-kernel CUDA-event profiler (bench.py / profiling only) -----------------------
+_prof = None          # None = disabled; else {tag: [(start_event, end_event, flops, bytes), ...]}
+
+
+def prof_enable(on: bool = True):
+    global _prof
+    _prof = {} if on else None
+
+
+def prof_results():
+    """{tag: (calls, total_ms, flops, bytes)} -- call after torch.cuda.synchronize()."""
+    out = {}
+    for tag, evs in (_prof or {}).items():
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in evs)
+        out[tag] = (len(evs), ms, sum(e[2] for e in evs), sum(e[3] for e in evs))
+    return out
+
+
+class prof_range:
+    """Records a CUDA-event pair on the current stream around the enclosed launches."""
+
+    def __init__(self, tag, flops=0, nbytes=0):
+        self.tag, self.flops, self.nbytes = tag, flops, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            import torch
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.b.record()
+            _prof.setdefault(self.tag, []).append((self.a, self.b, self.flops, self.nbytes))
+        return False
+
+
 def check(rc: int, what: str):
     if rc != 0:
         msg = load().dstag_last_error().decode("utf-8", "replace")

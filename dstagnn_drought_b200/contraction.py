@@ -171,7 +171,7 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                  c_add: Optional[Tuple[str, torch.Tensor]] = None,
                  c_mul: Optional[Tuple[str, torch.Tensor]] = None, alpha: float = 1.0,
                  relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
-                 precision=None) -> torch.Tensor:
+                 precision=None, tag: Optional[str] = None) -> torch.Tensor:
     """Enqueue one contraction on the current CUDA stream.  No autograd."""
     lib = _lib.load()
     _check(A, "A"), _check(B, "B")
@@ -195,7 +195,12 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             pass  # existing contents are kept; partial sums are added atomically
         accumulate = ACC_ATOMIC
     g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
-    _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
+    if _lib._prof is None:
+        _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
+    else:
+        nbytes = 4 * (A.numel() + B.numel() + out.numel())
+        with _lib.prof_range(tag or ("gemm:" + spec), 2 * M * N * K * nb, nbytes):
+            _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
     return out
 
 

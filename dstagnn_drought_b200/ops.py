@@ -227,7 +227,7 @@ class SpatialChebConv(torch.autograd.Function):
                      c_add=("kji", biasT[..., :N]))
         _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
         Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
-        contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]))
+        contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd")
         ctx.save_for_backward(qk, P, tkT, x3)
         return Z
 
@@ -242,9 +242,9 @@ class SpatialChebConv(torch.autograd.Function):
         Pv, Tv = P[..., :N], tkT[..., :N]
         dx = None
         if ctx.needs_input_grad[3]:
-            dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv))
+            dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv), tag="cheb_bwd_dx")
         dS = torch.empty_like(P)
-        contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], c_mul=("kji", Tv))
+        contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], c_mul=("kji", Tv), tag="cheb_bwd_dmap")
         _lib.check(lib.dstag_softmax_bwd(P.data_ptr(), dS.data_ptr(), B * K * N, N, ld, _stream(P)),
                    "dstag_softmax_bwd")
         dSv = dS[..., :N]

@@ -187,7 +187,7 @@ def test_make_model_matches_reference_state_dict_and_init(name):
     # Chebyshev constants equal the reference's (transposed, padded)
     blk = net.BlockList[0]
     for k, t in enumerate(cheb[:cfg["K"]]):
-        assert torch.allclose(blk.cheb_T[k, :, :cfg["N"]], t.t(), atol=1e-6)
+        assert torch.allclose(blk.cheb_T[k, :, :cfg["N"]], t.t(), atol=2e-5, rtol=1e-4)
         assert float(blk.cheb_T[k, :, cfg["N"]:].abs().max()) == 0.0 if blk.ld > cfg["N"] else True
 
 
