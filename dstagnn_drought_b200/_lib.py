@@ -83,8 +83,32 @@ def load():
     ver = lib.dstag_abi_version()
     if ver != ABI_VERSION:
         raise RuntimeError(f"libdstagnn_b200.so ABI {ver} != expected {ABI_VERSION}; rebuild it")
-    _lib = lib
-    return lib
+    _lib = _Profiled(lib)
+    return _lib
+
+
+class _Profiled:
+    """Thin proxy over the CDLL: identical calls; when the event profiler is enabled every
+    kernel entry point (except dstag_gemm, which contraction.py tags itself) is bracketed by
+    a CUDA-event pair named after the function."""
+
+    _PLAIN = ("dstag_abi_version", "dstag_last_error", "dstag_launch_count", "dstag_reset_launch_count",
+              "dstag_gemm", "dstag_gemm_uses_tensor_cores")
+
+    def __init__(self, lib):
+        self._cdll = lib
+        for name in SIGNATURES:
+            fn = getattr(lib, name)
+            setattr(self, name, fn if name in self._PLAIN else self._wrap(name, fn))
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*args):
+            if _prof is None:
+                return fn(*args)
+            with prof_range(name):
+                return fn(*args)
+        return call
 
 
 def stream_ptr(t):
