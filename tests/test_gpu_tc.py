@@ -1,0 +1,140 @@
+"""GPU tests of the tcgen05 contraction engine (csrc/gemm_tc.cu) against fp64 einsum:
+both operand-load modes (K-vector / row-gather), fused Hadamard operand, epilogue variants,
+split-K atomics, ragged tile edges, all three N-tile widths, both precisions."""
+import ctypes as C
+
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32x3": 2e-5, "tf32": 3e-3}
+
+
+def _uses_tc(spec, A, B, out, precision, **kw):
+    from dstagnn_drought_b200 import _lib, contraction as ct
+    g = ct.build_descriptor(spec, A, B, out, precision=ct._PRECISION[precision], **kw)
+    return bool(_lib.load().dstag_gemm_uses_tensor_cores(C.byref(g)))
+
+
+def _run(spec, A, B, precision, **kw):
+    from dstagnn_drought_b200 import contraction as ct
+    shape = ct.output_shape(spec, A, B)
+    out = kw.pop("out", None)
+    if out is None:
+        out = torch.full(shape, float("nan"), device=A.device)
+    assert _uses_tc(spec, A, B, out, precision, **{k: v for k, v in kw.items() if k in ("a_mul", "c_add", "c_mul")})
+    ct.contract_raw(spec, A, B, out=out, precision=ct._PRECISION[precision], **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("shape", [(1, 128, 128, 32), (1, 128, 128, 256), (2, 300, 200, 100), (1, 883, 384, 883),
+                                   (3, 129, 40, 70), (1, 1000, 24, 37), (1, 64, 64, 2048), (5, 257, 130, 33)])
+def test_tc_k_contiguous_operands(shape, precision):
+    """A (b,m,k) and B (b,n,k): both K-contiguous -> float4 producer path (when aligned)."""
+    b, m, n, k = shape
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    A = torch.randn(b, m, k, device=dev)
+    B = torch.randn(b, n, k, device=dev)
+    out = _run("bmk,bnk->bmn", A, B, precision)
+    ref = torch.einsum("bmk,bnk->bmn", A.double(), B.double())
+    assert rel_err(out, ref) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("shape", [(2, 256, 128, 64), (1, 883, 384, 883), (2, 150, 72, 333)])
+def test_tc_row_gather_operands(shape, precision):
+    """A (b,k,m) and B (b,k,n): M/N-contiguous, K strided -> row-gather producer path."""
+    b, m, n, k = shape
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    A = torch.randn(b, k, m, device=dev)
+    B = torch.randn(b, k, n, device=dev)
+    out = _run("bkm,bkn->bmn", A, B, precision)
+    ref = torch.einsum("bkm,bkn->bmn", A.double(), B.double())
+    assert rel_err(out, ref) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_tc_cheb_shapes_with_hadamard_operand(precision):
+    """The three Chebyshev contractions at a ragged N (padded maps, fused T_k, padded output)."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    Bz, K, N, E, ld = 2, 3, 307, 96, 320
+    P = torch.zeros(Bz, K, N, ld, device=dev)
+    P[..., :N] = torch.softmax(torch.randn(Bz, K, N, N, device=dev), -1)
+    T = torch.zeros(K, N, ld, device=dev)
+    T[..., :N] = torch.randn(K, N, N, device=dev)
+    X = torch.randn(Bz, N, E, device=dev)
+    Pv, Tv = P[..., :N], T[..., :N]
+    Z = _run("bkji,bie->kbje", Pv, X, precision, a_mul=("kji", Tv))
+    refZ = torch.einsum("bkji,kji,bie->kbje", Pv.double(), Tv.double(), X.double())
+    assert rel_err(Z, refZ) < TOL[precision]
+    dZ = torch.randn_like(Z)
+    dX = _run("bkji,kbje->bie", Pv, dZ, precision, a_mul=("kji", Tv))
+    assert rel_err(dX, torch.einsum("bkji,kji,kbje->bie", Pv.double(), Tv.double(), dZ.double())) < TOL[precision]
+    dS = torch.zeros(Bz, K, N, ld, device=dev)
+    _run("kbje,bie->bkji", dZ, X, precision, out=dS[..., :N], c_mul=("kji", Tv))
+    assert rel_err(dS[..., :N], torch.einsum("kbje,bie,kji->bkji", dZ.double(), X.double(), Tv.double())) < TOL[precision]
+    assert float(dS[..., N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("precision", ["tf32x3"])
+def test_tc_epilogue_variants_and_split_k(precision):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    X = torch.randn(20000, 96, device=dev)
+    W = torch.randn(64, 96, device=dev)
+    bias = torch.randn(64, device=dev)
+    out = _run("xk,ok->xo", X, W, precision, c_add=("o", bias), relu=True, alpha=0.7)
+    ref = torch.relu(0.7 * X.double() @ W.double().t() + bias.double())
+    assert rel_err(out, ref) < TOL[precision]
+    # weight gradient: tiny output, K = 20000 -> split-K with atomic accumulation
+    dO = torch.randn(20000, 64, device=dev)
+    dW = _run("xo,xk->ok", dO, X, precision, out=torch.empty(64, 96, device=dev))
+    assert rel_err(dW, dO.double().t() @ X.double()) < TOL[precision]
+    # accumulate into existing contents
+    acc = torch.ones(20000, 64, device=dev)
+    from dstagnn_drought_b200 import _lib
+    _run("xk,ok->xo", X, W, precision, out=acc, accumulate=_lib.ACC_ADD, split_k=1)
+    assert rel_err(acc, 1.0 + X.double() @ W.double().t()) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3"])
+def test_tc_unfolded_conv_and_m_contiguous_output(precision):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    Xn, Cc, T, ks = 3000, 32, 12, 5
+    g3 = torch.randn(Xn, Cc, T, device=dev)
+    w = torch.randn(2 * Cc, Cc, ks, device=dev) * 0.1
+    b = torch.randn(2 * Cc, device=dev)
+    u = _run("xctd,ocd->xot", g3.unfold(2, ks, 1), w, precision, c_add=("o", b))
+    ref = torch.nn.functional.conv2d(g3.double().permute(1, 0, 2).unsqueeze(0), w.double().unsqueeze(2),
+                                     b.double())[0].permute(1, 0, 2)
+    assert rel_err(u, ref) < TOL[precision]
+    du = torch.randn_like(u)
+    from dstagnn_drought_b200 import _lib
+    dg = torch.zeros_like(g3)
+    _run("xot,ocd->xctd", du, w, precision, out=dg.unfold(2, ks, 1), accumulate=_lib.ACC_ATOMIC, split_k=1)
+    g3r = g3.double().requires_grad_(True)
+    torch.nn.functional.conv2d(g3r.permute(1, 0, 2).unsqueeze(0), w.double().unsqueeze(2),
+                               b.double())[0].permute(1, 0, 2).backward(du.double())
+    assert rel_err(dg, g3r.grad) < TOL[precision]
+    dw = _run("xot,xctd->ocd", du, g3.unfold(2, ks, 1), precision, out=torch.empty(2 * Cc, Cc, ks, device=dev))
+    ref_dw = torch.einsum("xot,xctd->ocd", du.double(), g3.double().unfold(2, ks, 1))
+    assert rel_err(dw, ref_dw) < TOL[precision]
+
+
+def test_tc_many_tiles_persistent_loop():
+    """More tiles than SMs: every CTA walks several items through both TMEM accumulator stages."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    A = torch.randn(6, 1100, 200, device=dev)
+    B = torch.randn(6, 520, 200, device=dev)
+    out = _run("bmk,bnk->bmn", A, B, "tf32x3")
+    assert rel_err(out, torch.einsum("bmk,bnk->bmn", A.double(), B.double())) < TOL["tf32x3"]
