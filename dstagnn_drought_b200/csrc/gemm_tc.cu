@@ -25,14 +25,15 @@ namespace dstag {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // 32 x 4 B = one 128-byte swizzle row
-constexpr int TC_A_WARPS = 4, TC_B_WARPS = 4, TC_EPI_WARPS = 4;
-constexpr int TC_THREADS = (TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS + 1) * 32;   // 416
+constexpr int TC_A_WARPS = 4, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue warps 8-11: warp % 4 = TMEM lane quarter
+constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;   // 416
 constexpr int TC_SMEM_BUDGET = 196 * 1024;
 
 struct TcParams {
   dstag_gemm_t g;
   int ntm, ntn, kblocks, kb_per_split, nsplit, total_items;
-  int a_kvec, b_kvec;      // 1: K axis contiguous + 16B aligned -> float4 loads along K
+  int a_mode, b_mode;      // MODE_KVEC / MODE_MVEC / MODE_ROW (see Producer)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -111,11 +112,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1" format):
-// rows are 128 B apart, 8-row groups 1024 B apart (SBO), 16-byte chunks XOR-swizzled by row % 8.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 __device__ __forceinline__ uint32_t swz(int r, int c) {   // byte offset of 16B chunk c of row r
   return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + ((c ^ (r & 7)) << 4));
 }
@@ -148,109 +144,220 @@ __device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo
 }
 
 // ---------------------------------------------------------------------------------------
-// Operand producer: 128 threads fill one ROWS x 32 tile (hi [+ lo] plane) per k-block.
+// Operand producer.  NT threads fill one ROWS x 32 operand tile (hi [+ lo] plane) per k-block,
+// one k-block ahead in registers (the next block's global loads are in flight while the
+// current block is split / swizzled into shared memory).  Three load modes, chosen per launch:
+//   KVEC  K contiguous   : float4 along K  -> K-major  swizzled tile
+//   MVEC  row contiguous : float4 along M/N -> MN-major swizzled tile (no transpose needed:
+//                          tcgen05 kind::tf32 accepts MN-major operands)
+//   ROW   anything else  : scalar gather   -> K-major  swizzled tile
 // ---------------------------------------------------------------------------------------
-template <int ROWS, bool X3>
+enum { MODE_KVEC = 0, MODE_MVEC = 1, MODE_ROW = 2 };
+
+struct KWalk {   // offset of consecutive k indices along a (possibly two-level) axis, no division per step
+  int off, lo, s1, wrap, d1;
+  __device__ __forceinline__ void init(const dstag_axis_t& a, int k) {
+    d1 = a.d1;
+    if (d1 == 1) {
+      off = k * (int)a.s0; s1 = (int)a.s0; wrap = 0; lo = 0;
+    } else {
+      const int hi = k / d1;
+      lo = k - hi * d1;
+      off = hi * (int)a.s0 + lo * (int)a.s1;
+      s1 = (int)a.s1;
+      wrap = (int)a.s0 - (d1 - 1) * (int)a.s1;
+    }
+  }
+  __device__ __forceinline__ void next() {
+    if (d1 == 1) {
+      off += s1;
+    } else {
+      ++lo;
+      const bool w = lo == d1;
+      off += w ? wrap : s1;
+      lo = w ? 0 : lo;
+    }
+  }
+};
+
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+
+template <int ROWS, int NT, bool X3>
 struct Producer {
-  // ROW mode: thread <-> (row, group of consecutive k);  KVEC mode: thread <-> (16B chunk, rows)
-  static constexpr int KG = 128 / ROWS;        // k-groups per row in ROW mode (1, 2, 4)
-  static constexpr int KPT = TC_BK / KG;       // k's per thread in ROW mode (32, 16, 8)
-  static constexpr int RPT = ROWS / 16;        // rows per thread in KVEC mode (8, 4, 2)
+  static constexpr int NV = ROWS * 8 / NT;     // float4 per thread per k-block
+  static constexpr int RB = NT / 8;            // KVEC: rows per pass
+  static constexpr int QPK = ROWS / 4;         // MVEC: row quads per k
+  static constexpr int KGM = NT / QPK;         // MVEC: k groups
+  static constexpr int KPTM = TC_BK / KGM;     // MVEC: k's per thread (== NV)
+  static constexpr int KGR = NT / ROWS;        // ROW : k groups
+  static constexpr int KPTR = TC_BK / KGR;     // ROW : scalars per thread (== 4 NV)
+  static_assert(KPTM == NV && KPTR == 4 * NV && ROWS / RB == NV, "producer tiling mismatch");
 
   const float* base;
   const float* mbase;
   const dstag_axis_t* colax;
   const dstag_axis_t* mcolax;
-  int K, t, lane, kvec;
-  // ROW mode state
-  int ro, mo;
-  bool rok;
-  // KVEC mode state
-  int rov[RPT], mov[RPT];
-  bool rokv[RPT];
+  int K, t, mode;
+  int ro[NV], mo[NV];      // KVEC: one per row;  MVEC / ROW: only [0] used
+  int nvalid[NV];          // KVEC: row valid (0/1);  MVEC [0]: valid rows of the quad (0..4);  ROW [0]: 0/1
 
   __device__ __forceinline__ void begin_item(const float* b, const float* mb, const dstag_axis_t& rowax,
                                              const dstag_axis_t& mrowax, int row0, int limit) {
     base = b;
     mbase = mb;
-    if (kvec) {
+    if (mode == MODE_KVEC) {
       const int rb = t >> 3;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = row0 + rb + 16 * i;
-        rokv[i] = r < limit;
-        rov[i] = rokv[i] ? axoff32(rowax, r) : 0;
-        mov[i] = (mb && rokv[i]) ? axoff32(mrowax, r) : 0;
+      for (int i = 0; i < NV; ++i) {
+        const int r = row0 + rb + RB * i;
+        nvalid[i] = r < limit ? 1 : 0;
+        ro[i] = nvalid[i] ? axoff32(rowax, r) : 0;
+        mo[i] = (mb && nvalid[i]) ? axoff32(mrowax, r) : 0;
       }
+    } else if (mode == MODE_MVEC) {
+      const int r = row0 + 4 * (t % QPK);
+      const int nv = limit - r;
+      nvalid[0] = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+      ro[0] = nvalid[0] ? axoff32(rowax, r) : 0;
+      mo[0] = (mb && nvalid[0]) ? axoff32(mrowax, r) : 0;
     } else {
       const int r = row0 + (t % ROWS);
-      rok = r < limit;
-      ro = rok ? axoff32(rowax, r) : 0;
-      mo = (mb && rok) ? axoff32(mrowax, r) : 0;
+      nvalid[0] = r < limit ? 1 : 0;
+      ro[0] = nvalid[0] ? axoff32(rowax, r) : 0;
+      mo[0] = (mb && nvalid[0]) ? axoff32(mrowax, r) : 0;
     }
   }
 
-  __device__ __forceinline__ void fill(int kb, uint8_t* plane_hi, uint8_t* plane_lo) {
+  // issue the global loads of k-block kb into v[] (values are consumed one k-block later)
+  __device__ __forceinline__ void load(int kb, float4 (&v)[NV]) {
     const int k0 = kb * TC_BK;
-    if (kvec) {
-      const int c = t & 7, rb = t >> 3;
-      const int k = k0 + 4 * c;
-      float4 v[RPT];
+    if (mode == MODE_KVEC) {
+      const int k = k0 + 4 * (t & 7);
       if (k + 3 < K) {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
+        for (int i = 0; i < NV; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rokv[i]) v[i] = __ldg(reinterpret_cast<const float4*>(base + rov[i] + k));
+          if (nvalid[i]) v[i] = __ldg(reinterpret_cast<const float4*>(base + ro[i] + k));
         }
         if (mbase) {
 #pragma unroll
-          for (int i = 0; i < RPT; ++i)
-            if (rokv[i]) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(mbase + mov[i] + k));
-              v[i].x *= m.x; v[i].y *= m.y; v[i].z *= m.z; v[i].w *= m.w;
-            }
+          for (int i = 0; i < NV; ++i)
+            if (nvalid[i]) v[i] = mul4(v[i], __ldg(reinterpret_cast<const float4*>(mbase + mo[i] + k)));
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
+        for (int i = 0; i < NV; ++i) {
           float e[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             e[j] = 0.f;
-            if (rokv[i] && k + j < K) {
-              e[j] = __ldg(base + rov[i] + k + j);
-              if (mbase) e[j] *= __ldg(mbase + mov[i] + k + j);
+            if (nvalid[i] && k + j < K) {
+              e[j] = __ldg(base + ro[i] + k + j);
+              if (mbase) e[j] *= __ldg(mbase + mo[i] + k + j);
             }
           }
           v[i] = make_float4(e[0], e[1], e[2], e[3]);
         }
       }
+    } else if (mode == MODE_MVEC) {
+      const int kf = k0 + (t / QPK) * KPTM;
+      KWalk w, mw;
+      w.init(*colax, kf);
+      if (mbase) mw.init(*mcolax, kf);
+      const int nv = nvalid[0];
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) store_chunk<X3>(plane_hi, plane_lo, swz(rb + 16 * i, c), v[i]);
-    } else {
-      // every lane computes the column offset of one k of this block; broadcast by shuffle
-      const int kl = k0 + lane;
-      const int ko_l = kl < K ? axoff32(*colax, kl) : -1;
-      const int mko_l = (mbase && kl < K) ? axoff32(*mcolax, kl) : -1;
-      const int kg = t / ROWS;
-      float v[KPT];
-#pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const int ko = __shfl_sync(0xffffffffu, ko_l, kg * KPT + j);
-        v[j] = (rok && ko >= 0) ? __ldg(base + ro + ko) : 0.f;
+      for (int j = 0; j < NV; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kf + j < K) {
+          const float* ptr = base + ro[0] + w.off;
+          if (nv == 4) {
+            v[j] = __ldg(reinterpret_cast<const float4*>(ptr));
+          } else {
+            if (nv > 0) v[j].x = __ldg(ptr);
+            if (nv > 1) v[j].y = __ldg(ptr + 1);
+            if (nv > 2) v[j].z = __ldg(ptr + 2);
+          }
+        }
+        w.next();
       }
       if (mbase) {
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-          const int mko = __shfl_sync(0xffffffffu, mko_l, kg * KPT + j);
-          if (rok && mko >= 0) v[j] *= __ldg(mbase + mo + mko);
+        for (int j = 0; j < NV; ++j) {
+          if (kf + j < K) {
+            const float* ptr = mbase + mo[0] + mw.off;
+            if (nv == 4) {
+              v[j] = mul4(v[j], __ldg(reinterpret_cast<const float4*>(ptr)));
+            } else {
+              if (nv > 0) v[j].x *= __ldg(ptr);
+              if (nv > 1) v[j].y *= __ldg(ptr + 1);
+              if (nv > 2) v[j].z *= __ldg(ptr + 2);
+            }
+          }
+          mw.next();
         }
       }
-      const int r = t % ROWS;
+    } else {
+      const int kf = k0 + (t / ROWS) * KPTR;
+      KWalk w, mw;
+      w.init(*colax, kf);
+      if (mbase) mw.init(*mcolax, kf);
+      const bool rok = nvalid[0] != 0;
+      const float* rp = base + ro[0];
 #pragma unroll
-      for (int c = 0; c < KPT / 4; ++c)
-        store_chunk<X3>(plane_hi, plane_lo, swz(r, kg * (KPT / 4) + c),
-                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+      for (int c = 0; c < NV; ++c) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && kf + 4 * c + 0 < K) q.x = __ldg(rp + w.off);
+        w.next();
+        if (rok && kf + 4 * c + 1 < K) q.y = __ldg(rp + w.off);
+        w.next();
+        if (rok && kf + 4 * c + 2 < K) q.z = __ldg(rp + w.off);
+        w.next();
+        if (rok && kf + 4 * c + 3 < K) q.w = __ldg(rp + w.off);
+        w.next();
+        v[c] = q;
+      }
+      if (mbase) {
+        const float* mp = mbase + mo[0];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          if (rok && kf + 4 * c + 0 < K) v[c].x *= __ldg(mp + mw.off);
+          mw.next();
+          if (rok && kf + 4 * c + 1 < K) v[c].y *= __ldg(mp + mw.off);
+          mw.next();
+          if (rok && kf + 4 * c + 2 < K) v[c].z *= __ldg(mp + mw.off);
+          mw.next();
+          if (rok && kf + 4 * c + 3 < K) v[c].w *= __ldg(mp + mw.off);
+          mw.next();
+        }
+      }
+    }
+  }
+
+  // split / swizzle the staged registers into the shared-memory operand tile
+  __device__ __forceinline__ void store(const float4 (&v)[NV], uint8_t* plane_hi, uint8_t* plane_lo) {
+    if (mode == MODE_KVEC) {
+      const int c = t & 7, rb = t >> 3;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) store_chunk<X3>(plane_hi, plane_lo, swz(rb + RB * i, c), v[i]);
+    } else if (mode == MODE_MVEC) {
+      // tf32 MN-major uses the SWIZZLE_128B_BASE32B layout: atoms of 32 rows (one 128 B line) x 4 k
+      // (512 B); inside an atom the 32-byte units of line k are XOR-ed with k % 4.  Atom (ka, mb)
+      // lives at (ka * ROWS/32 + mb) * 512.
+      const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
+      const int mb = mq >> 3, mc = mq & 7;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int kl = kl0 + j, ka = kl >> 2, kr = kl & 3;
+        const uint32_t off = (uint32_t)(((ka * (ROWS / 32) + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) +
+                                        ((mc & 1) << 4));
+        store_chunk<X3>(plane_hi, plane_lo, off, v[j]);
+      }
+    } else {
+      const int r = t % ROWS, c0 = (t / ROWS) * NV;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) store_chunk<X3>(plane_hi, plane_lo, swz(r, c0 + c), v[c]);
     }
   }
 };
@@ -266,6 +373,41 @@ struct TcCfg {
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
+
+// shared-memory matrix descriptors (sm_100 "version 1", SWIZZLE_128B)
+//   K-major : rows 128 B apart, 8-row groups SBO = 1024 B apart; K step of 8 tf32 = +32 B
+//   MN-major (tf32 => SWIZZLE_128B_BASE32B): 32-row x 4-k atoms of 512 B; LBO = 512 B between
+//             row blocks, SBO between k atoms; one K = 8 MMA step spans two atoms
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+
+template <int ROWS, int NT, bool X3, int STAGES, int STAGE_BYTES>
+__device__ __forceinline__ void produce_item(Producer<ROWS, NT, X3>& pr, int kb0, int kb1, uint32_t& it,
+                                             uint8_t* smem, uint32_t plane_off, uint32_t plane_bytes,
+                                             uint64_t* full_bar, uint64_t* empty_bar, int lane) {
+  constexpr int NV = Producer<ROWS, NT, X3>::NV;
+  float4 cur[NV], nxt[NV];
+  pr.load(kb0, cur);
+  for (int kb = kb0; kb < kb1; ++kb, ++it) {
+    if (kb + 1 < kb1) pr.load(kb + 1, nxt);          // next block's loads fly while this one is stored
+    const int s = it % STAGES;
+    const uint32_t ph = (it / STAGES) & 1;
+    if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1);
+    __syncwarp();
+    uint8_t* st = smem + s * STAGE_BYTES + plane_off;
+    pr.store(cur, st, st + plane_bytes);
+    fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar + s);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+  }
+}
 
 template <int BN, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
@@ -293,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -302,15 +444,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp < TC_A_WARPS + TC_B_WARPS) {
     // =============================== producers =========================================
     const bool is_a = warp < TC_A_WARPS;
-    const int t = threadIdx.x & 127;
     uint32_t it = 0;   // running k-block counter across items (stage ring position)
-    Producer<TC_BM, X3> pa;
-    Producer<BN, X3> pb;
-    pa.t = pb.t = t;
-    pa.lane = pb.lane = lane;
+    Producer<TC_BM, TC_A_WARPS * 32, X3> pa;
+    Producer<BN, TC_B_WARPS * 32, X3> pb;
+    pa.t = threadIdx.x;
+    pb.t = threadIdx.x - TC_A_WARPS * 32;
     pa.K = pb.K = g.K;
-    pa.kvec = p.a_kvec;
-    pb.kvec = p.b_kvec;
+    pa.mode = p.a_mode;
+    pb.mode = p.b_mode;
     pa.colax = &g.A.col;
     pa.mcolax = &g.Amul.col;
     pb.colax = &g.B.row;      // B operand: tile rows = n (B.col axis), tile columns = k (B.row axis)
@@ -327,27 +468,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, batch);
         const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, batch) : nullptr;
         pa.begin_item(ab, mb, g.A.row, g.Amul.row, tm * TC_BM, g.M);
+        produce_item<TC_BM, TC_A_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(pa, kb0, kb1, it, smem, 0, Cfg::A_PLANE,
+                                                                          full_bar, empty_bar, lane);
       } else {
         const float* bb = (const float*)g.B.ptr + axoff64(g.B.batch, batch);
         pb.begin_item(bb, nullptr, g.B.col, g.B.col, tn * BN, g.N);
-      }
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        uint8_t* st = smem + s * Cfg::STAGE;
-        if (is_a) pa.fill(kb, st, st + Cfg::A_PLANE);
-        else pb.fill(kb, st + Cfg::PLANES * Cfg::A_PLANE, st + Cfg::PLANES * Cfg::A_PLANE + Cfg::B_PLANE);
-        fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar + s);
+        produce_item<BN, TC_B_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(pb, kb0, kb1, it, smem,
+                                                                       Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE,
+                                                                       full_bar, empty_bar, lane);
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ========================================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
+      const bool a_mn = p.a_mode == MODE_MVEC, b_mn = p.b_mode == MODE_MVEC;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // descriptor advance per K step of 8 (in 16-byte units): +32 B inside the swizzle row (K-major),
+      // one 8-k atom row (MN-major)
+      const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;   // 2 atoms of SBO = ROWS/32 * 512 B
+      const uint64_t b_adv = b_mn ? (uint64_t)((BN / 32) * 1024 >> 4) : 2ull;
       uint32_t it = 0, item = 0;
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
         const int ks = w % p.nsplit;
@@ -363,20 +503,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_wait(full_bar + s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE);
-          const uint64_t a_hi = make_desc(sa);
-          const uint64_t a_lo = make_desc(sa + Cfg::A_PLANE);
-          const uint64_t b_hi = make_desc(sa + Cfg::PLANES * Cfg::A_PLANE);
-          const uint64_t b_lo = make_desc(sa + Cfg::PLANES * Cfg::A_PLANE + Cfg::B_PLANE);
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE;
+          const uint64_t a_hi = a_mn ? make_desc_mn(sa, (TC_BM / 32) * 512) : make_desc_k(sa);
+          const uint64_t a_lo = a_mn ? make_desc_mn(sa + Cfg::A_PLANE, (TC_BM / 32) * 512) : make_desc_k(sa + Cfg::A_PLANE);
+          const uint64_t b_hi = b_mn ? make_desc_mn(sb, (BN / 32) * 512) : make_desc_k(sb);
+          const uint64_t b_lo = b_mn ? make_desc_mn(sb + Cfg::B_PLANE, (BN / 32) * 512) : make_desc_k(sb + Cfg::B_PLANE);
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);     // +32 bytes along K inside the swizzle row
+            const uint64_t aa = a_adv * kk, ba = b_adv * kk;
             const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
             if (X3) {
-              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
-              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              umma_tf32(d_tmem, a_lo + aa, b_hi + ba, idesc, first);
+              umma_tf32(d_tmem, a_hi + aa, b_lo + ba, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + aa, b_hi + ba, idesc, 1u);
             } else {
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              umma_tf32(d_tmem, a_hi + aa, b_hi + ba, idesc, first);
             }
           }
           umma_commit(empty_bar + s);          // stage reusable once these MMAs have read it
@@ -407,7 +548,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const bool c_unit = g.C.col.d1 == 1 && g.C.col.s0 == 1;
       const bool ca_unit = !Ca || (g.Cadd.col.d1 == 1 && g.Cadd.col.s0 == 1);
       const bool cm_unit = !Cm || (g.Cmul.col.d1 == 1 && g.Cmul.col.s0 == 1);
-      mbar_wait(tfull_bar + acc, (item >> 1) & 1);
+      if (lane == 0) mbar_wait(tfull_bar + acc, (item >> 1) & 1);
+      __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
@@ -465,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 12) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -497,6 +639,13 @@ bool gemm_tc_supported(const dstag_gemm_t* g) {
 static bool kvec_ok(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax) {
   if (!o.ptr) return true;
   return kax.d1 == 1 && kax.s0 == 1 && axis_mult4(rowax) && axis_mult4(o.batch) &&
+         (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+}
+
+// rows contiguous (single-level, stride 1), every K / batch stride a multiple of 4, aligned base
+static bool mvec_ok(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax) {
+  if (!o.ptr) return true;
+  return rowax.d1 == 1 && rowax.s0 == 1 && axis_mult4(kax) && axis_mult4(o.batch) &&
          (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
 }
 
@@ -539,8 +688,12 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
   const long long items = (long long)g->batch * p.ntm * p.ntn * p.nsplit;
   DSTAG_CHECK_ARG(items < (1ll << 31), "dstag_gemm(tc): too many tiles");
   p.total_items = (int)items;
-  p.a_kvec = (kvec_ok(g->A, g->A.col, g->A.row) && kvec_ok(g->Amul, g->Amul.col, g->Amul.row)) ? 1 : 0;
-  p.b_kvec = kvec_ok(g->B, g->B.row, g->B.col) ? 1 : 0;
+  if (kvec_ok(g->A, g->A.col, g->A.row) && kvec_ok(g->Amul, g->Amul.col, g->Amul.row)) p.a_mode = MODE_KVEC;
+  else if (mvec_ok(g->A, g->A.col, g->A.row) && mvec_ok(g->Amul, g->Amul.col, g->Amul.row)) p.a_mode = MODE_MVEC;
+  else p.a_mode = MODE_ROW;
+  if (kvec_ok(g->B, g->B.row, g->B.col)) p.b_mode = MODE_KVEC;
+  else if (mvec_ok(g->B, g->B.row, g->B.col)) p.b_mode = MODE_MVEC;
+  else p.b_mode = MODE_ROW;
   const bool x3 = g->precision == DSTAG_PREC_TF32X3;
   if (bn == 128) return x3 ? launch_tc<128, true>(p, stream) : launch_tc<128, false>(p, stream);
   if (bn == 64) return x3 ? launch_tc<64, true>(p, stream) : launch_tc<64, false>(p, stream);
