@@ -4,7 +4,7 @@
 //
 // Persistent, warp-specialised kernel (one CTA per SM, 13 warps):
 //   warps 0-3   A producers   global (any 2-level strided view) -> registers -> [x Amul] ->
-//                             [hi/lo TF32 split] -> 128B-swizzled K-major shared-memory tile
+//                             [hi/lo TF32 split] -> swizzled shared-memory operand tile
 //   warps 4-7   B producers   same for the second operand
 //   warps 8-11  epilogue      TMEM -> registers (tcgen05.ld) -> alpha / Cadd / Cmul / relu ->
 //                             global (store, add or atomic), accumulator double-buffered in TMEM
@@ -14,6 +14,8 @@
 // The operands never need a packed / transposed copy in HBM: the producers read the caller's
 // strides (permuted views, unfolded conv windows, padded leading dimensions) and the Hadamard
 // factor (T_k of cheb_conv_withSAt, model/DSTAGNN_my.py:128) is fused into the operand load.
+// Row-contiguous operands are staged MN-major (tcgen05 kind::tf32 takes either major), so no
+// transpose is ever materialised either.
 //
 // Precision: kind::tf32 keeps 10 mantissa bits of each operand.  DSTAG_PREC_TF32X3 restores
 // fp32-grade accuracy with the classic 3-pass split  a = a_hi + a_lo,  b = b_hi + b_lo,
@@ -25,15 +27,18 @@ namespace dstag {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // 32 x 4 B = one 128-byte swizzle row
-constexpr int TC_A_WARPS = 4, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue warps 8-11: warp % 4 = TMEM lane quarter
+constexpr int TC_A_WARPS = 8, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue warps 12-15: warp % 4 = TMEM lane quarter
 constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
-constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;   // 416
-constexpr int TC_SMEM_BUDGET = 196 * 1024;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;   // 544
+constexpr int TC_SMEM_BUDGET = 196 * 1024;            // operand stages
+constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 32 * 33 * 4;   // per-warp 32 x 33 transpose buffers
+
+enum { MODE_KVEC = 0, MODE_MVEC = 1, MODE_ROWG = 2, MODE_KSC = 3 };
 
 struct TcParams {
   dstag_gemm_t g;
   int ntm, ntn, kblocks, kb_per_split, nsplit, total_items;
-  int a_mode, b_mode;      // MODE_KVEC / MODE_MVEC / MODE_ROW (see Producer)
+  int a_mode, b_mode;      // MODE_* (see Producer)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -48,18 +53,26 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+// Spin on try_wait.  `backoff_ns` > 0 inserts a nanosleep between polls: used for the long epilogue
+// wait so that the poller does not steal issue slots from the producer warps on its SMSP.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(addr), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns) {
+  const uint32_t addr = smem_u32(bar);
+  while (!mbar_try_wait(addr, parity)) {
+    if (backoff_ns) __nanosleep(backoff_ns);
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -112,7 +125,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t swz(int r, int c) {   // byte offset of 16B chunk c of row r
+// shared-memory matrix descriptors (sm_100 "version 1")
+//   K-major, SWIZZLE_128B: rows 128 B apart, 8-row groups SBO = 1024 B apart, 16-byte chunks XOR-ed
+//             with row % 8; a K step of 8 tf32 is +32 B inside the row.
+//   MN-major (tf32 => SWIZZLE_128B_BASE32B): atoms of 32 rows (one 128 B line) x 4 k (512 B), 32-byte
+//             units of line k XOR-ed with k % 4; LBO = 512 B between row blocks, SBO between k atoms;
+//             one K = 8 MMA step spans two atoms.
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+__device__ __forceinline__ uint32_t swz(int r, int c) {   // K-major: byte offset of 16B chunk c of row r
   return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + ((c ^ (r & 7)) << 4));
 }
 
@@ -127,55 +153,33 @@ __device__ __forceinline__ long long axoff64(const dstag_axis_t& a, int idx) {
   return (long long)hi * a.s0 + (long long)(idx - hi * a.d1) * a.s1;
 }
 
-template <bool X3>
-__device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float4 v) {
-  if (X3) {
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(plane_hi + off) = h;
-    *reinterpret_cast<float4*>(plane_lo + off) = l;
-  } else {
-    *reinterpret_cast<float4*>(plane_hi + off) = v;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Operand producer.  NT threads fill one ROWS x 32 operand tile (hi [+ lo] plane) per k-block,
-// one k-block ahead in registers (the next block's global loads are in flight while the
-// current block is split / swizzled into shared memory).  Three load modes, chosen per launch:
-//   KVEC  K contiguous   : float4 along K  -> K-major  swizzled tile
-//   MVEC  row contiguous : float4 along M/N -> MN-major swizzled tile (no transpose needed:
-//                          tcgen05 kind::tf32 accepts MN-major operands)
-//   ROW   anything else  : scalar gather   -> K-major  swizzled tile
-// ---------------------------------------------------------------------------------------
-enum { MODE_KVEC = 0, MODE_MVEC = 1, MODE_ROW = 2 };
-
-struct KWalk {   // offset of consecutive k indices along a (possibly two-level) axis, no division per step
-  int off, lo, s1, wrap, d1;
-  __device__ __forceinline__ void init(const dstag_axis_t& a, int k) {
+// Offsets of idx0, idx0 + step, idx0 + 2 step, ... along a (possibly two-level) axis with one
+// division at init() and none per step.
+struct Walk {
+  int off, lo, d1, st_off, st_lo, wrap;
+  __device__ __forceinline__ void init(const dstag_axis_t& a, int idx0, int step) {
     d1 = a.d1;
     if (d1 == 1) {
-      off = k * (int)a.s0; s1 = (int)a.s0; wrap = 0; lo = 0;
+      off = idx0 * (int)a.s0;
+      st_off = step * (int)a.s0;
+      lo = st_lo = wrap = 0;
     } else {
-      const int hi = k / d1;
-      lo = k - hi * d1;
+      const int hi = idx0 / d1;
+      lo = idx0 - hi * d1;
       off = hi * (int)a.s0 + lo * (int)a.s1;
-      s1 = (int)a.s1;
-      wrap = (int)a.s0 - (d1 - 1) * (int)a.s1;
+      const int sh = step / d1;
+      st_lo = step - sh * d1;
+      st_off = sh * (int)a.s0 + st_lo * (int)a.s1;
+      wrap = (int)a.s0 - d1 * (int)a.s1;
     }
   }
   __device__ __forceinline__ void next() {
-    if (d1 == 1) {
-      off += s1;
-    } else {
-      ++lo;
-      const bool w = lo == d1;
-      off += w ? wrap : s1;
-      lo = w ? 0 : lo;
+    off += st_off;
+    if (d1 != 1) {
+      lo += st_lo;
+      const bool c = lo >= d1;
+      lo -= c ? d1 : 0;
+      off += c ? wrap : 0;
     }
   }
 };
@@ -183,95 +187,128 @@ struct KWalk {   // offset of consecutive k indices along a (possibly two-level)
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-template <int ROWS, int NT, bool X3>
+template <bool X3>
+__device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float4 v) {
+  if (X3) {
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(plane_hi + off) = h;
+    *reinterpret_cast<float4*>(plane_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  } else {
+    *reinterpret_cast<float4*>(plane_hi + off) = v;
+  }
+}
+template <bool X3>
+__device__ __forceinline__ void store_scalar(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float v) {
+  if (X3) {
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float*>(plane_hi + off) = h;
+    *reinterpret_cast<float*>(plane_lo + off) = v - h;
+  } else {
+    *reinterpret_cast<float*>(plane_hi + off) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Operand producer.  NT threads fill one ROWS x 32 operand tile (hi [+ lo] plane) per k-block,
+// one k-block ahead in registers (the next block's global loads are in flight while the
+// current block is split / swizzled into shared memory).  Load modes, chosen per launch:
+//   KVEC  K contiguous, 16B aligned   : float4 along K   -> K-major tile,  thread = (chunk, rows)
+//   MVEC  rows contiguous, aligned    : float4 along M/N -> MN-major tile, thread = (row quad, k's)
+//   KSC   K contiguous, unaligned     : scalar, lanes along K (coalesced)  -> K-major tile
+//   ROWG  rows contiguous / anything  : scalar, lanes along rows           -> K-major tile
+// ---------------------------------------------------------------------------------------
+template <int ROWS, int NT, bool X3, bool MUL>
 struct Producer {
-  static constexpr int NV = ROWS * 8 / NT;     // float4 per thread per k-block
+  static constexpr int NV = ROWS * 8 / NT;     // float4 (or 4 scalars) per thread per k-block
+  static constexpr int NM = MUL ? NV : 1;      // multiplier registers (unused without a Hadamard factor)
   static constexpr int RB = NT / 8;            // KVEC: rows per pass
   static constexpr int QPK = ROWS / 4;         // MVEC: row quads per k
-  static constexpr int KGM = NT / QPK;         // MVEC: k groups
-  static constexpr int KPTM = TC_BK / KGM;     // MVEC: k's per thread (== NV)
-  static constexpr int KGR = NT / ROWS;        // ROW : k groups
-  static constexpr int KPTR = TC_BK / KGR;     // ROW : scalars per thread (== 4 NV)
-  static_assert(KPTM == NV && KPTR == 4 * NV && ROWS / RB == NV, "producer tiling mismatch");
+  static constexpr int KPTM = TC_BK / (NT / QPK);   // MVEC: k's per thread (== NV)
+  static constexpr int KPTR = TC_BK / (NT / ROWS);  // ROWG: scalars per thread (== 4 NV)
+  static constexpr int NW = NT / 32;           // KSC : warps; rows per thread = ROWS / NW (== 4 NV)
+  static_assert(KPTM == NV && KPTR == 4 * NV && ROWS / RB == NV && ROWS / NW == 4 * NV, "producer tiling mismatch");
 
   const float* base;
   const float* mbase;
+  const dstag_axis_t* rowax;
   const dstag_axis_t* colax;
+  const dstag_axis_t* mrowax;
   const dstag_axis_t* mcolax;
-  int K, t, mode;
-  int ro[NV], mo[NV];      // KVEC: one per row;  MVEC / ROW: only [0] used
-  int nvalid[NV];          // KVEC: row valid (0/1);  MVEC [0]: valid rows of the quad (0..4);  ROW [0]: 0/1
+  int K, t, mode, row0, limit;
+  int r_off, r_lo, m_off, m_lo;   // row walk start (this thread's first row) for A and Amul
 
-  __device__ __forceinline__ void begin_item(const float* b, const float* mb, const dstag_axis_t& rowax,
-                                             const dstag_axis_t& mrowax, int row0, int limit) {
-    base = b;
-    mbase = mb;
-    if (mode == MODE_KVEC) {
-      const int rb = t >> 3;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int r = row0 + rb + RB * i;
-        nvalid[i] = r < limit ? 1 : 0;
-        ro[i] = nvalid[i] ? axoff32(rowax, r) : 0;
-        mo[i] = (mb && nvalid[i]) ? axoff32(mrowax, r) : 0;
-      }
-    } else if (mode == MODE_MVEC) {
-      const int r = row0 + 4 * (t % QPK);
-      const int nv = limit - r;
-      nvalid[0] = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
-      ro[0] = nvalid[0] ? axoff32(rowax, r) : 0;
-      mo[0] = (mb && nvalid[0]) ? axoff32(mrowax, r) : 0;
-    } else {
-      const int r = row0 + (t % ROWS);
-      nvalid[0] = r < limit ? 1 : 0;
-      ro[0] = nvalid[0] ? axoff32(rowax, r) : 0;
-      mo[0] = (mb && nvalid[0]) ? axoff32(mrowax, r) : 0;
-    }
+  __device__ __forceinline__ int first_row() const {
+    if (mode == MODE_KVEC) return row0 + (t >> 3);
+    if (mode == MODE_MVEC) return row0 + 4 * (t % QPK);
+    if (mode == MODE_KSC) return row0 + (t >> 5);
+    return row0 + (t % ROWS);
+  }
+  __device__ __forceinline__ int row_step() const {
+    return mode == MODE_KVEC ? RB : (mode == MODE_KSC ? NW : 0);
   }
 
-  // issue the global loads of k-block kb into v[] (values are consumed one k-block later)
-  __device__ __forceinline__ void load(int kb, float4 (&v)[NV]) {
+  __device__ __forceinline__ void begin_item(const float* b, const float* mb, int r0, int lim) {
+    base = b;
+    mbase = MUL ? mb : nullptr;
+    row0 = r0;
+    limit = lim;
+    const int fr = first_row();
+    Walk w;
+    w.init(*rowax, fr < lim ? fr : 0, 0);
+    r_off = w.off; r_lo = w.lo;
+    if (MUL && mb) {
+      w.init(*mrowax, fr < lim ? fr : 0, 0);
+      m_off = w.off; m_lo = w.lo;
+    }
+  }
+  __device__ __forceinline__ void row_walk(Walk& w, const dstag_axis_t& ax, int off, int lo) const {
+    w.init(ax, 0, row_step());
+    w.off = off;
+    w.lo = lo;
+  }
+
+  // One operand stream (the tile itself, or its Hadamard factor): issue the global loads of
+  // k-block kb into v[].  Nothing here consumes a loaded value, so the loads stay in flight.
+  template <int N>
+  __device__ __forceinline__ void load_stream(int kb, float4 (&v)[N], const float* bp, const dstag_axis_t& rax,
+                                              const dstag_axis_t& cax, int roff, int rlo) const {
+    static_assert(N == NV, "stream width");
     const int k0 = kb * TC_BK;
+    const int fr = first_row();
     if (mode == MODE_KVEC) {
       const int k = k0 + 4 * (t & 7);
+      Walk rw;
+      row_walk(rw, rax, roff, rlo);
       if (k + 3 < K) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (nvalid[i]) v[i] = __ldg(reinterpret_cast<const float4*>(base + ro[i] + k));
-        }
-        if (mbase) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (nvalid[i]) v[i] = mul4(v[i], __ldg(reinterpret_cast<const float4*>(mbase + mo[i] + k)));
+          if (fr + RB * i < limit) v[i] = __ldg(reinterpret_cast<const float4*>(bp + rw.off + k));
+          rw.next();
         }
       } else {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           float e[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            e[j] = 0.f;
-            if (nvalid[i] && k + j < K) {
-              e[j] = __ldg(base + ro[i] + k + j);
-              if (mbase) e[j] *= __ldg(mbase + mo[i] + k + j);
-            }
-          }
+          for (int j = 0; j < 4; ++j) e[j] = (fr + RB * i < limit && k + j < K) ? __ldg(bp + rw.off + k + j) : 0.f;
           v[i] = make_float4(e[0], e[1], e[2], e[3]);
+          rw.next();
         }
       }
     } else if (mode == MODE_MVEC) {
       const int kf = k0 + (t / QPK) * KPTM;
-      KWalk w, mw;
-      w.init(*colax, kf);
-      if (mbase) mw.init(*mcolax, kf);
-      const int nv = nvalid[0];
+      Walk w;
+      w.init(cax, kf, 1);
+      int nv = limit - fr;
+      nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kf + j < K) {
-          const float* ptr = base + ro[0] + w.off;
+          const float* ptr = bp + roff + w.off;
           if (nv == 4) {
             v[j] = __ldg(reinterpret_cast<const float4*>(ptr));
           } else {
@@ -282,69 +319,63 @@ struct Producer {
         }
         w.next();
       }
-      if (mbase) {
+    } else if (mode == MODE_KSC) {
+      // lane <-> k (32 consecutive k: one coalesced line per row), thread walks 4*NV rows
+      const int k = k0 + (t & 31);
+      const bool kok = k < K;
+      const int ko = kok ? axoff32(cax, k) : 0;
+      Walk rw;
+      row_walk(rw, rax, roff, rlo);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          if (kf + j < K) {
-            const float* ptr = mbase + mo[0] + mw.off;
-            if (nv == 4) {
-              v[j] = mul4(v[j], __ldg(reinterpret_cast<const float4*>(ptr)));
-            } else {
-              if (nv > 0) v[j].x *= __ldg(ptr);
-              if (nv > 1) v[j].y *= __ldg(ptr + 1);
-              if (nv > 2) v[j].z *= __ldg(ptr + 2);
-            }
-          }
-          mw.next();
+      for (int c = 0; c < NV; ++c) {
+        float e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          e[j] = (kok && fr + NW * (4 * c + j) < limit) ? __ldg(bp + rw.off + ko) : 0.f;
+          rw.next();
         }
+        v[c] = make_float4(e[0], e[1], e[2], e[3]);
       }
     } else {
       const int kf = k0 + (t / ROWS) * KPTR;
-      KWalk w, mw;
-      w.init(*colax, kf);
-      if (mbase) mw.init(*mcolax, kf);
-      const bool rok = nvalid[0] != 0;
-      const float* rp = base + ro[0];
+      Walk w;
+      w.init(cax, kf, 1);
+      const bool rok = fr < limit;
+      const float* rp = bp + roff;
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && kf + 4 * c + 0 < K) q.x = __ldg(rp + w.off);
-        w.next();
-        if (rok && kf + 4 * c + 1 < K) q.y = __ldg(rp + w.off);
-        w.next();
-        if (rok && kf + 4 * c + 2 < K) q.z = __ldg(rp + w.off);
-        w.next();
-        if (rok && kf + 4 * c + 3 < K) q.w = __ldg(rp + w.off);
-        w.next();
-        v[c] = q;
-      }
-      if (mbase) {
-        const float* mp = mbase + mo[0];
+        float e[4];
 #pragma unroll
-        for (int c = 0; c < NV; ++c) {
-          if (rok && kf + 4 * c + 0 < K) v[c].x *= __ldg(mp + mw.off);
-          mw.next();
-          if (rok && kf + 4 * c + 1 < K) v[c].y *= __ldg(mp + mw.off);
-          mw.next();
-          if (rok && kf + 4 * c + 2 < K) v[c].z *= __ldg(mp + mw.off);
-          mw.next();
-          if (rok && kf + 4 * c + 3 < K) v[c].w *= __ldg(mp + mw.off);
-          mw.next();
+        for (int j = 0; j < 4; ++j) {
+          e[j] = (rok && kf + 4 * c + j < K) ? __ldg(rp + w.off) : 0.f;
+          w.next();
         }
+        v[c] = make_float4(e[0], e[1], e[2], e[3]);
       }
     }
   }
 
-  // split / swizzle the staged registers into the shared-memory operand tile
-  __device__ __forceinline__ void store(const float4 (&v)[NV], uint8_t* plane_hi, uint8_t* plane_lo) {
+  __device__ __forceinline__ void load(int kb, float4 (&v)[NV], float4 (&m)[NM]) const {
+    load_stream<NV>(kb, v, base, *rowax, *colax, r_off, r_lo);
+    if constexpr (MUL) {
+      if (mbase) load_stream<NV>(kb, m, mbase, *mrowax, *mcolax, m_off, m_lo);
+    }
+  }
+
+  // [x Hadamard factor], split and swizzle the staged registers into the shared-memory tile
+  __device__ __forceinline__ void store(float4 (&v)[NV], const float4 (&m)[NM], uint8_t* plane_hi,
+                                        uint8_t* plane_lo) const {
+    if constexpr (MUL) {
+      if (mbase) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = mul4(v[i], m[i]);
+      }
+    }
     if (mode == MODE_KVEC) {
       const int c = t & 7, rb = t >> 3;
 #pragma unroll
       for (int i = 0; i < NV; ++i) store_chunk<X3>(plane_hi, plane_lo, swz(rb + RB * i, c), v[i]);
     } else if (mode == MODE_MVEC) {
-      // tf32 MN-major uses the SWIZZLE_128B_BASE32B layout: atoms of 32 rows (one 128 B line) x 4 k
-      // (512 B); inside an atom the 32-byte units of line k are XOR-ed with k % 4.  Atom (ka, mb)
-      // lives at (ka * ROWS/32 + mb) * 512.
       const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
       const int mb = mq >> 3, mc = mq & 7;
 #pragma unroll
@@ -353,6 +384,17 @@ struct Producer {
         const uint32_t off = (uint32_t)(((ka * (ROWS / 32) + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) +
                                         ((mc & 1) << 4));
         store_chunk<X3>(plane_hi, plane_lo, off, v[j]);
+      }
+    } else if (mode == MODE_KSC) {
+      const int kl = t & 31, w = t >> 5;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const float e[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = w + NW * (4 * c + j);
+          store_scalar<X3>(plane_hi, plane_lo, swz(r, kl >> 2) + ((kl & 3) << 2), e[j]);
+        }
       }
     } else {
       const int r = t % ROWS, c0 = (t / ROWS) * NV;
@@ -370,51 +412,52 @@ struct TcCfg {
   static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
   static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int EPI_OFF = BAR_OFF + 256;
+  static constexpr int SMEM = EPI_OFF + TC_EPI_SMEM + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-// shared-memory matrix descriptors (sm_100 "version 1", SWIZZLE_128B)
-//   K-major : rows 128 B apart, 8-row groups SBO = 1024 B apart; K step of 8 tf32 = +32 B
-//   MN-major (tf32 => SWIZZLE_128B_BASE32B): 32-row x 4-k atoms of 512 B; LBO = 512 B between
-//             row blocks, SBO between k atoms; one K = 8 MMA step spans two atoms
-__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
-         (1ull << 61);
-}
-
-template <int ROWS, int NT, bool X3, int STAGES, int STAGE_BYTES>
-__device__ __forceinline__ void produce_item(Producer<ROWS, NT, X3>& pr, int kb0, int kb1, uint32_t& it,
+template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES>
+__device__ __forceinline__ void produce_item(Producer<ROWS, NT, X3, MUL>& pr, int kb0, int kb1, uint32_t& it,
                                              uint8_t* smem, uint32_t plane_off, uint32_t plane_bytes,
                                              uint64_t* full_bar, uint64_t* empty_bar, int lane) {
-  constexpr int NV = Producer<ROWS, NT, X3>::NV;
-  float4 cur[NV], nxt[NV];
-  pr.load(kb0, cur);
-  for (int kb = kb0; kb < kb1; ++kb, ++it) {
-    if (kb + 1 < kb1) pr.load(kb + 1, nxt);          // next block's loads fly while this one is stored
-    const int s = it % STAGES;
-    const uint32_t ph = (it / STAGES) & 1;
-    if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1);
-    __syncwarp();
-    uint8_t* st = smem + s * STAGE_BYTES + plane_off;
-    pr.store(cur, st, st + plane_bytes);
-    fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar + s);
+  using P = Producer<ROWS, NT, X3, MUL>;
+  float4 cur[P::NV], nxt[P::NV], curm[P::NM], nxtm[P::NM];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+  for (int i = 0; i < P::NV; ++i) cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  // software pipeline with a single load site: iteration kb issues the loads of block kb + 1 and
+  // then (from kb0 on) stores block kb, so global latency overlaps the split / swizzle / barrier work
+#pragma unroll 1
+  for (int kb = kb0 - 1; kb < kb1; ++kb) {
+    if (kb + 1 < kb1) pr.load(kb + 1, nxt, nxtm);
+    if (kb >= kb0) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1, 0);
+      __syncwarp();
+      uint8_t* st = smem + s * STAGE_BYTES + plane_off;
+      pr.store(cur, curm, st, st + plane_bytes);
+      fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar + s);
+      ++it;
+    }
+#pragma unroll
+    for (int i = 0; i < P::NV; ++i) cur[i] = nxt[i];
+#pragma unroll
+    for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i];
   }
 }
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool AMUL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BN, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* full_bar = bars;                          // [STAGES] producers -> MMA
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES] MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2] MMA (commit) -> epilogue
@@ -445,35 +488,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // =============================== producers =========================================
     const bool is_a = warp < TC_A_WARPS;
     uint32_t it = 0;   // running k-block counter across items (stage ring position)
-    Producer<TC_BM, TC_A_WARPS * 32, X3> pa;
-    Producer<BN, TC_B_WARPS * 32, X3> pb;
-    pa.t = threadIdx.x;
-    pb.t = threadIdx.x - TC_A_WARPS * 32;
-    pa.K = pb.K = g.K;
-    pa.mode = p.a_mode;
-    pb.mode = p.b_mode;
-    pa.colax = &g.A.col;
-    pa.mcolax = &g.Amul.col;
-    pb.colax = &g.B.row;      // B operand: tile rows = n (B.col axis), tile columns = k (B.row axis)
-    pb.mcolax = &g.B.row;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-      int q = w;
-      const int ks = q % p.nsplit; q /= p.nsplit;
-      const int tn = q % p.ntn; q /= p.ntn;
-      const int tm = q % p.ntm;
-      const int batch = q / p.ntm;
-      const int kb0 = ks * p.kb_per_split;
-      const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-      if (is_a) {
+    if (is_a) {
+      Producer<TC_BM, TC_A_WARPS * 32, X3, AMUL> pa;
+      pa.t = threadIdx.x;
+      pa.K = g.K;
+      pa.mode = p.a_mode;
+      pa.rowax = &g.A.row; pa.colax = &g.A.col;
+      pa.mrowax = &g.Amul.row; pa.mcolax = &g.Amul.col;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        int q = w;
+        const int ks = q % p.nsplit; q /= p.nsplit;
+        q /= p.ntn;
+        const int tm = q % p.ntm;
+        const int batch = q / p.ntm;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, batch);
         const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, batch) : nullptr;
-        pa.begin_item(ab, mb, g.A.row, g.Amul.row, tm * TC_BM, g.M);
-        produce_item<TC_BM, TC_A_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(pa, kb0, kb1, it, smem, 0, Cfg::A_PLANE,
+        pa.begin_item(ab, mb, tm * TC_BM, g.M);
+        produce_item<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE>(pa, kb0, kb1, it, smem, 0, Cfg::A_PLANE,
                                                                           full_bar, empty_bar, lane);
-      } else {
+      }
+    } else {
+      Producer<BN, TC_B_WARPS * 32, X3, false> pb;
+      pb.t = threadIdx.x - TC_A_WARPS * 32;
+      pb.K = g.K;
+      pb.mode = p.b_mode;
+      pb.rowax = &g.B.col; pb.colax = &g.B.row;    // B tile rows = n (B.col axis), tile columns = k (B.row axis)
+      pb.mrowax = &g.B.col; pb.mcolax = &g.B.row;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        int q = w;
+        const int ks = q % p.nsplit; q /= p.nsplit;
+        const int tn = q % p.ntn; q /= p.ntn;
+        const int batch = q / p.ntm;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const float* bb = (const float*)g.B.ptr + axoff64(g.B.batch, batch);
-        pb.begin_item(bb, nullptr, g.B.col, g.B.col, tn * BN, g.N);
-        produce_item<BN, TC_B_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(pb, kb0, kb1, it, smem,
+        pb.begin_item(bb, nullptr, tn * BN, g.N);
+        produce_item<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE>(pb, kb0, kb1, it, smem,
                                                                        Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE,
                                                                        full_bar, empty_bar, lane);
       }
@@ -484,9 +536,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const bool a_mn = p.a_mode == MODE_MVEC, b_mn = p.b_mode == MODE_MVEC;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      // descriptor advance per K step of 8 (in 16-byte units): +32 B inside the swizzle row (K-major),
-      // one 8-k atom row (MN-major)
-      const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;   // 2 atoms of SBO = ROWS/32 * 512 B
+      // descriptor advance per K step of 8 (16-byte units): +32 B inside the swizzle row (K-major),
+      // two 4-k atoms of SBO = ROWS/32 * 512 B each (MN-major)
+      const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;
       const uint64_t b_adv = b_mn ? (uint64_t)((BN / 32) * 1024 >> 4) : 2ull;
       uint32_t it = 0, item = 0;
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
@@ -494,13 +546,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const uint32_t acc = item & 1;
-        mbar_wait(tempty_bar + acc, ((item >> 1) & 1) ^ 1);
+        mbar_wait(tempty_bar + acc, ((item >> 1) & 1) ^ 1, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
-          mbar_wait(full_bar + s, ph);
+          mbar_wait(full_bar + s, ph, 0);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE);
           const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE;
@@ -528,6 +580,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else {
     // =============================== epilogue ==========================================
     const int q4 = warp & 3;                   // TMEM lane quarter this warp may access
+    float* tbuf = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + q4 * (32 * 33);
+    const bool c_unit = g.C.col.d1 == 1 && g.C.col.s0 == 1;
+    const bool ca_unit = !g.Cadd.ptr || (g.Cadd.col.d1 == 1 && g.Cadd.col.s0 == 1);
+    const bool cm_unit = !g.Cmul.ptr || (g.Cmul.col.d1 == 1 && g.Cmul.col.s0 == 1);
     uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
       int q = w;
@@ -538,17 +594,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t acc = item & 1;
       const int m = tm * TC_BM + q4 * 32 + lane;
       const bool mok = m < g.M;
-      float* C = (float*)g.C.ptr + axoff64(g.C.batch, batch) + (mok ? axoff64(g.C.row, m) : 0);
-      const float* Ca = (g.Cadd.ptr && ks == 0)
-                            ? (const float*)g.Cadd.ptr + axoff64(g.Cadd.batch, batch) + (mok ? axoff64(g.Cadd.row, m) : 0)
-                            : nullptr;
-      const float* Cm = g.Cmul.ptr
-                            ? (const float*)g.Cmul.ptr + axoff64(g.Cmul.batch, batch) + (mok ? axoff64(g.Cmul.row, m) : 0)
-                            : nullptr;
-      const bool c_unit = g.C.col.d1 == 1 && g.C.col.s0 == 1;
-      const bool ca_unit = !Ca || (g.Cadd.col.d1 == 1 && g.Cadd.col.s0 == 1);
-      const bool cm_unit = !Cm || (g.Cmul.col.d1 == 1 && g.Cmul.col.s0 == 1);
-      if (lane == 0) mbar_wait(tfull_bar + acc, (item >> 1) & 1);
+      float* Cb = (float*)g.C.ptr + axoff64(g.C.batch, batch);
+      const float* Cab = (g.Cadd.ptr && ks == 0) ? (const float*)g.Cadd.ptr + axoff64(g.Cadd.batch, batch) : nullptr;
+      const float* Cmb = g.Cmul.ptr ? (const float*)g.Cmul.ptr + axoff64(g.Cmul.batch, batch) : nullptr;
+      const int c_ro = mok ? axoff32(g.C.row, m) : 0;
+      const int ca_ro = (Cab && mok) ? axoff32(g.Cadd.row, m) : 0;
+      const int cm_ro = (Cmb && mok) ? axoff32(g.Cmul.row, m) : 0;
+      float* C = Cb + c_ro;
+      const float* Ca = Cab ? Cab + ca_ro : nullptr;
+      const float* Cm = Cmb ? Cmb + cm_ro : nullptr;
+      if (lane == 0) mbar_wait(tfull_bar + acc, (item >> 1) & 1, 1000);
       __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
       tc_fence_after();
 #pragma unroll 1
@@ -556,41 +611,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         float v[32];
         tmem_ld32(tmem_base + acc * BN + cc * 32 + ((uint32_t)(q4 * 32) << 16), v);
         const int n0 = tn * BN + cc * 32;
-        if (!mok || n0 >= g.N) continue;
-        const bool vec = c_unit && ca_unit && cm_unit && g.accumulate != DSTAG_ACC_ATOMIC && (n0 + 32 <= g.N) &&
-                         ((reinterpret_cast<uintptr_t>(C + n0) & 15) == 0) &&
-                         (!Ca || (reinterpret_cast<uintptr_t>(Ca + n0) & 15) == 0) &&
-                         (!Cm || (reinterpret_cast<uintptr_t>(Cm + n0) & 15) == 0);
+        if (n0 >= g.N) continue;                       // warp-uniform
+        const bool full = n0 + 32 <= g.N;
+        // (a) row-contiguous, 16B-aligned output: every thread streams its own row with float4
+        bool vec = c_unit && ca_unit && cm_unit && g.accumulate != DSTAG_ACC_ATOMIC && full &&
+                   ((reinterpret_cast<uintptr_t>(C + n0) & 15) == 0) &&
+                   (!Ca || (reinterpret_cast<uintptr_t>(Ca + n0) & 15) == 0) &&
+                   (!Cm || (reinterpret_cast<uintptr_t>(Cm + n0) & 15) == 0);
+        vec = __all_sync(0xffffffffu, vec || !mok);
         if (vec) {
+          if (mok) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(g.alpha * v[j], g.alpha * v[j + 1], g.alpha * v[j + 2], g.alpha * v[j + 3]);
-            if (Ca) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(Ca + n0 + j));
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(g.alpha * v[j], g.alpha * v[j + 1], g.alpha * v[j + 2], g.alpha * v[j + 3]);
+              if (Ca) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(Ca + n0 + j));
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              if (Cm) o = mul4(o, __ldg(reinterpret_cast<const float4*>(Cm + n0 + j)));
+              if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              float4* dst = reinterpret_cast<float4*>(C + n0 + j);
+              if (g.accumulate == DSTAG_ACC_ADD) {
+                const float4 old = *dst;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *dst = o;
             }
-            if (Cm) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(Cm + n0 + j));
-              o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
-            }
-            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            float4* dst = reinterpret_cast<float4*>(C + n0 + j);
-            if (g.accumulate == DSTAG_ACC_ADD) {
-              const float4 old = *dst;
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *dst = o;
           }
-        } else {
+        } else if (c_unit && ca_unit && cm_unit) {
+          // (b) row-contiguous but unaligned / narrow / atomic: transpose the 32 x 32 block through
+          //     shared memory so that consecutive lanes touch consecutive columns (coalesced)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int n = n0 + lane;
+          const bool nok = n < g.N;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int mr = tm * TC_BM + q4 * 32 + rr;
+            const int ro = __shfl_sync(0xffffffffu, c_ro, rr);
+            const int rao = __shfl_sync(0xffffffffu, ca_ro, rr);
+            const int rmo = __shfl_sync(0xffffffffu, cm_ro, rr);
+            if (mr < g.M && nok) {
+              float o = g.alpha * tbuf[rr * 33 + lane];
+              if (Cab) o += __ldg(Cab + rao + n);
+              if (Cmb) o *= __ldg(Cmb + rmo + n);
+              if (g.relu) o = fmaxf(o, 0.f);
+              float* dst = Cb + ro + n;
+              if (g.accumulate == DSTAG_ACC_STORE) *dst = o;
+              else if (g.accumulate == DSTAG_ACC_ADD) *dst += o;
+              else atomicAdd(dst, o);
+            }
+          }
+          __syncwarp();
+        } else if (mok) {
+          // (c) column-strided output (e.g. M-contiguous conv layouts): lanes walk rows
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
             if (n < g.N) {
               float o = g.alpha * v[j];
-              if (Ca) o += __ldg(Ca + axoff64(g.Cadd.col, n));
-              if (Cm) o *= __ldg(Cm + axoff64(g.Cmul.col, n));
+              if (Ca) o += __ldg(Ca + axoff32(g.Cadd.col, n));
+              if (Cm) o *= __ldg(Cm + axoff32(g.Cmul.col, n));
               if (g.relu) o = fmaxf(o, 0.f);
-              float* dst = C + axoff64(g.C.col, n);
+              float* dst = C + axoff32(g.C.col, n);
               if (g.accumulate == DSTAG_ACC_STORE) *dst = o;
               else if (g.accumulate == DSTAG_ACC_ADD) *dst += o;
               else atomicAdd(dst, o);
@@ -620,11 +704,13 @@ static long long axis_extent(const dstag_axis_t& a, long long n) {   // max offs
 }
 static bool axis_nonneg(const dstag_axis_t& a) { return a.s0 >= 0 && (a.d1 == 1 || a.s1 >= 0); }
 static bool axis_mult4(const dstag_axis_t& a) { return a.s0 % 4 == 0 && (a.d1 == 1 || a.s1 % 4 == 0); }
+static long long inner_stride(const dstag_axis_t& a) { return a.d1 == 1 ? a.s0 : a.s1; }
 
 static bool operand_fits32(const dstag_operand_t& o, long long nrow, long long ncol) {
   if (!o.ptr) return true;
   if (!axis_nonneg(o.batch) || !axis_nonneg(o.row) || !axis_nonneg(o.col)) return false;
-  return axis_extent(o.row, nrow) + axis_extent(o.col, ncol) < (1ll << 31) - 64;
+  // Walk keeps s0 - d1 * s1 and step products in 32 bits as well
+  return axis_extent(o.row, nrow) + axis_extent(o.col, ncol) < (1ll << 30);
 }
 
 bool gemm_tc_supported(const dstag_gemm_t* g) {
@@ -635,28 +721,34 @@ bool gemm_tc_supported(const dstag_gemm_t* g) {
          operand_fits32(g->Cadd, g->M, g->N) && operand_fits32(g->Cmul, g->M, g->N);
 }
 
-// K contiguous and every other stride a multiple of 4 elements on a 16-byte aligned base
-static bool kvec_ok(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax) {
-  if (!o.ptr) return true;
-  return kax.d1 == 1 && kax.s0 == 1 && axis_mult4(rowax) && axis_mult4(o.batch) &&
-         (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+static bool aligned16(const dstag_operand_t& o) {
+  return (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && axis_mult4(o.batch);
 }
-
-// rows contiguous (single-level, stride 1), every K / batch stride a multiple of 4, aligned base
-static bool mvec_ok(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax) {
-  if (!o.ptr) return true;
-  return rowax.d1 == 1 && rowax.s0 == 1 && axis_mult4(kax) && axis_mult4(o.batch) &&
-         (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0;
+// pick the cheapest load mode an operand (and its optional Hadamard factor) admits
+static int pick_mode(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax,
+                     const dstag_operand_t* m, const dstag_axis_t* mkax, const dstag_axis_t* mrowax) {
+  const bool has_m = m && m->ptr;
+  auto kvec = [](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
+    return k.d1 == 1 && k.s0 == 1 && axis_mult4(r) && aligned16(x);
+  };
+  auto mvec = [](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
+    return r.d1 == 1 && r.s0 == 1 && axis_mult4(k) && aligned16(x);
+  };
+  if (kvec(o, kax, rowax) && (!has_m || kvec(*m, *mkax, *mrowax))) return MODE_KVEC;
+  if (mvec(o, kax, rowax) && (!has_m || mvec(*m, *mkax, *mrowax))) return MODE_MVEC;
+  // scalar modes: lanes along whichever index is contiguous in memory
+  if (inner_stride(kax) == 1 && inner_stride(rowax) != 1) return MODE_KSC;
+  return MODE_ROWG;
 }
 
 static int g_num_sms = 0;
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool AMUL>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BN, X3>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3, AMUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("dstag_gemm(tc): cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
       return (int)e;
@@ -664,7 +756,7 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
-  gemm_tc_kernel<BN, X3><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p);
+  gemm_tc_kernel<BN, X3, AMUL><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p);
   DSTAG_RETURN_LAUNCH("dstag_gemm(tcgen05)");
 }
 
@@ -688,16 +780,17 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
   const long long items = (long long)g->batch * p.ntm * p.ntn * p.nsplit;
   DSTAG_CHECK_ARG(items < (1ll << 31), "dstag_gemm(tc): too many tiles");
   p.total_items = (int)items;
-  if (kvec_ok(g->A, g->A.col, g->A.row) && kvec_ok(g->Amul, g->Amul.col, g->Amul.row)) p.a_mode = MODE_KVEC;
-  else if (mvec_ok(g->A, g->A.col, g->A.row) && mvec_ok(g->Amul, g->Amul.col, g->Amul.row)) p.a_mode = MODE_MVEC;
-  else p.a_mode = MODE_ROW;
-  if (kvec_ok(g->B, g->B.row, g->B.col)) p.b_mode = MODE_KVEC;
-  else if (mvec_ok(g->B, g->B.row, g->B.col)) p.b_mode = MODE_MVEC;
-  else p.b_mode = MODE_ROW;
+  p.a_mode = pick_mode(g->A, g->A.col, g->A.row, &g->Amul, &g->Amul.col, &g->Amul.row);
+  p.b_mode = pick_mode(g->B, g->B.row, g->B.col, nullptr, nullptr, nullptr);
   const bool x3 = g->precision == DSTAG_PREC_TF32X3;
-  if (bn == 128) return x3 ? launch_tc<128, true>(p, stream) : launch_tc<128, false>(p, stream);
-  if (bn == 64) return x3 ? launch_tc<64, true>(p, stream) : launch_tc<64, false>(p, stream);
-  return x3 ? launch_tc<32, true>(p, stream) : launch_tc<32, false>(p, stream);
+  const bool am = g->Amul.ptr != nullptr;
+#define DSTAG_TC_DISPATCH(BN_)                                                                     \
+  return x3 ? (am ? launch_tc<BN_, true, true>(p, stream) : launch_tc<BN_, true, false>(p, stream)) \
+            : (am ? launch_tc<BN_, false, true>(p, stream) : launch_tc<BN_, false, false>(p, stream))
+  if (bn == 128) DSTAG_TC_DISPATCH(128);
+  if (bn == 64) DSTAG_TC_DISPATCH(64);
+  DSTAG_TC_DISPATCH(32);
+#undef DSTAG_TC_DISPATCH
 }
 
 }  // namespace dstag
