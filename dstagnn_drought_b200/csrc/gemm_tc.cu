@@ -187,14 +187,20 @@ struct Walk {
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// Round-to-nearest TF32 (the tensor core itself truncates the low 13 mantissa bits): adding half a
+// TF32 ulp before masking halves the residual, so the lo term carries one more useful bit and its
+// own truncation error drops to ~2^-23 relative.
+__device__ __forceinline__ float tf32_hi(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
 
 template <bool X3>
 __device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float4 v) {
   if (X3) {
     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(plane_hi + off) = h;
-    *reinterpret_cast<float4*>(plane_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(plane_lo + off) =
+        make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
   } else {
     *reinterpret_cast<float4*>(plane_hi + off) = v;
   }
@@ -204,7 +210,7 @@ __device__ __forceinline__ void store_scalar(uint8_t* plane_hi, uint8_t* plane_l
   if (X3) {
     const float h = tf32_hi(v);
     *reinterpret_cast<float*>(plane_hi + off) = h;
-    *reinterpret_cast<float*>(plane_lo + off) = v - h;
+    *reinterpret_cast<float*>(plane_lo + off) = tf32_hi(v - h);
   } else {
     *reinterpret_cast<float*>(plane_hi + off) = v;
   }
