@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -56,7 +56,7 @@ SIGNATURES = {
     "dstag_tattn_fwd": (C.c_int, [_F, _F, _i32, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tattn_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_fwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
-    "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
+    "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F]),
     "dstag_tail_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i32, _i32, _f32,
                                  _u64, _F]),

@@ -1,6 +1,8 @@
 // Block tail: GTU gate and the fused  dropout -> relu(tc [+ g]) -> relu(r + .) -> LayerNorm_C
-// kernel (model/DSTAGNN_my.py:194-196, 243-252).  All tensors are (X = B*N, C, T) with T
-// innermost; a CTA stages a group of nodes in shared memory with fully coalesced loads,
+// kernel (model/DSTAGNN_my.py:194-196, 243-252).  tc / r / out are (X = B*N, C, T) with T
+// innermost (the block's boundary layout); the graph-conv output g and the GTU conv tensors are
+// channels-last (X, T, C) so that the temporal convolutions are plain K-contiguous contractions.
+// A CTA stages a group of nodes in shared memory with fully coalesced loads,
 // normalises every (node, t) column over the C channels out of shared memory (padded so
 // the column walk is bank-conflict free), and stores coalesced.
 #include "common.cuh"
@@ -11,33 +13,38 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __global__ void gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restrict__ out, long long total,
                                     int C, int Tp, int out_ld, int out_off) {
+  // u: (X, Tp, 2C) channels-last conv output;  out[x, c, off + t] = tanh(u[x,t,c]) * sigmoid(u[x,t,C+c])
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int ct = C * Tp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long x = i / ct;
     const int rem = (int)(i - x * ct);
-    const int c = rem / Tp, t = rem - c * Tp;
-    const float p = __ldg(u + x * 2 * ct + rem);
-    const float q = __ldg(u + x * 2 * ct + ct + rem);
-    out[(x * C + c) * out_ld + out_off + t] = tanhf(p) * sigmoidf_(q);
+    const int c = rem / Tp, t = rem - c * Tp;          // t fastest: coalesced writes; reads hit L1 lines
+    const float* up = u + (x * Tp + t) * 2 * C;
+    out[(x * C + c) * out_ld + out_off + t] = tanhf(__ldg(up + c)) * sigmoidf_(__ldg(up + C + c));
   }
 }
 
 __global__ void gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
-                                    float* __restrict__ du, long long total, int C, int Tp, int out_ld,
-                                    int out_off) {
+                                    float* __restrict__ dup, long long total, int C, int Tp, int pad,
+                                    int out_ld, int out_off) {
+  // dup: (X, Tp + 2 pad, 2C) channels-last gradient of the conv output, zero in the pad rows
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const int ct = C * Tp;
+  const int Tpad = Tp + 2 * pad, c2 = 2 * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long x = i / ct;
-    const int rem = (int)(i - x * ct);
-    const int c = rem / Tp, t = rem - c * Tp;
-    const float p = __ldg(u + x * 2 * ct + rem);
-    const float q = __ldg(u + x * 2 * ct + ct + rem);
-    const float d = __ldg(dout + (x * C + c) * out_ld + out_off + t);
-    const float th = tanhf(p), sg = sigmoidf_(q);
-    du[x * 2 * ct + rem] = d * sg * (1.f - th * th);
-    du[x * 2 * ct + ct + rem] = d * th * sg * (1.f - sg);
+    const long long xt = i / c2;                       // o fastest: coalesced writes of dup
+    const int o = (int)(i - xt * c2);
+    const long long x = xt / Tpad;
+    const int tp = (int)(xt - x * Tpad), t = tp - pad;
+    float r = 0.f;
+    if (t >= 0 && t < Tp) {
+      const int c = o < C ? o : o - C;
+      const float* up = u + (x * Tp + t) * c2;
+      const float th = tanhf(__ldg(up + c)), sg = sigmoidf_(__ldg(up + C + c));
+      const float d = __ldg(dout + (x * C + c) * out_ld + out_off + t);
+      r = o < C ? d * sg * (1.f - th * th) : d * th * sg * (1.f - sg);
+    }
+    dup[i] = r;
   }
 }
 
@@ -64,7 +71,10 @@ tail_fwd_kernel(const float* __restrict__ tc, const float* __restrict__ g, const
       const long long e = (x0 + xl) * ct + rem;
       float a = __ldg(tc + e);
       if (drop_p > 0.f) a *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
-      if (g) a += __ldg(g + e);
+      if (g) {                                   // g is channels-last (X, T, C)
+        const int c = rem / T, t = rem - c * T;
+        a += __ldg(g + ((x0 + xl) * T + t) * C + c);
+      }
       a = fmaxf(a, 0.f);
       V[xl * nst + rem] = fmaxf(__ldg(r + e) + a, 0.f);
     }
@@ -121,7 +131,10 @@ tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ tc, co
       const long long e = (x0 + xl) * ct + rem;
       float a = __ldg(tc + e);
       if (drop_p > 0.f) a *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
-      if (g) a += __ldg(g + e);
+      if (g) {
+        const int c = rem / T, t = rem - c * T;
+        a += __ldg(g + ((x0 + xl) * T + t) * C + c);
+      }
       const float s2 = __ldg(r + e) + fmaxf(a, 0.f);
       V[xl * nst + rem] = fmaxf(s2, 0.f);
       D[xl * nst + rem] = __ldg(dout + e);
@@ -168,10 +181,20 @@ tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ tc, co
       const float ds2 = (fl & 2) ? D[xl * nst + rem] : 0.f;
       const float ds1 = (fl & 1) ? ds2 : 0.f;
       dr[e] = ds2;
-      if (dg) dg[e] = ds1;
+      if (dg) {                                  // stage d(tco) transposed: V is free after the LN pass
+        const int c = rem / T, t = rem - c * T;
+        V[xl * nst + t * C + c] = ds1;
+      }
       float o = ds1;
       if (drop_p > 0.f) o *= dropout_scale((unsigned long long)e, seed, drop_p, inv_keep);
       dtc[e] = o;
+    }
+    if (dg) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < nn * ct; i += blockDim.x) {   // coalesced channels-last store
+        const int xl = i / ct, rem = i - xl * ct;
+        dg[(x0 + xl) * ct + rem] = V[xl * nst + rem];
+      }
     }
   }
   __syncthreads();
@@ -216,14 +239,15 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
   DSTAG_RETURN_LAUNCH("dstag_gtu_gate_fwd");
 }
 
-int dstag_gtu_gate_bwd(const float* u, const float* dout, float* du, int64_t X, int32_t C, int32_t Tp,
-                       int32_t out_ld, int32_t out_off, void* stream) {
-  DSTAG_CHECK_ARG(u && dout && du && X > 0 && C > 0 && Tp > 0 && out_off >= 0 && out_off + Tp <= out_ld,
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X, int32_t C, int32_t Tp,
+                       int32_t pad, int32_t out_ld, int32_t out_off, void* stream) {
+  DSTAG_CHECK_ARG(u && dout && dup && X > 0 && C > 0 && Tp > 0 && pad >= 0 && out_off >= 0 &&
+                      out_off + Tp <= out_ld,
                   "dstag_gtu_gate_bwd: bad arguments");
-  const long long total = (long long)X * C * Tp;
+  const long long total = (long long)X * (Tp + 2 * pad) * 2 * C;
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, du, total, C, Tp,
+  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, dup, total, C, Tp, pad,
                                                                           out_ld, out_off);
   DSTAG_RETURN_LAUNCH("dstag_gtu_gate_bwd");
 }

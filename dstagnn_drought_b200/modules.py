@@ -195,7 +195,7 @@ class DSTAGNN_block(nn.Module):
         qk = contract("rd,od->ro", se, w_sat).view(B, N, 2, K, dk)
         zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)             # (K, B, N, F*T)
         theta = torch.stack(list(self.cheb_conv_SAt.Theta))                             # (K, F, C)
-        g = contract("kxft,kfc->xct", zc.view(K, B * N, Fin, T), theta, relu=True)      # (B*N, C, T)
+        g = contract("kxft,kfc->xtc", zc.view(K, B * N, Fin, T), theta, relu=True)      # (B*N, T, C) channels-last
         # 7. gated temporal convolutions                                             (lines 237-242)
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
                                  self.gtu5.con2out.weight, self.gtu5.con2out.bias,

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACC_ATOMIC
+from ._lib import ACC_ADD, ACC_ATOMIC, ACC_STORE
 from .contraction import _check, colsum, contract_raw
 
 _VP = C.c_void_p
@@ -262,25 +262,36 @@ class SpatialChebConv(torch.autograd.Function):
 # GTU 3/5/7: Conv2d(C -> 2C, (1,k)) over time + tanh * sigmoid gate, concatenated over time
 # ----------------------------------------------------------------------------------------
 class GtuStack(torch.autograd.Function):
-    """gtu3/gtu5/gtu7 + torch.cat (lines 192-197, 238-242).  g: (X, C, T) -> (X, C, 3T-12).
+    """gtu3/gtu5/gtu7 + torch.cat (lines 192-197, 238-242).
+    g: (X, T, C) CHANNELS-LAST graph-conv output -> (X, C, 3T-12) (time innermost, fcmy's layout).
 
-    The convolution is a contraction over an *unfolded view* of g (window index folded into
-    the strides; no im2col buffer); its input gradient scatters back through the same view
-    with atomic accumulation."""
+    With channels last, the window of ks time steps that a Conv2d(C->2C, (1,ks)) output reads is
+    ks*C *contiguous* floats, so the convolution is a plain K-contiguous contraction over an
+    overlapping strided view of g (no im2col buffer).  Its input gradient is the correlation of
+    the zero-padded output gradient with the flipped kernel -- again a gather-only contraction
+    over an overlapping view, no atomics -- and its weight gradient contracts the same two views
+    over (x, t)."""
+
+    KS = (3, 5, 7)
+
+    @staticmethod
+    def _views(g, ks):
+        X, T, Cc = g.shape
+        return g.as_strided((X, T - ks + 1, ks * Cc), (T * Cc, Cc, 1))
 
     @staticmethod
     def forward(ctx, g, w3, b3, w5, b5, w7, b7):
         lib = _lib.load()
         _check(g, "g")
         g = g.contiguous()
-        X, Cc, T = g.shape
-        widths = [T - ks + 1 for ks in (3, 5, 7)]
+        X, T, Cc = g.shape
+        widths = [T - ks + 1 for ks in GtuStack.KS]
         total = sum(widths)
         out = torch.empty((X, Cc, total), device=g.device, dtype=torch.float32)
         us, off = [], 0
-        for ks, w, b, tp in zip((3, 5, 7), (w3, w5, w7), (b3, b5, b7), widths):
-            gu = g.unfold(2, ks, 1)                                    # (X, C, T', ks) view
-            u = contract_raw("xctd,ocd->xot", gu, w.view(2 * Cc, Cc, ks), c_add=("o", b))
+        for ks, w, b, tp in zip(GtuStack.KS, (w3, w5, w7), (b3, b5, b7), widths):
+            wk = w[:, :, 0, :].permute(0, 2, 1).reshape(2 * Cc, ks * Cc).contiguous()      # (o, (d, c))
+            u = contract_raw("xtk,ok->xto", GtuStack._views(g, ks), wk, c_add=("o", b), tag=f"gtu{ks}_fwd")
             _lib.check(lib.dstag_gtu_gate_fwd(u.data_ptr(), out.data_ptr(), X, Cc, tp, total, off,
                                               _stream(g)), "dstag_gtu_gate_fwd")
             us.append(u)
@@ -292,22 +303,27 @@ class GtuStack(torch.autograd.Function):
     def backward(ctx, dout):
         lib = _lib.load()
         g, w3, w5, w7, u3, u5, u7 = ctx.saved_tensors
-        X, Cc, T = g.shape
+        X, T, Cc = g.shape
         dout = dout.contiguous()
         total = dout.shape[-1]
-        dg = torch.zeros_like(g) if ctx.needs_input_grad[0] else None
-        grads, off = [], 0
-        for ks, w, u in zip((3, 5, 7), (w3, w5, w7), (u3, u5, u7)):
-            tp = T - ks + 1
-            du = torch.empty_like(u)
-            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), du.data_ptr(), X, Cc, tp,
+        dg = torch.empty_like(g) if ctx.needs_input_grad[0] else None
+        grads, off, first = [], 0, True
+        for ks, w, u in zip(GtuStack.KS, (w3, w5, w7), (u3, u5, u7)):
+            tp, pad = T - ks + 1, ks - 1
+            tpad = tp + 2 * pad
+            dup = torch.empty((X, tpad, 2 * Cc), device=g.device, dtype=torch.float32)
+            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), X, Cc, tp, pad,
                                               total, off, _stream(g)), "dstag_gtu_gate_bwd")
-            gu = g.unfold(2, ks, 1)
-            dw = contract_raw("xot,xctd->ocd", du, gu).view(w.shape)
-            db = colsum(du, X, 2 * Cc * tp).view(2 * Cc, tp).sum(dim=1)
+            du = dup[:, pad:pad + tp, :]                                             # valid rows (view)
+            dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
+            dw = dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1).reshape(w.shape)
+            db = colsum(dup, X * tpad, 2 * Cc)                                       # pad rows are zero
             if dg is not None:
-                contract_raw("xot,ocd->xctd", du, w.view(2 * Cc, Cc, ks), out=dg.unfold(2, ks, 1),
-                             accumulate=ACC_ATOMIC, split_k=1)
+                wflip = w[:, :, 0, :].flip(-1).permute(1, 2, 0).reshape(Cc, ks * 2 * Cc).contiguous()
+                dview = dup.as_strided((X, T, ks * 2 * Cc), (tpad * 2 * Cc, 2 * Cc, 1))
+                contract_raw("xtk,ck->xtc", dview, wflip, out=dg, accumulate=ACC_STORE if first else ACC_ADD,
+                             split_k=1, tag=f"gtu{ks}_dx")
+                first = False
             grads += [dw, db]
             off += tp
         return (dg, *grads)
@@ -317,7 +333,8 @@ class GtuStack(torch.autograd.Function):
 # block tail
 # ----------------------------------------------------------------------------------------
 class BlockTail(torch.autograd.Function):
-    """out = LN_C(relu(r + relu(dropout(tc) [+ g])))  (lines 243-252); all (X, C, T)."""
+    """out = LN_C(relu(r + relu(dropout(tc) [+ g])))  (lines 243-252).
+    tc, r, out: (X, C, T);  g (and its gradient): (X, T, C) channels-last."""
 
     @staticmethod
     def forward(ctx, tc, g, r, gamma, beta, drop_p, seed):
@@ -347,7 +364,7 @@ class BlockTail(torch.autograd.Function):
         dout = dout.contiguous()
         dtc = torch.empty_like(tc)
         dr = torch.empty_like(tc)
-        dg = torch.empty_like(tc) if g is not None else None
+        dg = torch.empty_like(g) if g is not None else None
         dgamma = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
         dbeta = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
         _lib.check(lib.dstag_tail_bwd(dout.data_ptr(), tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(),

@@ -144,26 +144,31 @@ int dstag_tattn_bwd(const float* qkv, const float* scores, const float* dctx,
                     int32_t H, int32_t T, int32_t dk, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * GTU gate (model/DSTAGNN_my.py:194-196): out[x, c, off + t] = tanh(u[x, c, t]) * sigmoid(u[x, C + c, t])
- *   u (X, 2C, Tp) contiguous; out rows have leading dimension out_ld (the concatenated
- *   time axis 3T-12 of line 242).
+ * GTU gate (model/DSTAGNN_my.py:194-196) on the CHANNELS-LAST conv output u (X, Tp, 2C):
+ *   out[x, c, off + t] = tanh(u[x, t, c]) * sigmoid(u[x, t, C + c])
+ * out rows have leading dimension out_ld (the concatenated time axis 3T-12 of line 242).
+ * The temporal convolutions themselves run through dstag_gemm on an overlapping strided view
+ * of the channels-last activation (K = ks*C contiguous), see ops.GtuStack.
  * ---------------------------------------------------------------------------------- */
 int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t Tp, int32_t out_ld,
                        int32_t out_off, void* stream);
-int dstag_gtu_gate_bwd(const float* u, const float* dout, float* du, int64_t X, int32_t C, int32_t Tp,
-                       int32_t out_ld, int32_t out_off, void* stream);
+/* dup (X, Tp + 2*pad, 2C): gradient w.r.t. u, written with `pad` zero rows before and after the
+ * Tp valid time steps, so that the conv input gradient is a gather-only correlation over an
+ * unfolded view of dup (no atomics). */
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X, int32_t C, int32_t Tp,
+                       int32_t pad, int32_t out_ld, int32_t out_off, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Block tail (model/DSTAGNN_my.py:243-252):
  *   tc' = dropout(tc) ; tco = relu(tc' [+ g]) ; out = LN_C(relu(r + tco)) over the channel axis
- *   tc, g, r, out: (X, C, T) with X = B*N ; g == NULL in block 0 (line 245).
+ *   tc, r, out: (X, C, T) with X = B*N;  g: (X, T, C) channels-last, NULL in block 0 (line 245).
  *   mean/rstd: (X, T) saved statistics.
  * ---------------------------------------------------------------------------------- */
 int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
                    const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
                    int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
-/* dtc, dr always written; dg written when g != NULL (dg == d tco).  dgamma/dbeta accumulated
- * atomically into caller-zeroed buffers. */
+/* dtc, dr always written; dg (X, T, C) written when g != NULL (dg == d tco).  dgamma/dbeta
+ * accumulated atomically into caller-zeroed buffers. */
 int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
                    const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
                    float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 1
+        return 2
 
     def dstag_last_error(self):
         return self.err
@@ -196,19 +196,21 @@ class FakeLib:
     # ---- GTU gate + tail ----
     def dstag_gtu_gate_fwd(self, u, out, X, Cc, Tp, out_ld, out_off, stream):
         self.launches += 1
-        U = _arr(u, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp).astype(np.float64)
+        U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
         O = _arr(out, X * Cc * out_ld).reshape(X, Cc, out_ld)
-        O[:, :, out_off:out_off + Tp] = np.tanh(U[:, :Cc]) / (1 + np.exp(-U[:, Cc:]))
+        O[:, :, out_off:out_off + Tp] = (np.tanh(U[:, :, :Cc]) / (1 + np.exp(-U[:, :, Cc:]))).transpose(0, 2, 1)
         return 0
 
-    def dstag_gtu_gate_bwd(self, u, dout, du, X, Cc, Tp, out_ld, out_off, stream):
+    def dstag_gtu_gate_bwd(self, u, dout, dup, X, Cc, Tp, pad, out_ld, out_off, stream):
         self.launches += 1
-        U = _arr(u, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp).astype(np.float64)
+        U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
         d = _arr(dout, X * Cc * out_ld).reshape(X, Cc, out_ld)[:, :, out_off:out_off + Tp].astype(np.float64)
-        th, sg = np.tanh(U[:, :Cc]), 1 / (1 + np.exp(-U[:, Cc:]))
-        D = _arr(du, X * 2 * Cc * Tp).reshape(X, 2 * Cc, Tp)
-        D[:, :Cc] = d * sg * (1 - th * th)
-        D[:, Cc:] = d * th * sg * (1 - sg)
+        d = d.transpose(0, 2, 1)                                                   # (X, Tp, C)
+        th, sg = np.tanh(U[:, :, :Cc]), 1 / (1 + np.exp(-U[:, :, Cc:]))
+        D = _arr(dup, X * (Tp + 2 * pad) * 2 * Cc).reshape(X, Tp + 2 * pad, 2 * Cc)
+        D[:] = 0
+        D[:, pad:pad + Tp, :Cc] = d * sg * (1 - th * th)
+        D[:, pad:pad + Tp, Cc:] = d * th * sg * (1 - sg)
         return 0
 
     def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, stream):
@@ -217,7 +219,7 @@ class FakeLib:
         n = X * Cc * T
         s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
         if g:
-            s1 = s1 + _arr(g, n).reshape(X, Cc, T)
+            s1 = s1 + _arr(g, n).reshape(X, T, Cc).transpose(0, 2, 1)             # g is channels-last
         v = np.maximum(_arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0), 0)
         mu = v.mean(1)
         rs = 1 / np.sqrt(v.var(1) + eps)
@@ -234,7 +236,7 @@ class FakeLib:
         n = X * Cc * T
         s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
         if g:
-            s1 = s1 + _arr(g, n).reshape(X, Cc, T)
+            s1 = s1 + _arr(g, n).reshape(X, T, Cc).transpose(0, 2, 1)
         s2 = _arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0)
         v = np.maximum(s2, 0)
         mu = _arr(mean, X * T).reshape(X, 1, T).astype(np.float64)
@@ -248,7 +250,7 @@ class FakeLib:
         _arr(dr, n).reshape(X, Cc, T)[:] = ds2
         _arr(dtc, n).reshape(X, Cc, T)[:] = ds1
         if dg:
-            _arr(dg, n).reshape(X, Cc, T)[:] = ds1
+            _arr(dg, n).reshape(X, T, Cc)[:] = ds1.transpose(0, 2, 1)
         _arr(dgamma, Cc)[:] += (d * xh).sum((0, 2))
         _arr(dbeta, Cc)[:] += d.sum((0, 2))
         return 0

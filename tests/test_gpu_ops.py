@@ -203,13 +203,13 @@ def test_gtu_stack(dev, precision, cfg):
     from dstagnn_drought_b200.ops import GtuStack
     X, Cc, T = cfg
     torch.manual_seed(8)
-    g = torch.randn(X, Cc, T, device=dev)
+    g = torch.randn(X, T, Cc, device=dev)                                     # channels-last
     ws = [torch.randn(2 * Cc, Cc, 1, ks, device=dev) * 0.2 for ks in (3, 5, 7)]
     bs = [torch.randn(2 * Cc, device=dev) for _ in range(3)]
     dout = torch.randn(X, Cc, 3 * T - 12, device=dev)
 
     def ref_fn(g_, w3, b3, w5, b5, w7, b7):
-        xc = g_.permute(1, 0, 2).unsqueeze(0)                                 # (1, C, X, T)
+        xc = g_.permute(2, 0, 1).unsqueeze(0)                                 # (1, C, X, T)
         outs = []
         for w, b in ((w3, b3), (w5, b5), (w7, b7)):
             u = torch.nn.functional.conv2d(xc, w, b)
@@ -230,12 +230,13 @@ def test_block_tail(dev, cfg):
     from dstagnn_drought_b200.ops import BlockTail
     X, Cc, T, with_g = cfg
     torch.manual_seed(9)
-    tc, g, r = (torch.randn(X, Cc, T, device=dev) for _ in range(3))
+    tc, r = (torch.randn(X, Cc, T, device=dev) for _ in range(2))
+    g = torch.randn(X, T, Cc, device=dev)                                     # channels-last
     gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
     dout = torch.randn(X, Cc, T, device=dev)
 
     def ref_fn(tc_, g_, r_, ga_, be_):
-        tco = torch.relu(tc_ + g_) if with_g else torch.relu(tc_)
+        tco = torch.relu(tc_ + g_.permute(0, 2, 1)) if with_g else torch.relu(tc_)
         v = torch.relu(r_ + tco).permute(0, 2, 1)
         return torch.nn.functional.layer_norm(v, (Cc,), ga_, be_, 1e-5).permute(0, 2, 1)
 
