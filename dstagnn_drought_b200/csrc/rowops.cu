@@ -100,8 +100,47 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, long lo
 }
 
 // ======================================================================================
-// Column sums with a 2-level (in-CTA + atomic) reduction.
+// Column sums.  Two regimes:
+//   wide   (cols >= 2048, e.g. the batch reduction of the N x N map gradients): one thread per 4
+//          columns, float4 loads, rows walked with 4 independent accumulators; row chunks combine
+//          with atomicAdd;
+//   narrow (bias gradients: 12..512 columns, 10^5..10^6 rows): a CTA owns a row range, lanes run
+//          along the columns (coalesced), 8-row unrolled accumulation, shared-memory combine,
+//          one atomicAdd per column per CTA.
 // ======================================================================================
+__global__ void __launch_bounds__(kRowThreads)
+colsum_wide_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, long long cols,
+                   long long ld, long long rows_per_chunk) {
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in + (r + u) * ld + c));
+      acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+    }
+  }
+  for (; r < r1; ++r) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * ld + c));
+    acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+  }
+  const float4 t = make_float4(acc[0].x + acc[1].x + acc[2].x + acc[3].x, acc[0].y + acc[1].y + acc[2].y + acc[3].y,
+                               acc[0].z + acc[1].z + acc[2].z + acc[3].z, acc[0].w + acc[1].w + acc[2].w + acc[3].w);
+  if (gridDim.y == 1) {
+    float4* o = reinterpret_cast<float4*>(out + c);
+    const float4 old = *o;
+    *o = make_float4(old.x + t.x, old.y + t.y, old.z + t.z, old.w + t.w);
+  } else {
+    atomicAdd(out + c, t.x); atomicAdd(out + c + 1, t.y); atomicAdd(out + c + 2, t.z); atomicAdd(out + c + 3, t.w);
+  }
+}
+
 __global__ void __launch_bounds__(kRowThreads)
 colsum_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, long long cols,
               long long ld, int lanes_c, long long rows_per_chunk) {
@@ -110,9 +149,18 @@ colsum_kernel(const float* __restrict__ in, float* __restrict__ out, long long r
   const long long c = (long long)blockIdx.x * lanes_c + lc;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
   const long long r1 = min(rows, r0 + rows_per_chunk);
-  float acc = 0.f;
-  if (c < cols)
-    for (long long r = r0 + lr; r < r1; r += lanes_r) acc += __ldg(in + r * ld + c);
+  float a[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = 0.f;
+  if (c < cols) {
+    long long r = r0 + lr;
+    for (; r + 7LL * lanes_r < r1; r += 8LL * lanes_r) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldg(in + (r + (long long)u * lanes_r) * ld + c);
+    }
+    for (; r < r1; r += lanes_r) a[0] += __ldg(in + r * ld + c);
+  }
+  float acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   part[threadIdx.x] = acc;
   __syncthreads();
   if (lr == 0 && c < cols) {
@@ -259,12 +307,25 @@ int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a
 
 int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream) {
   DSTAG_CHECK_ARG(in && out && rows > 0 && cols > 0 && ld >= cols, "dstag_colsum: bad arguments");
+  const bool wide = cols >= 2048 && cols % 4 == 0 && ld % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (wide) {
+    const long long gx = (cols / 4 + kRowThreads - 1) / kRowThreads;
+    long long chunks = (kNumSMs * 8 + gx - 1) / gx;                 // enough CTAs to fill the machine
+    const long long max_chunks = (rows + 15) / 16;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const long long rpc = (rows + chunks - 1) / chunks;
+    const dim3 grid((unsigned)gx, (unsigned)((rows + rpc - 1) / rpc));
+    colsum_wide_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(in, out, rows, cols, ld, rpc);
+    DSTAG_RETURN_LAUNCH("dstag_colsum(wide)");
+  }
   int lanes_c = 256;
   while (lanes_c > 1 && lanes_c / 2 >= cols) lanes_c /= 2;   // smallest power of two >= cols, <= 256
   const int lanes_r = kRowThreads / lanes_c;
   const long long gx = (cols + lanes_c - 1) / lanes_c;
-  long long chunks = (kNumSMs * 4 + gx - 1) / gx;
-  const long long max_chunks = (rows + (long long)lanes_r * 4 - 1) / ((long long)lanes_r * 4);
+  long long chunks = (kNumSMs * 8 + gx - 1) / gx;
+  const long long max_chunks = (rows + (long long)lanes_r * 16 - 1) / ((long long)lanes_r * 16);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;

@@ -9,7 +9,10 @@
 
 namespace dstag {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// exp-based gate functions on the fast-math units (abs error ~1e-7: far inside the parity budget;
+// the libm tanhf/expf versions made the gate kernels instruction-bound, not HBM-bound)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 __global__ void gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restrict__ out, long long total,
                                     int C, int Tp, int out_ld, int out_off) {
@@ -21,30 +24,32 @@ __global__ void gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restri
     const int rem = (int)(i - x * ct);
     const int c = rem / Tp, t = rem - c * Tp;          // t fastest: coalesced writes; reads hit L1 lines
     const float* up = u + (x * Tp + t) * 2 * C;
-    out[(x * C + c) * out_ld + out_off + t] = tanhf(__ldg(up + c)) * sigmoidf_(__ldg(up + C + c));
+    out[(x * C + c) * out_ld + out_off + t] = tanhf_(__ldg(up + c)) * sigmoidf_(__ldg(up + C + c));
   }
 }
 
 __global__ void gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
                                     float* __restrict__ dup, long long total, int C, int Tp, int pad,
                                     int out_ld, int out_off) {
-  // dup: (X, Tp + 2 pad, 2C) channels-last gradient of the conv output, zero in the pad rows
+  // dup: (X, Tp + 2 pad, 2C) channels-last gradient of the conv output, zero in the pad rows.
+  // One thread per (x, padded t, c): evaluates the gate once and writes both halves (p and q).
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const int Tpad = Tp + 2 * pad, c2 = 2 * C;
+  const int Tpad = Tp + 2 * pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long xt = i / c2;                       // o fastest: coalesced writes of dup
-    const int o = (int)(i - xt * c2);
+    const long long xt = i / C;                        // c fastest: coalesced reads of u, writes of dup
+    const int c = (int)(i - xt * C);
     const long long x = xt / Tpad;
     const int tp = (int)(xt - x * Tpad), t = tp - pad;
-    float r = 0.f;
+    float rp = 0.f, rq = 0.f;
     if (t >= 0 && t < Tp) {
-      const int c = o < C ? o : o - C;
-      const float* up = u + (x * Tp + t) * c2;
-      const float th = tanhf(__ldg(up + c)), sg = sigmoidf_(__ldg(up + C + c));
+      const float* up = u + (x * Tp + t) * 2 * C;
+      const float th = tanhf_(__ldg(up + c)), sg = sigmoidf_(__ldg(up + C + c));
       const float d = __ldg(dout + (x * C + c) * out_ld + out_off + t);
-      r = o < C ? d * sg * (1.f - th * th) : d * th * sg * (1.f - sg);
+      rp = d * sg * (1.f - th * th);
+      rq = d * th * sg * (1.f - sg);
     }
-    dup[i] = r;
+    dup[xt * 2 * C + c] = rp;
+    dup[xt * 2 * C + C + c] = rq;
   }
 }
 
@@ -244,7 +249,7 @@ int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X,
   DSTAG_CHECK_ARG(u && dout && dup && X > 0 && C > 0 && Tp > 0 && pad >= 0 && out_off >= 0 &&
                       out_off + Tp <= out_ld,
                   "dstag_gtu_gate_bwd: bad arguments");
-  const long long total = (long long)X * (Tp + 2 * pad) * 2 * C;
+  const long long total = (long long)X * (Tp + 2 * pad) * C;
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, dup, total, C, Tp, pad,
