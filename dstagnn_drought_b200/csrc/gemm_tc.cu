@@ -424,37 +424,79 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES>
-__device__ __forceinline__ void produce_item(Producer<ROWS, NT, X3, MUL>& pr, int kb0, int kb1, uint32_t& it,
-                                             uint8_t* smem, uint32_t plane_off, uint32_t plane_bytes,
-                                             uint64_t* full_bar, uint64_t* empty_bar, int lane) {
+// Flat producer pipeline over the CTA's (item, k-block) sequence: iteration i issues the global loads
+// of position i + 1 -- which may already belong to the NEXT output tile -- and then stores position i,
+// so load latency is hidden across tile boundaries too (tiles with a single k-block, e.g. Q K^T with
+// d_k = 32, would otherwise expose one full DRAM round trip per tile).
+template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES, bool IS_A>
+__device__ __forceinline__ void produce_all(const TcParams& p, uint8_t* smem, uint32_t plane_off,
+                                            uint32_t plane_bytes, uint64_t* full_bar, uint64_t* empty_bar,
+                                            int t, int lane) {
   using P = Producer<ROWS, NT, X3, MUL>;
+  const dstag_gemm_t& g = p.g;
+  P pr;
+  pr.t = t;
+  pr.K = g.K;
+  if (IS_A) {
+    pr.mode = p.a_mode;
+    pr.rowax = &g.A.row; pr.colax = &g.A.col;
+    pr.mrowax = &g.Amul.row; pr.mcolax = &g.Amul.col;
+  } else {
+    pr.mode = p.b_mode;
+    pr.rowax = &g.B.col; pr.colax = &g.B.row;      // B tile rows = n (B.col axis), columns = k (B.row axis)
+    pr.mrowax = &g.B.col; pr.mcolax = &g.B.row;
+  }
+  auto enter_item = [&](int w, int& kb0, int& kb1) {
+    int q = w;
+    const int ks = q % p.nsplit; q /= p.nsplit;
+    const int tn = q % p.ntn; q /= p.ntn;
+    const int tm = q % p.ntm;
+    const int batch = q / p.ntm;
+    kb0 = ks * p.kb_per_split;
+    kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+    if (IS_A) {
+      const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, batch);
+      const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, batch) : nullptr;
+      pr.begin_item(ab, mb, tm * TC_BM, g.M);
+    } else {
+      const float* bb = (const float*)g.B.ptr + axoff64(g.B.batch, batch);
+      pr.begin_item(bb, nullptr, tn * ROWS, g.N);
+    }
+  };
   float4 cur[P::NV], nxt[P::NV], curm[P::NM], nxtm[P::NM];
 #pragma unroll
-  for (int i = 0; i < P::NV; ++i) cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
   for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-  // software pipeline with a single load site: iteration kb issues the loads of block kb + 1 and
-  // then (from kb0 on) stores block kb, so global latency overlaps the split / swizzle / barrier work
+  int w = blockIdx.x;
+  if (w >= p.total_items) return;
+  int kb, kb1;
+  enter_item(w, kb, kb1);
+  pr.load(kb, nxt, nxtm);                        // position 0
+  uint32_t it = 0;
+  bool more = true;
 #pragma unroll 1
-  for (int kb = kb0 - 1; kb < kb1; ++kb) {
-    if (kb + 1 < kb1) pr.load(kb + 1, nxt, nxtm);
-    if (kb >= kb0) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1, 0);
-      __syncwarp();
-      uint8_t* st = smem + s * STAGE_BYTES + plane_off;
-      pr.store(cur, curm, st, st + plane_bytes);
-      fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + s);
-      ++it;
-    }
+  while (more) {
 #pragma unroll
     for (int i = 0; i < P::NV; ++i) cur[i] = nxt[i];
 #pragma unroll
     for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i];
+    // advance to the next position and put its loads in flight
+    if (++kb >= kb1) {
+      w += gridDim.x;
+      more = w < p.total_items;
+      if (more) enter_item(w, kb, kb1);
+    }
+    if (more) pr.load(kb, nxt, nxtm);
+    // store the current position
+    const int s = it % STAGES;
+    const uint32_t ph = (it / STAGES) & 1;
+    if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1, 0);
+    __syncwarp();
+    uint8_t* st = smem + s * STAGE_BYTES + plane_off;
+    pr.store(cur, curm, st, st + plane_bytes);
+    fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar + s);
+    ++it;
   }
 }
 
@@ -492,50 +534,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   if (warp < TC_A_WARPS + TC_B_WARPS) {
     // =============================== producers =========================================
-    const bool is_a = warp < TC_A_WARPS;
-    uint32_t it = 0;   // running k-block counter across items (stage ring position)
-    if (is_a) {
-      Producer<TC_BM, TC_A_WARPS * 32, X3, AMUL> pa;
-      pa.t = threadIdx.x;
-      pa.K = g.K;
-      pa.mode = p.a_mode;
-      pa.rowax = &g.A.row; pa.colax = &g.A.col;
-      pa.mrowax = &g.Amul.row; pa.mcolax = &g.Amul.col;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-        int q = w;
-        const int ks = q % p.nsplit; q /= p.nsplit;
-        q /= p.ntn;
-        const int tm = q % p.ntm;
-        const int batch = q / p.ntm;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, batch);
-        const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, batch) : nullptr;
-        pa.begin_item(ab, mb, tm * TC_BM, g.M);
-        produce_item<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE>(pa, kb0, kb1, it, smem, 0, Cfg::A_PLANE,
-                                                                          full_bar, empty_bar, lane);
-      }
-    } else {
-      Producer<BN, TC_B_WARPS * 32, X3, false> pb;
-      pb.t = threadIdx.x - TC_A_WARPS * 32;
-      pb.K = g.K;
-      pb.mode = p.b_mode;
-      pb.rowax = &g.B.col; pb.colax = &g.B.row;    // B tile rows = n (B.col axis), tile columns = k (B.row axis)
-      pb.mrowax = &g.B.col; pb.mcolax = &g.B.row;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-        int q = w;
-        const int ks = q % p.nsplit; q /= p.nsplit;
-        const int tn = q % p.ntn; q /= p.ntn;
-        const int batch = q / p.ntm;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        const float* bb = (const float*)g.B.ptr + axoff64(g.B.batch, batch);
-        pb.begin_item(bb, nullptr, tn * BN, g.N);
-        produce_item<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE>(pb, kb0, kb1, it, smem,
-                                                                       Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE,
-                                                                       full_bar, empty_bar, lane);
-      }
-    }
+    if (warp < TC_A_WARPS)
+      produce_all<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
+          p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, threadIdx.x, lane);
+    else
+      produce_all<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
+          p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar,
+          threadIdx.x - TC_A_WARPS * 32, lane);
   } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ========================================
     if (lane == 0) {

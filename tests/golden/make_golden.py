@@ -80,20 +80,40 @@ def main():
         net = make_model("cpu", 1, nb, 1, K, 32, 32, 1, torch.FloatTensor(tmd), torch.FloatTensor(pa),
                          torch.FloatTensor(tmd), P, T, N, D, 32, 32, H)
         net.eval()
-        g = torch.Generator().manual_seed(7)
-        x = torch.randn(B, N, 1, T, generator=g)
-        target = torch.randn(B, N, P, generator=g)
         cheb = [t.detach().clone() for t in net.BlockList[0].cheb_conv_SAt.cheb_polynomials]
-
-        y32, l32, blk32, att32, g32 = run(net, x, target)
-
         net64 = copy.deepcopy(net).double()
         for blk in net64.BlockList:      # plain attributes are not moved by .double() (Q15)
             blk.adj_pa = blk.adj_pa.double()
             blk.cheb_conv_SAt.cheb_polynomials = [t.double() for t in cheb]
-        y64, l64, blk64, att64, g64 = run(net64, x.double(), target.double())
 
-        out = {"cfg": np.array([N, T, K, H, D, nb, B, P], np.int64),
+        # Conditioning check: the model has ReLUs, so an input whose pre-activation sits within fp32
+        # noise of a kink has a gradient that ANY fp32 implementation may or may not reproduce.  Pick
+        # the first data seed whose fp64 gradients are stable under a 1e-6 relative input perturbation.
+        for data_seed in range(7, 64):
+            g = torch.Generator().manual_seed(data_seed)
+            x = torch.randn(B, N, 1, T, generator=g)
+            target = torch.randn(B, N, P, generator=g)
+            y64, l64, blk64, att64, g64 = run(net64, x.double(), target.double())
+            cond = 0.0
+            for trial in range(8):              # several draws: each flips a near-kink unit with p ~ 1/2
+                eps = (1e-7, 3e-7, 1e-6, 3e-6)[trial % 4]
+                netp = copy.deepcopy(net64)            # perturb every weight AND the input
+                with torch.no_grad():
+                    for prm in netp.parameters():
+                        prm.mul_(1 + eps * torch.randn(prm.shape, generator=g, dtype=torch.float64))
+                xp = x.double() * (1 + eps * torch.randn(x.shape, generator=g, dtype=torch.float64))
+                _, _, _, _, gp = run(netp, xp, target.double())
+                cond = max(cond, max(float((gp[k] - g64[k]).abs().max() / g64[k].abs().max()) / (eps / 1e-6)
+                                     for k in g64 if g64[k] is not None))
+            print(f"  {name}: data seed {data_seed}: gradient sensitivity per 1e-6 weight+input noise (max of 8 draws) = {cond:.2e}")
+            if cond < 2e-5:
+                break
+        else:
+            raise SystemExit("no well-conditioned data seed found")
+
+        y32, l32, blk32, att32, g32 = run(net, x, target)
+
+        out = {"cfg": np.array([N, T, K, H, D, nb, B, P], np.int64), "data_seed": np.array(data_seed),
                "x": x.numpy(), "target": target.numpy(), "adj_tmd": tmd, "adj_pa": pa,
                "y32": y32.numpy(), "y64": y64.numpy(),
                "loss32": l32.numpy(), "loss64": l64.numpy()}

@@ -16,9 +16,12 @@ name = sys.argv[1] if len(sys.argv) > 1 else "g_n33"
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 2e-5
 orig = ct.contract_raw
 bad = []
+stats = []
 
 
 def checked(spec, A, B, **kw):
+    if kw.get("accumulate", 0) != 0:
+        return orig(spec, A, B, **kw)
     out = kw.get("out")
     pre = out.clone() if out is not None else None
     res = orig(spec, A, B, **kw)
@@ -31,6 +34,7 @@ def checked(spec, A, B, **kw):
         kw2["out"] = ref_out
     ref = orig(spec, A, B, **kw2)
     e = rel_err(res, ref)
+    stats.append((e, spec, tuple(A.shape), tuple(B.shape)))
     if e > thr:
         bad.append((spec, tuple(A.shape), tuple(B.shape), e))
         print(f"MISMATCH {spec:22s} A{tuple(A.shape)} B{tuple(B.shape)} err={e:.3e} kw={[k for k in kw if k != 'out']}")
@@ -54,3 +58,5 @@ print("pred err", rel_err(y.detach(), d["y64"]))
 worst = sorted(((rel_err(p.grad, g[k]), k) for k, p in net.named_parameters() if p.grad is not None), reverse=True)[:5]
 print("worst grads", worst)
 print("mismatching contractions:", len(bad))
+for e, spec, sa, sb in sorted(stats, reverse=True)[:12]:
+    print(f"  {e:.2e} {spec:24s} {sa} {sb}")
