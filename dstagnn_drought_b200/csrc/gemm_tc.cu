@@ -21,6 +21,10 @@
 // fp32-grade accuracy with the classic 3-pass split  a = a_hi + a_lo,  b = b_hi + b_lo,
 // a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (error ~2^-21 relative), all accumulated in the
 // same fp32 TMEM accumulator.  DSTAG_PREC_TF32 issues the single a_hi*b_hi pass.
+#include <cuda.h>   // CUtensorMap types only; cuTensorMapEncodeTiled is fetched at run time (no libcuda link)
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace dstag {
@@ -29,7 +33,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // 32 x 4 B = one 128-byte swizzle row
 constexpr int TC_A_WARPS = 8, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue warps 12-15: warp % 4 = TMEM lane quarter
 constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
-constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;   // 544
+constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;         // one thread issues the TMA bulk-tensor loads
+constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // 576
 constexpr int TC_SMEM_BUDGET = 196 * 1024;            // operand stages
 constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 32 * 33 * 4;   // per-warp 32 x 33 transpose buffers
 
@@ -39,6 +44,12 @@ struct TcParams {
   dstag_gemm_t g;
   int ntm, ntn, kblocks, kb_per_split, nsplit, total_items;
   int a_mode, b_mode;      // MODE_* (see Producer)
+  int a_tma, b_tma;        // operand tile arrives by TMA (cp.async.bulk.tensor) instead of LDG
+  int a_bdim[2], b_bdim[2];  // which of the two batch levels are real tensor-map dimensions
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap a, b;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -73,6 +84,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   while (!mbar_try_wait(addr, parity)) {
     if (backoff_ns) __nanosleep(backoff_ns);
   }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 4-D tiled bulk tensor copy global -> shared, completion signalled on an mbarrier (TMA)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -129,8 +152,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 //   K-major, SWIZZLE_128B: rows 128 B apart, 8-row groups SBO = 1024 B apart, 16-byte chunks XOR-ed
 //             with row % 8; a K step of 8 tf32 is +32 B inside the row.
 //   MN-major (tf32 => SWIZZLE_128B_BASE32B): atoms of 32 rows (one 128 B line) x 4 k (512 B), 32-byte
-//             units of line k XOR-ed with k % 4; LBO = 512 B between row blocks, SBO between k atoms;
-//             one K = 8 MMA step spans two atoms.
+//             units of line k XOR-ed with k % 4.  Atom (ka, mb) lives at (ka * ROWS/32 + mb) * 512:
+//             row blocks are adjacent atoms (the hardware assumes LBO = 512 B here -- a layout with
+//             the row blocks 4096 B apart and LBO = 4096 did NOT work), SBO = ROWS/32 * 512 B between
+//             k atoms; one K = 8 MMA step spans two atoms.
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
@@ -419,10 +444,72 @@ struct TcCfg {
   static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BAR_OFF = STAGES * STAGE;
-  static constexpr int EPI_OFF = BAR_OFF + 256;
+  static constexpr int EPI_OFF = BAR_OFF + 512;
   static constexpr int SMEM = EPI_OFF + TC_EPI_SMEM + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
+
+// The CTA's flat (output tile, k-block) sequence, walked identically by every role.
+struct PosIter {
+  int w, kb, kb1, tm, tn, batch;
+  __device__ __forceinline__ void enter(const TcParams& p) {
+    int q = w;
+    const int ks = q % p.nsplit; q /= p.nsplit;
+    tn = q % p.ntn; q /= p.ntn;
+    tm = q % p.ntm;
+    batch = q / p.ntm;
+    kb = ks * p.kb_per_split;
+    kb1 = min(p.kblocks, kb + p.kb_per_split);
+  }
+  __device__ __forceinline__ bool init(const TcParams& p) {
+    w = blockIdx.x;
+    if (w >= p.total_items) return false;
+    enter(p);
+    return true;
+  }
+  __device__ __forceinline__ bool next(const TcParams& p) {
+    if (++kb < kb1) return true;
+    w += gridDim.x;
+    if (w >= p.total_items) return false;
+    enter(p);
+    return true;
+  }
+};
+
+// TMA-fed operand: the raw fp32 tile lands (already swizzled) in the hi plane -- the tensor core ignores
+// the low 13 mantissa bits, so the raw tile IS the hi operand -- and these warps only derive the lo plane
+// (v - trunc_tf32(v)) for the 3-pass mode.  Up to STAGES k-blocks are in flight per operand.
+template <int ROWS, int NT, bool X3, int STAGES, int STAGE_BYTES>
+__device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, uint32_t plane_off,
+                                              uint32_t plane_bytes, uint64_t* full_bar, uint64_t* raw_bar, int t,
+                                              int lane) {
+  PosIter pos;
+  uint32_t it = 0;
+  for (bool ok = pos.init(p); ok; ok = pos.next(p), ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (it / STAGES) & 1;
+    if (lane == 0) mbar_wait(raw_bar + s, ph, 0);
+    __syncwarp();
+    if (X3) {
+      uint8_t* hi = smem + s * STAGE_BYTES + plane_off;
+      uint8_t* lo = hi + plane_bytes;
+#pragma unroll
+      for (int i = 0; i < ROWS * 8 / NT; ++i) {
+        const uint32_t off = (uint32_t)(t + i * NT) * 16u;
+        const float4 v = *reinterpret_cast<const float4*>(hi + off);
+        float4 l;
+        l.x = tf32_hi(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+        l.y = tf32_hi(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+        l.z = tf32_hi(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+        l.w = tf32_hi(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<float4*>(lo + off) = l;
+      }
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar + s);
+  }
+}
 
 // Flat producer pipeline over the CTA's (item, k-block) sequence: iteration i issues the global loads
 // of position i + 1 -- which may already belong to the NEXT output tile -- and then stores position i,
@@ -501,7 +588,8 @@ __device__ __forceinline__ void produce_all(const TcParams& p, uint8_t* smem, ui
 }
 
 template <int BN, bool X3, bool AMUL>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p,
+                                                                const __grid_constant__ TcMaps maps) {
   using Cfg = TcCfg<BN, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -510,7 +598,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES] MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2] MMA (commit) -> epilogue
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  uint64_t* rawa_bar = bars + 2 * Cfg::STAGES + 4;    // [STAGES] TMA bytes of the A tile landed
+  uint64_t* rawb_bar = bars + 3 * Cfg::STAGES + 4;    // [STAGES] TMA bytes of the B tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const dstag_gemm_t& g = p.g;
@@ -519,6 +609,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, TC_A_WARPS + TC_B_WARPS);
       mbar_init(empty_bar + s, 1);
+      mbar_init(rawa_bar + s, 1);
+      mbar_init(rawb_bar + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
@@ -534,13 +626,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   if (warp < TC_A_WARPS + TC_B_WARPS) {
     // =============================== producers =========================================
-    if (warp < TC_A_WARPS)
-      produce_all<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
-          p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, threadIdx.x, lane);
-    else
-      produce_all<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
-          p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar,
-          threadIdx.x - TC_A_WARPS * 32, lane);
+    if (warp < TC_A_WARPS) {
+      if (!AMUL && p.a_tma)
+        transform_all<TC_BM, TC_A_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(p, smem, 0, Cfg::A_PLANE, full_bar,
+                                                                          rawa_bar, threadIdx.x, lane);
+      else
+        produce_all<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
+            p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, threadIdx.x, lane);
+    } else {
+      if (p.b_tma)
+        transform_all<BN, TC_B_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(
+            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, lane);
+      else
+        produce_all<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
+            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar,
+            threadIdx.x - TC_A_WARPS * 32, lane);
+    }
+  } else if (warp == TC_TMA_WARP) {
+    // =============================== TMA issuer ========================================
+    if (lane == 0 && (p.a_tma || p.b_tma)) {
+      const bool a_mn = p.a_mode == MODE_MVEC, b_mn = p.b_mode == MODE_MVEC;
+      PosIter pos;
+      uint32_t it = 0;
+      for (bool ok = pos.init(p); ok; ok = pos.next(p), ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1, 0);            // the MMAs that read this stage have retired
+        uint8_t* st = smem + s * Cfg::STAGE;
+        const int k0 = pos.kb * TC_BK;
+        if (!AMUL && p.a_tma) {
+          const int bl = p.a_bdim[1] ? pos.batch % g.A.batch.d1 : 0, bh = p.a_bdim[0] ? pos.batch / g.A.batch.d1 : 0;
+          mbar_expect_tx(rawa_bar + s, Cfg::A_PLANE);
+          if (a_mn) {
+#pragma unroll
+            for (int mb = 0; mb < TC_BM / 32; ++mb)
+              tma_load_4d(st + mb * 4096, &maps.a, rawa_bar + s, pos.tm * TC_BM + mb * 32, k0, bl, bh);
+          } else {
+            tma_load_4d(st, &maps.a, rawa_bar + s, k0, pos.tm * TC_BM, bl, bh);
+          }
+        }
+        if (p.b_tma) {
+          const int bl = p.b_bdim[1] ? pos.batch % g.B.batch.d1 : 0, bh = p.b_bdim[0] ? pos.batch / g.B.batch.d1 : 0;
+          uint8_t* sb = st + Cfg::PLANES * Cfg::A_PLANE;
+          mbar_expect_tx(rawb_bar + s, Cfg::B_PLANE);
+          if (b_mn) {
+#pragma unroll
+            for (int mb = 0; mb < BN / 32; ++mb)
+              tma_load_4d(sb + mb * 4096, &maps.b, rawb_bar + s, pos.tn * BN + mb * 32, k0, bl, bh);
+          } else {
+            tma_load_4d(sb, &maps.b, rawb_bar + s, k0, pos.tn * BN, bl, bh);
+          }
+        }
+      }
+    }
   } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ========================================
     if (lane == 0) {
@@ -548,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       // descriptor advance per K step of 8 (16-byte units): +32 B inside the swizzle row (K-major),
-      // two 4-k atoms of SBO = ROWS/32 * 512 B each (MN-major)
+      // two 4-k atoms = +1024 B (MN-major)
       const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;
       const uint64_t b_adv = b_mn ? (uint64_t)((BN / 32) * 1024 >> 4) : 2ull;
       uint32_t it = 0, item = 0;
@@ -752,10 +890,62 @@ static int pick_mode(const dstag_operand_t& o, const dstag_axis_t& kax, const ds
   return MODE_ROWG;
 }
 
+// ---- TMA tensor maps -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* env = getenv("DSTAG_TC_TMA");
+    if (env && env[0] == '0') return nullptr;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// Rank-4 map (inner, outer, batch_lo, batch_hi) of one operand in its KVEC (inner = K) or MVEC (inner = rows)
+// orientation.  Returns false when the view is not expressible (two-level row / K axis, odd strides).
+static bool make_tmap(CUtensorMap* map, int* bdim, const dstag_operand_t& o, const dstag_axis_t& kax,
+                      const dstag_axis_t& rowax, int mode, long long K, long long rows, long long batch,
+                      int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc || !o.ptr) return false;
+  if (mode != MODE_KVEC) return false;   // MN-major tiles need 512-byte atoms per (k-atom, row block): LDG path
+  if (kax.d1 != 1 || rowax.d1 != 1) return false;
+  const long long inner_n = mode == MODE_KVEC ? K : rows, outer_n = mode == MODE_KVEC ? rows : K;
+  const long long outer_stride = mode == MODE_KVEC ? rowax.s0 : kax.s0;     // elements
+  if (outer_stride <= 0 || outer_stride % 4 != 0) return false;
+  const long long nb_lo = o.batch.d1 > 1 ? o.batch.d1 : 1;
+  const long long nb_hi = (batch + nb_lo - 1) / nb_lo;
+  const long long s_lo = o.batch.d1 > 1 ? o.batch.s1 : 0, s_hi = o.batch.s0;
+  bdim[1] = (nb_lo > 1 && s_lo > 0) ? 1 : 0;
+  bdim[0] = (nb_hi > 1 && s_hi > 0) ? 1 : 0;
+  if ((bdim[1] && s_lo % 4 != 0) || (bdim[0] && s_hi % 4 != 0)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)inner_n, (cuuint64_t)outer_n, (cuuint64_t)(bdim[1] ? nb_lo : 1),
+                        (cuuint64_t)(bdim[0] ? nb_hi : 1)};
+  const cuuint64_t dummy = (cuuint64_t)outer_stride * 4;                    // stride of a size-1 dimension
+  cuuint64_t strides[3] = {(cuuint64_t)outer_stride * 4, bdim[1] ? (cuuint64_t)s_lo * 4 : dummy,
+                           bdim[0] ? (cuuint64_t)s_hi * 4 : dummy};
+  cuuint32_t box[4] = {32u, (cuuint32_t)(mode == MODE_KVEC ? box_rows : 32), 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapSwizzle sw = mode == MODE_KVEC ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static int g_num_sms = 0;
 
 template <int BN, bool X3, bool AMUL>
-static int launch_tc(const TcParams& p, cudaStream_t stream) {
+static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream) {
   using Cfg = TcCfg<BN, X3>;
   static bool configured = false;
   if (!configured) {
@@ -767,7 +957,7 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
-  gemm_tc_kernel<BN, X3, AMUL><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p);
+  gemm_tc_kernel<BN, X3, AMUL><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p, maps);
   DSTAG_RETURN_LAUNCH("dstag_gemm(tcgen05)");
 }
 
@@ -795,9 +985,14 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
   p.b_mode = pick_mode(g->B, g->B.row, g->B.col, nullptr, nullptr, nullptr);
   const bool x3 = g->precision == DSTAG_PREC_TF32X3;
   const bool am = g->Amul.ptr != nullptr;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
+  p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
+  p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
-  return x3 ? (am ? launch_tc<BN_, true, true>(p, stream) : launch_tc<BN_, true, false>(p, stream)) \
-            : (am ? launch_tc<BN_, false, true>(p, stream) : launch_tc<BN_, false, false>(p, stream))
+  return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
+            : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))
   if (bn == 128) DSTAG_TC_DISPATCH(128);
   if (bn == 64) DSTAG_TC_DISPATCH(64);
   DSTAG_TC_DISPATCH(32);
