@@ -166,6 +166,22 @@ def output_shape(spec: str, A, B):
     return tuple(size[l] for l in pl.c)
 
 
+def _prefers_swap(spec: str, out, A, B) -> bool:
+    """True when the output's memory-innermost index belongs to the FIRST operand only (it would be an
+    m index: strided epilogue stores) -- the caller then swaps the operands."""
+    pl = plan(spec)
+    if not pl.c or not pl.m or not pl.n:
+        return False
+    if out is not None:
+        strides = {l: out.stride(i) for i, l in enumerate(pl.c) if out.shape[i] > 1}
+        if not strides:
+            return False
+        inner = min(strides, key=strides.get)
+    else:
+        inner = pl.c[-1]
+    return inner in pl.m
+
+
 def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[torch.Tensor] = None,
                  a_mul: Optional[Tuple[str, torch.Tensor]] = None,
                  c_add: Optional[Tuple[str, torch.Tensor]] = None,
@@ -173,6 +189,13 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                  relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
                  precision=None, tag: Optional[str] = None) -> torch.Tensor:
     """Enqueue one contraction on the current CUDA stream.  No autograd."""
+    if a_mul is None and _prefers_swap(spec, out, A, B):
+        # C = A.B is symmetric in its operands; put the one that owns the output's innermost index
+        # second, so that index becomes the GEMM's n (contiguous, coalesced epilogue stores)
+        ins, res = spec.replace(" ", "").split("->")
+        sa, sb = ins.split(",")
+        return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
+                            accumulate=accumulate, split_k=split_k, precision=precision, tag=tag)
     lib = _lib.load()
     _check(A, "A"), _check(B, "B")
     for opt in (a_mul, c_add, c_mul):

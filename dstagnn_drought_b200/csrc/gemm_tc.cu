@@ -733,6 +733,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const bool c_unit = g.C.col.d1 == 1 && g.C.col.s0 == 1;
     const bool ca_unit = !g.Cadd.ptr || (g.Cadd.col.d1 == 1 && g.Cadd.col.s0 == 1);
     const bool cm_unit = !g.Cmul.ptr || (g.Cmul.col.d1 == 1 && g.Cmul.col.s0 == 1);
+    auto inner1 = [](const dstag_axis_t& a) { return (a.d1 == 1 ? a.s0 : a.s1) == 1; };
+    const bool c_inner1 = inner1(g.C.col);
+    const bool ca_inner1 = !g.Cadd.ptr || inner1(g.Cadd.col) || (g.Cadd.col.s0 == 0 && g.Cadd.col.d1 == 1);
+    const bool cm_inner1 = !g.Cmul.ptr || inner1(g.Cmul.col) || (g.Cmul.col.s0 == 0 && g.Cmul.col.d1 == 1);
     uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
       int q = w;
@@ -787,14 +791,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               *dst = o;
             }
           }
-        } else if (c_unit && ca_unit && cm_unit) {
-          // (b) row-contiguous but unaligned / narrow / atomic: transpose the 32 x 32 block through
-          //     shared memory so that consecutive lanes touch consecutive columns (coalesced)
+        } else if (c_inner1 && ca_inner1 && cm_inner1) {
+          // (b) columns contiguous in memory but unaligned / narrow / atomic / two-level (e.g. n = (x, t)):
+          //     transpose the 32 x 32 block through shared memory so that consecutive lanes touch
+          //     consecutive columns (coalesced)
 #pragma unroll
           for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = v[j];
           __syncwarp();
           const int n = n0 + lane;
           const bool nok = n < g.N;
+          const int co = nok ? axoff32(g.C.col, n) : 0;
+          const int cao = (Cab && nok) ? axoff32(g.Cadd.col, n) : 0;
+          const int cmo = (Cmb && nok) ? axoff32(g.Cmul.col, n) : 0;
 #pragma unroll 4
           for (int rr = 0; rr < 32; ++rr) {
             const int mr = tm * TC_BM + q4 * 32 + rr;
@@ -803,10 +811,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int rmo = __shfl_sync(0xffffffffu, cm_ro, rr);
             if (mr < g.M && nok) {
               float o = g.alpha * tbuf[rr * 33 + lane];
-              if (Cab) o += __ldg(Cab + rao + n);
-              if (Cmb) o *= __ldg(Cmb + rmo + n);
+              if (Cab) o += __ldg(Cab + rao + cao);
+              if (Cmb) o *= __ldg(Cmb + rmo + cmo);
               if (g.relu) o = fmaxf(o, 0.f);
-              float* dst = Cb + ro + n;
+              float* dst = Cb + ro + co;
               if (g.accumulate == DSTAG_ACC_STORE) *dst = o;
               else if (g.accumulate == DSTAG_ACC_ADD) *dst += o;
               else atomicAdd(dst, o);
@@ -863,7 +871,7 @@ static bool operand_fits32(const dstag_operand_t& o, long long nrow, long long n
 }
 
 bool gemm_tc_supported(const dstag_gemm_t* g) {
-  if (g->N < 8 || g->K < 8 || g->M < 32) return false;
+  if (g->N < 8 || g->K < 8 || g->M < 8) return false;
   if ((long long)g->M * g->N * g->K * g->batch < (1ll << 19)) return false;   // tiny: not worth a persistent launch
   return operand_fits32(g->A, g->M, g->K) && operand_fits32(g->Amul, g->M, g->K) &&
          operand_fits32(g->B, g->K, g->N) && operand_fits32(g->C, g->M, g->N) &&

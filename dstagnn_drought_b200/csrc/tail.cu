@@ -298,3 +298,220 @@ int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const flo
 }
 
 }  // extern "C"
+
+// =======================================================================================
+// Fused block tail for the PEMS shapes (T = 12, C = 32):
+//   tc = fcmy(cat) ; tc' = dropout(tc) ; tco = relu(tc' [+ g]) ; out = LN_C(relu(r + tco))
+// One WARP per node (lane = channel): the 24 -> 12 fcmy Linear of model/DSTAGNN_my.py:243 runs on
+// register-resident rows against the weight matrix in the constant bank (FFMA with an immediate
+// constant operand -- no loads), and the LayerNorm over the 32 channels is a warp-shuffle
+// reduction per time step.  tc / dtc never touch HBM.
+// =======================================================================================
+namespace dstag {
+
+constexpr int kFusedMaxW = 4096;
+__constant__ float c_wf[kFusedMaxW];   // fcmy weight (T, S) row-major, re-uploaded per call (stream-ordered)
+__constant__ float c_wf2[kFusedMaxW];  // second copy: the backward uses every weight twice (recompute + d cat);
+                                       // with ONE symbol the compiler keeps all T*S weights in registers
+                                       // (and spills) instead of using constant-bank FFMA operands
+__constant__ float c_bf[64];           // fcmy bias (T)
+
+// dropout multipliers of one (node, channel) row: element e = row * T + t draws word (e & 3) of
+// philox(e >> 2) exactly like dropout_scale(), but one Philox evaluation serves 4 time steps
+template <int T>
+__device__ __forceinline__ void row_dropout(float (&ds)[T], long long row, unsigned long long seed, float p,
+                                            float inv_keep) {
+  static_assert(T % 4 == 0, "row_dropout needs T % 4 == 0");
+#pragma unroll
+  for (int i = 0; i < T / 4; ++i) {
+    const uint4 q = philox4x32((unsigned long long)(row * (T / 4) + i), seed);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      ds[4 * i + j] = ((float)(w[j] >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256)
+tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ g, const float* __restrict__ r,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, long long X,
+                      float drop_p, unsigned long long seed) {
+  constexpr int S = 3 * T - 12, C = 32;
+  static_assert(S % 4 == 0 && T % 4 == 0 && T <= 32, "fused tail tiling");
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float gam = __ldg(gamma + lane), bet = __ldg(beta + lane);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long x = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); x < X; x += nwarps) {
+    const long long row = x * C + lane;
+    float cv[S];
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(cat + row * S) + i);
+      cv[4 * i] = q.x; cv[4 * i + 1] = q.y; cv[4 * i + 2] = q.z; cv[4 * i + 3] = q.w;
+    }
+    float rv[T];
+#pragma unroll
+    for (int i = 0; i < T / 4; ++i) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(r + row * T) + i);
+      rv[4 * i] = q.x; rv[4 * i + 1] = q.y; rv[4 * i + 2] = q.z; rv[4 * i + 3] = q.w;
+    }
+    float v[T], ds[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ds[t] = 1.f;
+    if (drop_p > 0.f) row_dropout<T>(ds, row, seed, drop_p, inv_keep);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float a = c_bf[t];
+#pragma unroll
+      for (int s = 0; s < S; ++s) a = fmaf(cv[s], c_wf[t * S + s], a);
+      a *= ds[t];
+      if (g) a += __ldg(g + (x * T + t) * C + lane);          // channels-last: coalesced over lanes
+      v[t] = fmaxf(rv[t] + fmaxf(a, 0.f), 0.f);
+    }
+    float o[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float mu = warp_sum(v[t]) * (1.f / C);
+      const float d = v[t] - mu;
+      const float rs = rsqrtf(warp_sum(d * d) * (1.f / C) + eps);
+      o[t] = d * rs * gam + bet;
+      if (lane == t) { mean[x * T + t] = mu; rstd[x * T + t] = rs; }
+    }
+#pragma unroll
+    for (int i = 0; i < T / 4; ++i)
+      reinterpret_cast<float4*>(out + row * T)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256, 2)
+tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ cat, const float* __restrict__ g,
+                      const float* __restrict__ r, const float* __restrict__ gamma, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, float* __restrict__ dcat, float* __restrict__ dtc_out,
+                      float* __restrict__ dg, float* __restrict__ dr, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, long long X, float drop_p, unsigned long long seed) {
+  constexpr int S = 3 * T - 12, C = 32, NW = 8;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * NW;
+  const float gam = __ldg(gamma + lane);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float acc_g = 0.f, acc_be = 0.f;     // d gamma[c], d beta[c] partials (lane = c)
+  for (long long x = (long long)blockIdx.x * NW + wid; x < X; x += nwarps) {
+    const long long row = x * C + lane;
+    float cv[S];
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(cat + row * S) + i);
+      cv[4 * i] = q.x; cv[4 * i + 1] = q.y; cv[4 * i + 2] = q.z; cv[4 * i + 3] = q.w;
+    }
+    float ds[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ds[t] = 1.f;
+    if (drop_p > 0.f) row_dropout<T>(ds, row, seed, drop_p, inv_keep);
+    float dtc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      // ---- recompute the forward of this element
+      float a = c_bf[t];
+#pragma unroll
+      for (int s = 0; s < S; ++s) a = fmaf(cv[s], c_wf[t * S + s], a);
+      a *= ds[t];
+      if (g) a += __ldg(g + (x * T + t) * C + lane);
+      const float s2 = __ldg(r + row * T + t) + fmaxf(a, 0.f);
+      const float vv = fmaxf(s2, 0.f);
+      // ---- LayerNorm backward over the 32 lanes
+      const float mu = __ldg(mean + x * T + t), rs = __ldg(rstd + x * T + t);
+      const float xh = (vv - mu) * rs;
+      const float d = __ldg(dout + row * T + t);
+      const float gy = d * gam;
+      const float m1 = warp_sum(gy) * (1.f / C);
+      const float m2 = warp_sum(gy * xh) * (1.f / C);
+      acc_g = fmaf(d, xh, acc_g);
+      acc_be += d;
+      const float ds2 = s2 > 0.f ? rs * (gy - m1 - xh * m2) : 0.f;
+      const float ds1 = a > 0.f ? ds2 : 0.f;
+      dr[row * T + t] = ds2;
+      if (dg) dg[(x * T + t) * C + lane] = ds1;                 // channels-last, coalesced over lanes
+      dtc[t] = ds1 * ds[t];
+    }
+#pragma unroll
+    for (int i = 0; i < T / 4; ++i)    // d tc feeds the (tensor-core) weight-gradient contraction and d bias
+      reinterpret_cast<float4*>(dtc_out + row * T)[i] = make_float4(dtc[4 * i], dtc[4 * i + 1], dtc[4 * i + 2], dtc[4 * i + 3]);
+    // ---- d cat[s] = sum_t dtc[t] Wf[t][s]
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) a = fmaf(dtc[t], c_wf2[t * S + 4 * i + j], a);
+        o[j] = a;
+      }
+      reinterpret_cast<float4*>(dcat + row * S)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  atomicAdd(dgamma + lane, acc_g);
+  atomicAdd(dbeta + lane, acc_be);
+}
+
+static int upload_fcmy(const float* wf, const float* bf, int T, int S, cudaStream_t stream, const char* name) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_wf, wf, sizeof(float) * T * S, 0, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_wf2, wf, sizeof(float) * T * S, 0, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_bf, bf, sizeof(float) * T, 0, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) {
+    set_error("%s: constant upload failed: %s", name, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace dstag
+
+extern "C" {
+
+int dstag_tail_fused_supported(int32_t C, int32_t T) { return (C == 32 && T == 12) ? 1 : 0; }
+
+int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, const float* g, const float* r,
+                         const float* gamma, const float* beta, float eps, float* out, float* mean, float* rstd,
+                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream) {
+  DSTAG_CHECK_ARG(cat && wf && bf && r && gamma && beta && out && mean && rstd, "dstag_tail_fused_fwd: null pointer");
+  DSTAG_CHECK_ARG(X > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_fused_fwd: bad sizes");
+  if (!dstag_tail_fused_supported(C, T)) {
+    set_error("dstag_tail_fused_fwd: only C = 32, T = 12 is fused (got C=%d T=%d); use the unfused path", C, T);
+    return DSTAG_ERR_UNSUPPORTED;
+  }
+  int rc = upload_fcmy(wf, bf, T, 3 * T - 12, (cudaStream_t)stream, "dstag_tail_fused_fwd");
+  if (rc) return rc;
+  const long long blocks = (X + 7) / 8;
+  const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
+  tail_fused_fwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(cat, g, r, gamma, beta, eps, out, mean, rstd, X,
+                                                                    drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_tail_fused_fwd");
+}
+
+int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, const float* bf, const float* g,
+                         const float* r, const float* gamma, const float* mean, const float* rstd, float* dcat,
+                         float* dtc, float* dg, float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C,
+                         int32_t T, float drop_p, uint64_t seed, void* stream) {
+  DSTAG_CHECK_ARG(dout && cat && wf && bf && r && gamma && mean && rstd && dcat && dtc && dr && dgamma && dbeta,
+                  "dstag_tail_fused_bwd: null pointer");
+  DSTAG_CHECK_ARG((g == nullptr) == (dg == nullptr), "dstag_tail_fused_bwd: g and dg must both be given or both be null");
+  DSTAG_CHECK_ARG(X > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_fused_bwd: bad sizes");
+  if (!dstag_tail_fused_supported(C, T)) {
+    set_error("dstag_tail_fused_bwd: only C = 32, T = 12 is fused (got C=%d T=%d)", C, T);
+    return DSTAG_ERR_UNSUPPORTED;
+  }
+  int rc = upload_fcmy(wf, bf, T, 3 * T - 12, (cudaStream_t)stream, "dstag_tail_fused_bwd");
+  if (rc) return rc;
+  const long long blocks = (X + 7) / 8;
+  const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
+  tail_fused_bwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, cat, g, r, gamma, mean, rstd, dcat, dtc, dg,
+                                                                    dr, dgamma, dbeta, X, drop_p, seed);
+  DSTAG_RETURN_LAUNCH("dstag_tail_fused_bwd");
+}
+
+}  // extern "C"

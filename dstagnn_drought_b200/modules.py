@@ -200,19 +200,23 @@ class DSTAGNN_block(nn.Module):
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
                                  self.gtu5.con2out.weight, self.gtu5.con2out.bias,
                                  self.gtu7.con2out.weight, self.gtu7.con2out.bias)       # (B*N, C, 3T-12)
-        # 8. fcmy over the concatenated time axis                                    (line 243)
+        # 8-11. fcmy over the concatenated time axis, combine, residual, LayerNorm over channels
+        #       (lines 243-252); one fused kernel for the PEMS shapes, GEMM + tail kernel otherwise
         lin = self.fcmy[0]
-        tc = contract("rs,ts->rt", cat.view(B * N * C, 3 * T - 12), lin.weight, c_add=("t", lin.bias))
-        tc = tc.view(B * N, C, T)
-        # 9-11. combine, residual, LayerNorm over channels                           (lines 244-252)
         p_fc = self.fcmy[1].p if train else 0.0
         seed = ops.next_seed() if train else 0
         if Fin == 1:
             w_res = self.residual_conv.weight.view(C, Fin)
             r = contract("xft,cf->xct", x.view(B * N, Fin, T), w_res, c_add=("c", self.residual_conv.bias))
-            out = ops.BlockTail.apply(tc, None, r, self.ln.weight, self.ln.bias, p_fc, seed)
+            g_res = None
         else:
-            out = ops.BlockTail.apply(tc, g, x.view(B * N, C, T), self.ln.weight, self.ln.bias, p_fc, seed)
+            r = x.view(B * N, C, T)
+            g_res = g
+        if ops.FusedTail.supported(C, T):
+            out = ops.FusedTail.apply(cat, lin.weight, lin.bias, g_res, r, self.ln.weight, self.ln.bias, p_fc, seed)
+        else:
+            tc = contract("rs,ts->rt", cat.view(B * N * C, 3 * T - 12), lin.weight, c_add=("t", lin.bias))
+            out = ops.BlockTail.apply(tc.view(B * N, C, T), g_res, r, self.ln.weight, self.ln.bias, p_fc, seed)
         return out.view(B, N, C, T), logits
 
 

@@ -372,3 +372,57 @@ class BlockTail(torch.autograd.Function):
                                       dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
                                       _stream(tc)), "dstag_tail_bwd")
         return dtc, dg, dr, dgamma, dbeta, None, None
+
+
+class FusedTail(torch.autograd.Function):
+    """fcmy + BlockTail in one kernel for C = 32, T = 12 (lines 243-252): the Linear over the
+    concatenated GTU time axis is evaluated per (node, channel) row in registers, so tc / dtc never make
+    an HBM round trip in the forward, and the backward emits dcat directly.
+    cat (X, C, S); wf (T, S); bf (T); g (X, T, C) or None; r (X, C, T) -> out (X, C, T)."""
+
+    @staticmethod
+    def supported(C_, T_):
+        return bool(_lib.load().dstag_tail_fused_supported(C_, T_))
+
+    @staticmethod
+    def forward(ctx, cat, wf, bf, g, r, gamma, beta, drop_p, seed):
+        lib = _lib.load()
+        for t, n in ((cat, "cat"), (wf, "wf"), (bf, "bf"), (r, "r"), (gamma, "gamma"), (beta, "beta")):
+            _check(t, n)
+        cat, wf, bf, r = cat.contiguous(), wf.contiguous(), bf.contiguous(), r.contiguous()
+        if g is not None:
+            g = g.contiguous()
+        X, Cc, T = r.shape
+        out = torch.empty_like(r)
+        mean = torch.empty((X, T), device=r.device, dtype=torch.float32)
+        rstd = torch.empty((X, T), device=r.device, dtype=torch.float32)
+        _lib.check(lib.dstag_tail_fused_fwd(cat.data_ptr(), wf.data_ptr(), bf.data_ptr(), _p(g), r.data_ptr(),
+                                            gamma.data_ptr(), beta.data_ptr(), 1e-5, out.data_ptr(),
+                                            mean.data_ptr(), rstd.data_ptr(), X, Cc, T, float(drop_p), int(seed),
+                                            _stream(r)), "dstag_tail_fused_fwd")
+        ctx.save_for_backward(cat, wf, bf, g, r, gamma, mean, rstd)
+        ctx.meta = (float(drop_p), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        cat, wf, bf, g, r, gamma, mean, rstd = ctx.saved_tensors
+        drop_p, seed = ctx.meta
+        X, Cc, T = r.shape
+        S = cat.shape[-1]
+        dout = dout.contiguous()
+        dcat = torch.empty_like(cat)
+        dtc = torch.empty_like(r)
+        dr = torch.empty_like(r)
+        dg = torch.empty_like(g) if g is not None else None
+        dgamma = torch.zeros(Cc, device=r.device, dtype=torch.float32)
+        dbeta = torch.zeros(Cc, device=r.device, dtype=torch.float32)
+        _lib.check(lib.dstag_tail_fused_bwd(dout.data_ptr(), cat.data_ptr(), wf.data_ptr(), bf.data_ptr(), _p(g),
+                                            r.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                            dcat.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
+                                            dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
+                                            _stream(r)), "dstag_tail_fused_bwd")
+        dwf = contract_raw("rt,rs->ts", dtc.view(X * Cc, T), cat.view(X * Cc, S), tag="fcmy_dw")
+        dbf = colsum(dtc, X * Cc, T)
+        return dcat, dwf, dbf, dg, dr, dgamma, dbeta, None, None

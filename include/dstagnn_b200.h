@@ -174,6 +174,24 @@ int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const flo
                    float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
                    float drop_p, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fused block tail for C = 32, T = 12 (all PEMS configurations): the fcmy Linear over the
+ * concatenated time axis (model/DSTAGNN_my.py:243) is folded into the tail, so tc never touches HBM:
+ *   tc = cat . wf^T + bf ; then exactly dstag_tail_fwd.   cat (X, C, S = 3T-12), wf (T, S), bf (T).
+ * One warp per node, fcmy weights in the constant bank, LayerNorm by warp shuffles.
+ * dstag_tail_fused_supported() tells whether (C, T) is served; otherwise use dstag_gemm + dstag_tail_*.
+ * ---------------------------------------------------------------------------------- */
+int dstag_tail_fused_supported(int32_t C, int32_t T);
+int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, const float* g, const float* r,
+                         const float* gamma, const float* beta, float eps, float* out, float* mean, float* rstd,
+                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
+/* Writes dcat (X, C, S), dtc (X, C, T) (needed for the fcmy weight / bias gradients, which are a
+ * dstag_gemm over (X*C) and a dstag_colsum), dr, dg (when g != NULL); accumulates dgamma / dbeta. */
+int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, const float* bf, const float* g,
+                         const float* r, const float* gamma, const float* mean, const float* rstd, float* dcat,
+                         float* dtc, float* dg, float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C,
+                         int32_t T, float drop_p, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 2
+        return 3
 
     def dstag_last_error(self):
         return self.err
@@ -254,6 +254,30 @@ class FakeLib:
         _arr(dgamma, Cc)[:] += (d * xh).sum((0, 2))
         _arr(dbeta, Cc)[:] += d.sum((0, 2))
         return 0
+
+
+    def dstag_tail_fused_supported(self, Cc, T):
+        return 1 if (Cc == 32 and T == 12) else 0
+
+    def dstag_tail_fused_fwd(self, cat, wf, bf, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed,
+                             stream):
+        S = 3 * T - 12
+        tc = (_arr(cat, X * Cc * S).reshape(X, Cc, S).astype(np.float64) @ _arr(wf, T * S).reshape(T, S).T
+              + _arr(bf, T)).astype(np.float32)
+        self._tc = np.ascontiguousarray(tc)
+        return self.dstag_tail_fwd(self._tc.ctypes.data, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p,
+                                   seed, stream)
+
+    def dstag_tail_fused_bwd(self, dout, cat, wf, bf, g, r, gamma, mean, rstd, dcat, dtc, dg, dr, dgamma, dbeta, X,
+                             Cc, T, drop_p, seed, stream):
+        S = 3 * T - 12
+        W = _arr(wf, T * S).reshape(T, S).astype(np.float64)
+        tc = np.ascontiguousarray((_arr(cat, X * Cc * S).reshape(X, Cc, S).astype(np.float64) @ W.T
+                                   + _arr(bf, T)).astype(np.float32))
+        rc = self.dstag_tail_bwd(dout, tc.ctypes.data, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma, dbeta, X, Cc, T,
+                                 drop_p, seed, stream)
+        _arr(dcat, X * Cc * S).reshape(X, Cc, S)[:] = _arr(dtc, X * Cc * T).reshape(X, Cc, T).astype(np.float64) @ W
+        return rc
 
 
 def install(monkeypatch):

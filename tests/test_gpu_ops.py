@@ -288,3 +288,52 @@ def test_transpose_softmax_colsum_relu(dev):
     assert float(P[:, 33:].abs().max()) == 0.0
     y, dy = torch.randn(1001, device=dev), torch.randn(1001, device=dev)
     assert torch.equal(relu_bwd(y, dy), dy * (y > 0))
+
+
+@pytest.mark.parametrize("cfg", [(3, True), (500, False), (37, True)])
+def test_fused_tail(dev, precision, cfg):
+    """fcmy + tail in one kernel (C = 32, T = 12) against the unfused formula."""
+    from dstagnn_drought_b200.ops import FusedTail
+    X, with_g = cfg
+    Cc, T, S = 32, 12, 24
+    assert FusedTail.supported(Cc, T) and not FusedTail.supported(32, 18)
+    torch.manual_seed(12)
+    cat = torch.randn(X, Cc, S, device=dev)
+    wf, bf = torch.randn(T, S, device=dev) * 0.3, torch.rand(T, device=dev)
+    g = torch.randn(X, T, Cc, device=dev)
+    r = torch.randn(X, Cc, T, device=dev)
+    gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
+    dout = torch.randn(X, Cc, T, device=dev)
+
+    def ref_fn(cat_, wf_, bf_, g_, r_, ga_, be_):
+        tc = cat_ @ wf_.t() + bf_
+        tco = torch.relu(tc + g_.permute(0, 2, 1)) if with_g else torch.relu(tc)
+        v = torch.relu(r_ + tco).permute(0, 2, 1)
+        return torch.nn.functional.layer_norm(v, (Cc,), ga_, be_, 1e-5).permute(0, 2, 1)
+
+    def fn(cat_, wf_, bf_, g_, r_, ga_, be_):
+        return FusedTail.apply(cat_, wf_, bf_, g_ if with_g else None, r_, ga_, be_, 0.0, 0)
+
+    args = [cat, wf, bf, g, r, gam, bet]
+    out, gr = _grads(fn, args, dout)
+    ref, rr = _grads(ref_fn, [a.double() for a in args], dout.double())
+    assert rel_err(out, ref) < TOL
+    for i, (got, want) in enumerate(zip(gr, rr)):
+        if i == 3 and not with_g:
+            continue
+        assert rel_err(got, want) < 5e-5, i
+
+
+def test_fused_tail_dropout_matches_unfused_mask(dev):
+    """Same seed => the fused kernel drops exactly the elements the unfused tail kernel drops."""
+    from dstagnn_drought_b200.ops import BlockTail, FusedTail
+    torch.manual_seed(13)
+    X, Cc, T, S, p = 300, 32, 12, 24, 0.05
+    cat = torch.randn(X, Cc, S, device=dev)
+    wf, bf = torch.randn(T, S, device=dev) * 0.3, torch.rand(T, device=dev)
+    r = torch.randn(X, Cc, T, device=dev)
+    gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
+    tc = cat @ wf.t() + bf
+    a = FusedTail.apply(cat, wf, bf, None, r, gam, bet, p, 4242)
+    b = BlockTail.apply(tc, None, r, gam, bet, p, 4242)
+    assert rel_err(a, b) < 1e-5
