@@ -53,6 +53,7 @@ SIGNATURES = {
     "dstag_softmax_fwd": (C.c_int, [_F, _i64, _i32, _i32, _F]),
     "dstag_softmax_bwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _F]),
     "dstag_relu_bwd": (C.c_int, [_F, _F, _F, _i64, _F]),
+    "dstag_sat_softmax_fwd": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tattn_fwd": (C.c_int, [_F, _F, _i32, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tattn_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_fwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _i32, _i32, _F]),

@@ -247,6 +247,145 @@ __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __rest
     dx[i] = __ldg(y + i) > 0.f ? __ldg(dy + i) : 0.f;
 }
 
+// ======================================================================================
+// Warp-per-row variants (rows of up to 1024 elements: every shape of the PEMS configurations).
+// A warp keeps its row in registers, reduces with shuffles and never touches shared memory or
+// a block barrier, so 8 rows per CTA are in flight and the kernels run at HBM speed.
+// ======================================================================================
+constexpr int kWR = 32;                 // register elements per lane -> rows up to 1024
+
+__global__ void __launch_bounds__(256)
+ln_fwd_warp_kernel(const float* __restrict__ a, const float* __restrict__ tab, int tab_mod,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, int L,
+                   float drop_p, unsigned long long seed) {
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  const float invL = 1.f / (float)L;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+    const float* ap = a + (long long)r * L;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
+    float v[kWR];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = 0.f;
+      if (c < L) {
+        v[i] = __ldg(ap + c);
+        if (tp) v[i] += __ldg(tp + c);
+        s += v[i];
+      }
+    }
+    const float mu = warp_sum(s) * invL;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      if (c < L) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+    }
+    const float rs = rsqrtf(warp_sum(q) * invL + eps);
+    float* yp = y + (long long)r * L;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      if (c < L) {
+        float o = (v[i] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
+        if (drop_p > 0.f) o *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
+        yp[c] = o;
+      }
+    }
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ tab,
+                   int tab_mod, const float* __restrict__ gamma, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, float* __restrict__ dpre, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, int rows, int L, float drop_p, unsigned long long seed) {
+  extern __shared__ float sm[];          // [2][L] CTA-level d gamma / d beta accumulators
+  float* sg = sm;
+  float* sb = sm + L;
+  for (int c = threadIdx.x; c < L; c += blockDim.x) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  const float invL = 1.f / (float)L;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float ag[kWR], ab[kWR];
+#pragma unroll
+  for (int i = 0; i < kWR; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+    const float* ap = a + (long long)r * L;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
+    const float* dyp = dy + (long long)r * L;
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float xh[kWR], gg[kWR];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      xh[i] = 0.f; gg[i] = 0.f;
+      if (c < L) {
+        float v = __ldg(ap + c);
+        if (tp) v += __ldg(tp + c);
+        const float x = (v - mu) * rs;
+        float d = __ldg(dyp + c);
+        if (drop_p > 0.f) d *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
+        const float g = d * __ldg(gamma + c);
+        xh[i] = x; gg[i] = g;
+        ag[i] = fmaf(d, x, ag[i]);
+        ab[i] += d;
+        s1 += g;
+        s2 = fmaf(g, x, s2);
+      }
+    }
+    const float m1 = warp_sum(s1) * invL, m2 = warp_sum(s2) * invL;
+    float* op = dpre + (long long)r * L;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      if (c < L) op[c] = rs * (gg[i] - m1 - xh[i] * m2);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kWR; ++i) {
+    const int c = lane + 32 * i;
+    if (c < L) { atomicAdd(sg + c, ag[i]); atomicAdd(sb + c, ab[i]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < L; c += blockDim.x) {
+    atomicAdd(dgamma + c, sg[c]);
+    atomicAdd(dbeta + c, sb[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_bwd_warp_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int L, int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+    const float* pp = p + r * ld;
+    float* dpp = dp + r * ld;
+    float pv[kWR], dv[kWR];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      pv[i] = 0.f; dv[i] = 0.f;
+      if (c < L) { pv[i] = __ldg(pp + c); dv[i] = dpp[c]; s = fmaf(pv[i], dv[i], s); }
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int i = 0; i < kWR; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld) dpp[c] = c < L ? pv[i] * (dv[i] - s) : 0.f;
+    }
+  }
+}
+
 static int ensure_smem(const void* fn, size_t bytes, const char* name) {
   if (bytes > (size_t)kMaxDynSmem) {
     set_error("%s: row too long (%zu bytes of shared memory needed, %d available)", name, bytes,
@@ -277,6 +416,13 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_fwd: bad sizes rows=%d L=%d", rows, L);
   DSTAG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dstag_layernorm_fwd: bad dropout p");
+  if (a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {
+    const int blocks = (rows + 7) / 8;
+    const int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
+    ln_fwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L,
+                                                              drop_p, seed);
+    DSTAG_RETURN_LAUNCH("dstag_layernorm_fwd(warp)");
+  }
   const size_t smem = (size_t)(L + 40) * sizeof(float);
   int rc = ensure_smem((const void*)ln_fwd_kernel, smem, "dstag_layernorm_fwd");
   if (rc) return rc;
@@ -295,6 +441,13 @@ int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a
                   "dstag_layernorm_bwd: null pointer");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_bwd: bad sizes rows=%d L=%d", rows, L);
+  if (a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {
+    const int blocks = (rows + 7) / 8;
+    const int grid = blocks < kNumSMs * 2 ? blocks : kNumSMs * 2;
+    ln_bwd_warp_kernel<<<grid, 256, (size_t)2 * L * sizeof(float), (cudaStream_t)stream>>>(
+        dy, a, tab, tab_mod, gamma, mean, rstd, dpre, dgamma, dbeta, rows, L, drop_p, seed);
+    DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd(warp)");
+  }
   const size_t smem = (size_t)(4 * L + 40) * sizeof(float);
   int rc = ensure_smem((const void*)ln_bwd_kernel, smem, "dstag_layernorm_bwd");
   if (rc) return rc;
@@ -355,6 +508,12 @@ int dstag_softmax_fwd(float* x, int64_t rows, int32_t L, int32_t ld, void* strea
 
 int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_t ld, void* stream) {
   DSTAG_CHECK_ARG(p && dp && rows > 0 && L > 0 && ld >= L, "dstag_softmax_bwd: bad arguments");
+  if (ld <= 32 * kWR) {
+    const long long blocks = (rows + 7) / 8;
+    const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
+    softmax_bwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, dp, rows, L, ld);
+    DSTAG_RETURN_LAUNCH("dstag_softmax_bwd(warp)");
+  }
   const size_t smem = (size_t)(2 * L + 40) * sizeof(float);
   int rc = ensure_smem((const void*)softmax_bwd_kernel, smem, "dstag_softmax_bwd");
   if (rc) return rc;

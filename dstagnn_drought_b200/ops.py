@@ -223,9 +223,14 @@ class SpatialChebConv(torch.autograd.Function):
         FT = x3.shape[-1]
         Qs, Ks = qk[:, :, 0], qk[:, :, 1]                      # (B,N,K,dk) views
         P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
-        contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
-                     c_add=("kji", biasT[..., :N]))
-        _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+        biasT = biasT.contiguous()
+        rc = lib.dstag_sat_softmax_fwd(qk.data_ptr(), biasT.data_ptr(), P.data_ptr(), B, N, K, dk, ld, _stream(P))
+        if rc == -3:      # DSTAG_ERR_SMEM: N too large for the fused row strip -> GEMM + row softmax
+            contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
+                         c_add=("kji", biasT[..., :N]))
+            _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+        else:
+            _lib.check(rc, "dstag_sat_softmax_fwd")
         Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
         contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd")
         ctx.save_for_backward(qk, P, tkT, x3)

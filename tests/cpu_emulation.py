@@ -153,6 +153,17 @@ class FakeLib:
         D[:, L:] = 0
         return 0
 
+    def dstag_sat_softmax_fwd(self, qk, biasT, P, B, N, K, dk, ld, stream):
+        self.launches += 1
+        q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk).astype(np.float64)
+        s = np.einsum("bjkd,bikd->bkji", q[:, :, 1], q[:, :, 0]) / math.sqrt(dk)
+        s = s + _arr(biasT, K * N * ld).reshape(K, N, ld)[None, :, :, :N]
+        e = np.exp(s - s.max(-1, keepdims=True))
+        out = _arr(P, B * K * N * ld).reshape(B, K, N, ld)
+        out[..., :N] = e / e.sum(-1, keepdims=True)
+        out[..., N:] = 0
+        return 0
+
     def dstag_relu_bwd(self, y, dy, dx, n, stream):
         self.launches += 1
         _arr(dx, n)[:] = np.where(_arr(y, n) > 0, _arr(dy, n), 0)
