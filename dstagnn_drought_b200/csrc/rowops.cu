@@ -416,7 +416,7 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_fwd: bad sizes rows=%d L=%d", rows, L);
   DSTAG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dstag_layernorm_fwd: bad dropout p");
-  if (a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {
+  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {   // measured slower than block-per-row
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
     ln_fwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L,
@@ -441,7 +441,7 @@ int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a
                   "dstag_layernorm_bwd: null pointer");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_bwd: bad sizes rows=%d L=%d", rows, L);
-  if (a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {
+  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {   // measured slower than block-per-row
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 2 ? blocks : kNumSMs * 2;
     ln_bwd_warp_kernel<<<grid, 256, (size_t)2 * L * sizeof(float), (cudaStream_t)stream>>>(

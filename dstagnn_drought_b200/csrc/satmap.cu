@@ -52,9 +52,19 @@ sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ b
 #pragma unroll 8
     for (int d = 0; d < dk; ++d) {
       const float4 q = *reinterpret_cast<const float4*>(QsT + d * kSatQld + 4 * iq);
+      float kvv[MR];                                              // warp-uniform rows: one broadcast load
+      if (MR == 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(KsT + d * R + rgp * MR);
+        kvv[0] = t4.x; kvv[1 % MR] = t4.y; kvv[2 % MR] = t4.z; kvv[3 % MR] = t4.w;
+      } else if (MR == 2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(KsT + d * R + rgp * MR);
+        kvv[0] = t2.x; kvv[1 % MR] = t2.y;
+      } else {
+        kvv[0] = KsT[d * R + rgp * MR];
+      }
 #pragma unroll
       for (int rr = 0; rr < MR; ++rr) {
-        const float kv = KsT[d * R + rgp * MR + rr];             // warp-uniform: broadcast
+        const float kv = kvv[rr];
         acc[rr][0] = fmaf(q.x, kv, acc[rr][0]);
         acc[rr][1] = fmaf(q.y, kv, acc[rr][1]);
         acc[rr][2] = fmaf(q.z, kv, acc[rr][2]);
@@ -125,6 +135,8 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float*
     sat_softmax_fwd_kernel<R_><<<grid, kSatThreads, smem, (cudaStream_t)stream>>>(qk, biasT, P, N, K, dk, ld, scale); \
     DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd");                                                                \
   } while (0)
+  if (2 * need(32) <= budget + 24 * 1024) DSTAG_SAT_LAUNCH(32);   // two CTAs per SM preferred
+  if (2 * need(16) <= budget + 24 * 1024) DSTAG_SAT_LAUNCH(16);
   if (need(32) <= budget) DSTAG_SAT_LAUNCH(32);
   if (need(16) <= budget) DSTAG_SAT_LAUNCH(16);
   if (need(8) <= budget) DSTAG_SAT_LAUNCH(8);
