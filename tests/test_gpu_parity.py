@@ -64,7 +64,9 @@ def test_net_matches_reference_golden(name, precision):
 
 @pytest.mark.parametrize("shape", [dict(N=170, T=12, K=3, H=3, D=64, nb=2, B=3),
                                    dict(N=307, T=12, K=3, H=3, D=128, nb=2, B=2),
-                                   dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2)])
+                                   dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2),
+                                   # GAMBIA drought layout (in_channels = 1): T = 144, K = 2, H = 2, d_model = 64
+                                   dict(N=37, T=144, K=2, H=2, D=64, nb=2, B=2)])
 def test_net_matches_oracle_at_config_shapes(shape):
     """Ragged PEMS08 / PEMS04 node counts and a longer horizon, against the fp64 CPU oracle."""
     from oracle import dstagnn_oracle as O
