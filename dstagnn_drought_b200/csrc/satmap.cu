@@ -139,8 +139,9 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float*
   if (2 * need(16) <= budget + 24 * 1024) DSTAG_SAT_LAUNCH(16);
   if (need(32) <= budget) DSTAG_SAT_LAUNCH(32);
   if (need(16) <= budget) DSTAG_SAT_LAUNCH(16);
-  if (need(8) <= budget) DSTAG_SAT_LAUNCH(8);
-  set_error("dstag_sat_softmax_fwd: N = %d too large for the shared-memory row strip", N);
+  // Strips of 8 rows would fit up to N ~ 6000 but leave one FMA per shared-memory load: the
+  // tensor-core logits GEMM + row softmax pair is faster there (measured at N = 4096).
+  set_error("dstag_sat_softmax_fwd: N = %d too large for a 16-row shared-memory strip; use dstag_gemm + dstag_softmax_fwd", N);
   return DSTAG_ERR_SMEM;
 #undef DSTAG_SAT_LAUNCH
 }

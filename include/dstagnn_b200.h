@@ -127,7 +127,7 @@ int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_
  * (SScaledDotProductAttention, model/DSTAGNN_my.py:19, and lines 126-127 of cheb_conv_withSAt):
  *   P[b,k,j,i] = softmax_i( Qs[b,i,k,:] . Ks[b,j,k,:] / sqrt(dk) + biasT[k,j,i] ),  pad columns = 0
  *   qk (B, N, 2, K, dk) packed [W_Q | W_K] projections; biasT (K, N, ld); P (B, K, N, ld); ld % 4 == 0.
- * Returns DSTAG_ERR_SMEM when a strip of 8 rows of N logits does not fit in shared memory
+ * Returns DSTAG_ERR_SMEM when a strip of 16 rows of N logits does not fit in shared memory (N > ~2900)
  * (then use dstag_gemm + dstag_softmax_fwd). */
 int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float* P, int32_t B, int32_t N, int32_t K,
                           int32_t dk, int32_t ld, void* stream);
