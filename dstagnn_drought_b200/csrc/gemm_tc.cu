@@ -45,6 +45,7 @@ struct TcParams {
   int ntm, ntn, kblocks, kb_per_split, nsplit, total_items;
   int a_mode, b_mode;      // MODE_* (see Producer)
   int a_tma, b_tma;        // operand tile arrives by TMA (cp.async.bulk.tensor) instead of LDG
+  int a_async, b_async;    // operand chunks arrive by cp.async (vector modes without a tensor map)
   int a_bdim[2], b_bdim[2];  // which of the two batch levels are real tensor-map dimensions
 };
 
@@ -96,6 +97,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS); bytes beyond src_bytes are zero-filled
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -386,6 +395,53 @@ struct Producer {
     }
   }
 
+  // Asynchronous variant of load_stream for the vector modes: the 16-byte chunks go straight from
+  // global memory to their final (swizzled) place in the shared-memory plane with cp.async, so any
+  // number of k-blocks can be in flight without holding registers.
+  __device__ __forceinline__ void issue_stream(int kb, uint8_t* plane, const float* bp, const dstag_axis_t& rax,
+                                               const dstag_axis_t& cax, int roff, int rlo) const {
+    const int k0 = kb * TC_BK;
+    const int fr = first_row();
+    const uint32_t pbase = smem_u32(plane);
+    if (mode == MODE_KVEC) {
+      const int c = t & 7, rb = t >> 3;
+      const int k = k0 + 4 * c;
+      int kbytes = 4 * (K - k);
+      kbytes = kbytes < 0 ? 0 : (kbytes > 16 ? 16 : kbytes);
+      Walk rw;
+      row_walk(rw, rax, roff, rlo);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t bytes = (fr + RB * i < limit) ? (uint32_t)kbytes : 0u;
+        cp_async16(pbase + swz(rb + RB * i, c), bytes ? (const void*)(bp + rw.off + k) : (const void*)bp, bytes);
+        rw.next();
+      }
+    } else {   // MODE_MVEC
+      const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
+      const int mb = mq >> 3, mc = mq & 7;
+      const int kf = k0 + kl0;
+      Walk w;
+      w.init(cax, kf, 1);
+      int nv = limit - fr;
+      nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int kl = kl0 + j, ka = kl >> 2, kr = kl & 3;
+        const uint32_t off = (uint32_t)(((ka * (ROWS / 32) + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) +
+                                        ((mc & 1) << 4));
+        const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
+        cp_async16(pbase + off, bytes ? (const void*)(bp + roff + w.off) : (const void*)bp, bytes);
+        w.next();
+      }
+    }
+  }
+  __device__ __forceinline__ void issue(int kb, uint8_t* plane_hi, uint8_t* plane_lo) const {
+    issue_stream(kb, plane_hi, base, *rowax, *colax, r_off, r_lo);
+    if constexpr (MUL) {
+      if (mbase) issue_stream(kb, plane_lo, mbase, *mrowax, *mcolax, m_off, m_lo);   // factor parks in the lo plane
+    }
+  }
+
   __device__ __forceinline__ void load(int kb, float4 (&v)[NV], float4 (&m)[NM]) const {
     load_stream<NV>(kb, v, base, *rowax, *colax, r_off, r_lo);
     if constexpr (MUL) {
@@ -511,6 +567,103 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
   }
 }
 
+// Asynchronous producer for the vector load modes (K- or row-contiguous, 16B aligned): cp.async drops
+// the raw fp32 chunks directly into the stage's hi plane (the Hadamard factor, if any, into the lo plane)
+// STAGES-1 k-blocks ahead; when a block has landed the same warps finish it in place:
+//   plain   : lo = v - trunc_tf32(v)               (the raw tile IS the hi operand)
+//   Hadamard: v = p * t ; hi = rn_tf32(v) ; lo = rn_tf32(v - hi)
+template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES, bool IS_A>
+__device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, uint32_t plane_off,
+                                              uint32_t plane_bytes, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint64_t* raw_bar, int t, int lane) {
+  using P = Producer<ROWS, NT, X3, MUL>;
+  const dstag_gemm_t& g = p.g;
+  P pr;
+  pr.t = t;
+  pr.K = g.K;
+  if (IS_A) {
+    pr.mode = p.a_mode;
+    pr.rowax = &g.A.row; pr.colax = &g.A.col;
+    pr.mrowax = &g.Amul.row; pr.mcolax = &g.Amul.col;
+  } else {
+    pr.mode = p.b_mode;
+    pr.rowax = &g.B.col; pr.colax = &g.B.row;
+    pr.mrowax = &g.B.col; pr.mcolax = &g.B.row;
+  }
+  const bool has_mul = MUL && g.Amul.ptr != nullptr;
+  PosIter pi, px;
+  bool oki = pi.init(p), okx = px.init(p);
+  if (!okx) return;
+  int cur_w = -1;
+  uint32_t ni = 0, nx = 0;
+  auto issue_one = [&]() {
+    const int s = ni % STAGES;
+    const uint32_t ph = (ni / STAGES) & 1;
+    if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1, 0);
+    __syncwarp();
+    if (pi.w != cur_w) {
+      cur_w = pi.w;
+      if (IS_A) {
+        const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, pi.batch);
+        const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, pi.batch) : nullptr;
+        pr.begin_item(ab, mb, pi.tm * TC_BM, g.M);
+      } else {
+        pr.begin_item((const float*)g.B.ptr + axoff64(g.B.batch, pi.batch), nullptr, pi.tn * ROWS, g.N);
+      }
+    }
+    uint8_t* hi = smem + s * STAGE_BYTES + plane_off;
+    pr.issue(pi.kb, hi, hi + plane_bytes);
+    cp_async_arrive(raw_bar + s);
+    oki = pi.next(p);
+    ++ni;
+  };
+  for (int d = 0; d < STAGES - 1 && oki; ++d) issue_one();
+  while (okx) {
+    const int s = nx % STAGES;
+    const uint32_t ph = (nx / STAGES) & 1;
+    if (lane == 0) mbar_wait(raw_bar + s, ph, 0);
+    __syncwarp();
+    uint8_t* hi = smem + s * STAGE_BYTES + plane_off;
+    uint8_t* lo = hi + plane_bytes;
+    if (has_mul) {
+#pragma unroll
+      for (int i = 0; i < ROWS * 8 / NT; ++i) {
+        const uint32_t off = (uint32_t)(t + i * NT) * 16u;
+        const float4 v = mul4(*reinterpret_cast<const float4*>(hi + off), *reinterpret_cast<const float4*>(lo + off));
+        if (X3) {
+          const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(lo + off) =
+              make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+        } else {
+          *reinterpret_cast<float4*>(hi + off) = v;
+        }
+      }
+      fence_proxy_async_smem();
+    } else if (X3) {
+#pragma unroll
+      for (int i = 0; i < ROWS * 8 / NT; ++i) {
+        const uint32_t off = (uint32_t)(t + i * NT) * 16u;
+        const float4 v = *reinterpret_cast<const float4*>(hi + off);
+        float4 l;
+        l.x = tf32_hi(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+        l.y = tf32_hi(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+        l.z = tf32_hi(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+        l.w = tf32_hi(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<float4*>(lo + off) = l;
+      }
+      fence_proxy_async_smem();
+    } else {
+      fence_proxy_async_smem();      // cp.async wrote through the generic proxy
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar + s);
+    okx = px.next(p);
+    ++nx;
+    if (oki) issue_one();
+  }
+}
+
 // Flat producer pipeline over the CTA's (item, k-block) sequence: iteration i issues the global loads
 // of position i + 1 -- which may already belong to the NEXT output tile -- and then stores position i,
 // so load latency is hidden across tile boundaries too (tiles with a single k-block, e.g. Q K^T with
@@ -609,8 +762,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, TC_A_WARPS + TC_B_WARPS);
       mbar_init(empty_bar + s, 1);
-      mbar_init(rawa_bar + s, 1);
-      mbar_init(rawb_bar + s, 1);
+      mbar_init(rawa_bar + s, p.a_async ? TC_A_WARPS * 32 : 1);
+      mbar_init(rawb_bar + s, p.b_async ? TC_B_WARPS * 32 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
@@ -630,6 +783,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (!AMUL && p.a_tma)
         transform_all<TC_BM, TC_A_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(p, smem, 0, Cfg::A_PLANE, full_bar,
                                                                           rawa_bar, threadIdx.x, lane);
+      else if (p.a_async)
+        produce_async<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
+            p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, rawa_bar, threadIdx.x, lane);
       else
         produce_all<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
             p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, threadIdx.x, lane);
@@ -637,6 +793,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (p.b_tma)
         transform_all<BN, TC_B_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(
             p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, lane);
+      else if (p.b_async)
+        produce_async<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
+            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar, rawb_bar,
+            threadIdx.x - TC_A_WARPS * 32, lane);
       else
         produce_all<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
             p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar,
@@ -998,6 +1158,14 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
   p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
   p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
   p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
+  static int async_on = -1;
+  if (async_on < 0) {
+    const char* env = getenv("DSTAG_TC_ASYNC");
+    async_on = (env && env[0] == '0') ? 0 : 1;
+  }
+  // the Hadamard factor parks in the lo plane: only possible in the 3-pass mode (which has one)
+  p.a_async = (async_on && !p.a_tma && (p.a_mode == MODE_KVEC || p.a_mode == MODE_MVEC) && (!am || x3)) ? 1 : 0;
+  p.b_async = (async_on && !p.b_tma && (p.b_mode == MODE_KVEC || p.b_mode == MODE_MVEC)) ? 1 : 0;
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
             : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))
