@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -44,12 +44,12 @@ SIGNATURES = {
     "dstag_reset_launch_count": (None, []),
     "dstag_gemm": (C.c_int, [C.POINTER(Gemm), _F]),
     "dstag_gemm_uses_tensor_cores": (C.c_int, [C.POINTER(Gemm)]),
-    "dstag_layernorm_fwd": (C.c_int, [_F, _i64, _i64, _i32, _i64, _F, _i32, _F, _F, _f32, _F, _F, _F,
+    "dstag_layernorm_fwd": (C.c_int, [_F, _i64, _i64, _i32, _i64, _F, _i32, _i64, _F, _F, _f32, _F, _i64, _F, _F,
                                       _i32, _i32, _f32, _u64, _F]),
-    "dstag_layernorm_bwd": (C.c_int, [_F, _F, _i64, _i64, _i32, _i64, _F, _i32, _F, _F, _F, _F, _F, _F,
-                                      _i32, _i32, _f32, _u64, _F]),
+    "dstag_layernorm_bwd": (C.c_int, [_F, _i64, _F, _i64, _i64, _i32, _i64, _F, _i32, _i64, _F, _F, _F, _F, _i64,
+                                      _F, _F, _i32, _i32, _f32, _u64, _F]),
     "dstag_colsum": (C.c_int, [_F, _F, _i64, _i64, _i64, _F]),
-    "dstag_transpose": (C.c_int, [_F, _F, _i32, _i32, _i32, _F]),
+    "dstag_transpose": (C.c_int, [_F, _i64, _F, _i64, _i32, _i32, _i32, _F]),
     "dstag_softmax_fwd": (C.c_int, [_F, _i64, _i32, _i32, _F]),
     "dstag_softmax_bwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _F]),
     "dstag_relu_bwd": (C.c_int, [_F, _F, _F, _i64, _F]),

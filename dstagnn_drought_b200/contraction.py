@@ -240,6 +240,51 @@ def colsum(t2d: torch.Tensor, rows: int, cols: int, ld: Optional[int] = None) ->
     return out
 
 
+def padded_ld(n: int) -> int:
+    """Leading dimension for rows of n floats: the next multiple of 4 (16-byte rows), so that the
+    contraction engine can use its vector / TMA load paths on odd graph sizes (N = 883, 170, ...)."""
+    return (n + 3) // 4 * 4
+
+
+def empty_rows(shape, device) -> torch.Tensor:
+    """Uninitialised fp32 tensor of ``shape`` whose innermost rows are padded to 16 bytes
+    (a view ``buf[..., :n]``; contiguous when n % 4 == 0)."""
+    n = shape[-1]
+    ld = padded_ld(n)
+    buf = torch.empty(tuple(shape[:-1]) + (ld,), device=device, dtype=torch.float32)
+    return buf if ld == n else buf[..., :n]
+
+
+def is_row_padded(t: torch.Tensor) -> bool:
+    """True for the layout ``empty_rows`` produces (or plain contiguous): inner stride 1, outer dims
+    contiguous over a leading dimension >= the row length."""
+    if t.dim() == 0 or t.stride(-1) != 1:
+        return False
+    if t.dim() == 1:
+        return True
+    ld = t.stride(-2)
+    if ld < t.shape[-1]:
+        return False
+    expect = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            return False
+        expect *= t.shape[d]
+    return True
+
+
+def dense_rows(t: torch.Tensor) -> torch.Tensor:
+    """``t`` itself when it is contiguous or row padded, else a contiguous copy."""
+    return t if is_row_padded(t) else t.contiguous()
+
+
+def empty_like_rows(t: torch.Tensor) -> torch.Tensor:
+    """Gradient buffer with the same (possibly row-padded) layout as ``t``."""
+    if t.is_contiguous() or not is_row_padded(t):
+        return torch.empty(t.shape, device=t.device, dtype=torch.float32)
+    return torch.empty_strided(t.shape, t.stride(), device=t.device, dtype=torch.float32)
+
+
 def relu_bwd(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     dy = dy.contiguous()
@@ -271,8 +316,12 @@ def reduce_to(sub_out: str, grad: torch.Tensor, sub_keep: str) -> torch.Tensor:
 
 class _Contract(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, A, B, cadd, amul, spec, cadd_sub, amul_sub, alpha, relu):
-        out = contract_raw(spec, A, B, a_mul=(amul_sub, amul) if amul is not None else None,
+    def forward(ctx, A, B, cadd, amul, spec, cadd_sub, amul_sub, alpha, relu, pad_rows):
+        out = None
+        if pad_rows:
+            assert not relu
+            out = empty_rows(output_shape(spec, A, B), A.device)
+        out = contract_raw(spec, A, B, out=out, a_mul=(amul_sub, amul) if amul is not None else None,
                            c_add=(cadd_sub, cadd) if cadd is not None else None, alpha=alpha, relu=relu)
         ctx.spec, ctx.cadd_sub, ctx.amul_sub, ctx.alpha, ctx.relu = spec, cadd_sub, amul_sub, alpha, relu
         ctx.has_cadd = cadd is not None
@@ -283,27 +332,27 @@ class _Contract(torch.autograd.Function):
     def backward(ctx, dC):
         A, B, amul, out = ctx.saved_tensors
         pl = plan(ctx.spec)
-        dC = dC.contiguous()
+        dC = dense_rows(dC)
         if ctx.relu:
             dC = relu_bwd(out, dC)
         dA = dB = dadd = None
         am = (ctx.amul_sub, amul) if amul is not None else None
         if ctx.needs_input_grad[0]:
-            dA = torch.empty(A.shape, device=A.device, dtype=torch.float32)
+            dA = empty_like_rows(A)        # gradients keep the (row-padded) layout of their tensors
             contract_raw(f"{pl.c},{pl.b}->{pl.a}", dC, B, out=dA, c_mul=am, alpha=ctx.alpha)
         if ctx.needs_input_grad[1]:
-            dB = torch.empty(B.shape, device=B.device, dtype=torch.float32)
+            dB = empty_like_rows(B)
             contract_raw(f"{pl.a},{pl.c}->{pl.b}", A, dC, out=dB, a_mul=am, alpha=ctx.alpha)
         if ctx.has_cadd and ctx.needs_input_grad[2]:
-            dadd = reduce_to(pl.c, dC, ctx.cadd_sub)
-        return dA, dB, dadd, None, None, None, None, None, None
+            dadd = reduce_to(pl.c, dC.contiguous(), ctx.cadd_sub)
+        return dA, dB, dadd, None, None, None, None, None, None, None
 
 
 def contract(spec: str, A: torch.Tensor, B: torch.Tensor, *, c_add=None, a_mul=None, alpha: float = 1.0,
-             relu: bool = False) -> torch.Tensor:
+             relu: bool = False, pad_rows: bool = False) -> torch.Tensor:
     """Differentiable contraction.  ``c_add=(subscripts, tensor)`` is a differentiable additive
     epilogue term (bias vector / bias matrix); ``a_mul=(subscripts, tensor)`` is a constant
     Hadamard factor applied to the first operand while it is loaded."""
     cadd_sub, cadd = c_add if c_add is not None else (None, None)
     amul_sub, amul = a_mul if a_mul is not None else (None, None)
-    return _Contract.apply(A, B, cadd, amul, spec, cadd_sub, amul_sub, float(alpha), bool(relu))
+    return _Contract.apply(A, B, cadd, amul, spec, cadd_sub, amul_sub, float(alpha), bool(relu), bool(pad_rows))

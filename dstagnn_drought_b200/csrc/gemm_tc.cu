@@ -103,6 +103,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 // arrive on the mbarrier once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -416,7 +419,7 @@ struct Producer {
         cp_async16(pbase + swz(rb + RB * i, c), bytes ? (const void*)(bp + rw.off + k) : (const void*)bp, bytes);
         rw.next();
       }
-    } else {   // MODE_MVEC
+    } else if (mode == MODE_MVEC) {
       const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
       const int mb = mq >> 3, mc = mq & 7;
       const int kf = k0 + kl0;
@@ -432,6 +435,39 @@ struct Producer {
         const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
         cp_async16(pbase + off, bytes ? (const void*)(bp + roff + w.off) : (const void*)bp, bytes);
         w.next();
+      }
+    } else if (mode == MODE_KSC) {
+      // unaligned K-contiguous rows: 4-byte copies, lane <-> k (one coalesced line per row)
+      const int kl = t & 31, wq = t >> 5;
+      const int k = k0 + kl;
+      const bool kok = k < K;
+      const int ko = kok ? axoff32(cax, k) : 0;
+      Walk rw;
+      row_walk(rw, rax, roff, rlo);
+#pragma unroll
+      for (int i = 0; i < 4 * NV; ++i) {
+        const int r = wq + NW * i;
+        const uint32_t bytes = (kok && fr + NW * i < limit) ? 4u : 0u;
+        cp_async4(pbase + swz(r, kl >> 2) + ((kl & 3) << 2), bytes ? (const void*)(bp + rw.off + ko) : (const void*)bp,
+                  bytes);
+        rw.next();
+      }
+    } else {
+      // unaligned row-contiguous operand: 4-byte copies, lane <-> row, transposed into the K-major tile
+      const int r = t % ROWS, c0 = (t / ROWS) * NV;
+      const int kf = k0 + (t / ROWS) * KPTR;
+      Walk w;
+      w.init(cax, kf, 1);
+      const bool rok = fr < limit;
+      const float* rp = bp + roff;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t bytes = (rok && kf + 4 * c + j < K) ? 4u : 0u;
+          cp_async4(pbase + swz(r, c0 + c) + (j << 2), bytes ? (const void*)(rp + w.off) : (const void*)bp, bytes);
+          w.next();
+        }
       }
     }
   }
@@ -1164,8 +1200,14 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
     async_on = (env && env[0] == '0') ? 0 : 1;
   }
   // the Hadamard factor parks in the lo plane: only possible in the 3-pass mode (which has one)
-  p.a_async = (async_on && !p.a_tma && (p.a_mode == MODE_KVEC || p.a_mode == MODE_MVEC) && (!am || x3)) ? 1 : 0;
-  p.b_async = (async_on && !p.b_tma && (p.b_mode == MODE_KVEC || p.b_mode == MODE_MVEC)) ? 1 : 0;
+  static int async_scalar = -1;
+  if (async_scalar < 0) {
+    const char* env = getenv("DSTAG_TC_ASYNC_SCALAR");
+    async_scalar = (env && env[0] == '0') ? 0 : 1;
+  }
+  auto vec = [](int m) { return m == MODE_KVEC || m == MODE_MVEC; };
+  p.a_async = (async_on && !p.a_tma && (vec(p.a_mode) || async_scalar) && (!am || x3)) ? 1 : 0;
+  p.b_async = (async_on && !p.b_tma && (vec(p.b_mode) || async_scalar)) ? 1 : 0;
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
             : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))

@@ -13,8 +13,8 @@ constexpr int kMaxDynSmem = 200 * 1024;
 // ======================================================================================
 __global__ void __launch_bounds__(kRowThreads)
 ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a_div, long long a_sc,
-              const float* __restrict__ tab, int tab_mod, const float* __restrict__ gamma,
-              const float* __restrict__ beta, float eps, float* __restrict__ y,
+              const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, float* __restrict__ y, long long y_ld,
               float* __restrict__ mean, float* __restrict__ rstd, int rows, int L, float drop_p,
               unsigned long long seed) {
   extern __shared__ float sm[];
@@ -24,7 +24,7 @@ ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a
   const float invL = 1.f / (float)L;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* ap = a + (long long)(r / a_div) * a_s0 + (long long)(r % a_div) * a_s1;
-    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * tab_ld : nullptr;
     float s = 0.f;
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
       float v = __ldg(ap + (long long)c * a_sc);
@@ -39,7 +39,7 @@ ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a
       q = fmaf(d, d, q);
     }
     const float rs = rsqrtf(block_sum(q, red) * invL + eps);
-    float* yp = y + (long long)r * L;
+    float* yp = y + (long long)r * y_ld;
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
       float o = (row[c] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
       if (drop_p > 0.f) o *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
@@ -54,11 +54,12 @@ ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a
 // dgamma / dbeta are accumulated per CTA in shared memory, then one atomicAdd per column.
 // ======================================================================================
 __global__ void __launch_bounds__(kRowThreads)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, long long a_s0,
+ln_bwd_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ a, long long a_s0,
               long long a_s1, int a_div, long long a_sc, const float* __restrict__ tab, int tab_mod,
-              const float* __restrict__ gamma, const float* __restrict__ mean,
-              const float* __restrict__ rstd, float* __restrict__ dpre, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int rows, int L, float drop_p, unsigned long long seed) {
+              long long tab_ld, const float* __restrict__ gamma, const float* __restrict__ mean,
+              const float* __restrict__ rstd, float* __restrict__ dpre, long long dpre_ld,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int L, float drop_p,
+              unsigned long long seed) {
   extern __shared__ float sm[];
   float* xh = sm;            // xhat
   float* gg = sm + L;        // dy * gamma
@@ -70,8 +71,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, long lo
   for (int c = threadIdx.x; c < L; c += blockDim.x) { ag[c] = 0.f; ab[c] = 0.f; }
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* ap = a + (long long)(r / a_div) * a_s0 + (long long)(r % a_div) * a_s1;
-    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
-    const float* dyp = dy + (long long)r * L;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * tab_ld : nullptr;
+    const float* dyp = dy + (long long)r * dy_ld;
     const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
     float s1 = 0.f, s2 = 0.f;
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
@@ -90,7 +91,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, long lo
     }
     const float m1 = block_sum(s1, red) * invL;
     const float m2 = block_sum(s2, red) * invL;
-    float* op = dpre + (long long)r * L;
+    float* op = dpre + (long long)r * dpre_ld;
     for (int c = threadIdx.x; c < L; c += blockDim.x) op[c] = rs * (gg[c] - m1 - xh[c] * m2);
   }
   for (int c = threadIdx.x; c < L; c += blockDim.x) {
@@ -173,21 +174,22 @@ colsum_kernel(const float* __restrict__ in, float* __restrict__ out, long long r
 // Batched transpose through a padded shared tile.
 // ======================================================================================
 __global__ void __launch_bounds__(256)
-transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+transpose_kernel(const float* __restrict__ in, long long in_ld, float* __restrict__ out, long long out_ld, int R,
+                 int C) {
   __shared__ float tile[32][33];
-  const long long base = (long long)blockIdx.z * R * C;
+  const long long ibase = (long long)blockIdx.z * R * in_ld, obase = (long long)blockIdx.z * C * out_ld;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int r = r0 + ty + j, c = c0 + tx;
-    if (r < R && c < C) tile[ty + j][tx] = __ldg(in + base + (long long)r * C + c);
+    if (r < R && c < C) tile[ty + j][tx] = __ldg(in + ibase + (long long)r * in_ld + c);
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int c = c0 + ty + j, r = r0 + tx;
-    if (r < R && c < C) out[base + (long long)c * R + r] = tile[tx][ty + j];
+    if (r < R && c < C) out[obase + (long long)c * out_ld + r] = tile[tx][ty + j];
   }
 }
 
@@ -409,14 +411,16 @@ using namespace dstag;
 extern "C" {
 
 int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
-                        const float* tab, int32_t tab_mod, const float* gamma, const float* beta,
-                        float eps, float* y, float* mean, float* rstd, int32_t rows, int32_t L,
+                        const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma, const float* beta,
+                        float eps, float* y, int64_t y_ld, float* mean, float* rstd, int32_t rows, int32_t L,
                         float drop_p, uint64_t seed, void* stream) {
   DSTAG_CHECK_ARG(a && gamma && beta && y && mean && rstd, "dstag_layernorm_fwd: null pointer");
+  DSTAG_CHECK_ARG(y_ld >= L && (tab == nullptr || tab_ld >= L), "dstag_layernorm_fwd: leading dimension < L");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_fwd: bad sizes rows=%d L=%d", rows, L);
   DSTAG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dstag_layernorm_fwd: bad dropout p");
-  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {   // measured slower than block-per-row
+  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && y_ld == L && tab_ld == L &&
+      L <= 32 * kWR) {   // measured slower than block-per-row
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
     ln_fwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L,
@@ -428,20 +432,23 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
   if (rc) return rc;
   const int grid = rows < kNumSMs * 8 ? rows : kNumSMs * 8;
   ln_fwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
-      a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L, drop_p, seed);
+      a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, beta, eps, y, y_ld, mean, rstd, rows, L, drop_p, seed);
   DSTAG_RETURN_LAUNCH("dstag_layernorm_fwd");
 }
 
-int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
-                        int64_t a_sc, const float* tab, int32_t tab_mod, const float* gamma,
-                        const float* mean, const float* rstd, float* dpre, float* dgamma,
+int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
+                        int64_t a_sc, const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma,
+                        const float* mean, const float* rstd, float* dpre, int64_t dpre_ld, float* dgamma,
                         float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
                         void* stream) {
+  DSTAG_CHECK_ARG(dy_ld >= L && dpre_ld >= L && (tab == nullptr || tab_ld >= L),
+                  "dstag_layernorm_bwd: leading dimension < L");
   DSTAG_CHECK_ARG(dy && a && gamma && mean && rstd && dpre && dgamma && dbeta,
                   "dstag_layernorm_bwd: null pointer");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_bwd: bad sizes rows=%d L=%d", rows, L);
-  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && L <= 32 * kWR) {   // measured slower than block-per-row
+  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && dy_ld == L && dpre_ld == L && tab_ld == L &&
+      L <= 32 * kWR) {   // measured slower than block-per-row
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 2 ? blocks : kNumSMs * 2;
     ln_bwd_warp_kernel<<<grid, 256, (size_t)2 * L * sizeof(float), (cudaStream_t)stream>>>(
@@ -453,8 +460,8 @@ int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a
   if (rc) return rc;
   const int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
   ln_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
-      dy, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, mean, rstd, dpre, dgamma, dbeta, rows, L,
-      drop_p, seed);
+      dy, dy_ld, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta,
+      rows, L, drop_p, seed);
   DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd");
 }
 
@@ -488,11 +495,13 @@ int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_
   DSTAG_RETURN_LAUNCH("dstag_colsum");
 }
 
-int dstag_transpose(const float* in, float* out, int32_t batch, int32_t R, int32_t C, void* stream) {
-  DSTAG_CHECK_ARG(in && out && batch > 0 && R > 0 && C > 0, "dstag_transpose: bad arguments");
+int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, int32_t batch, int32_t R, int32_t C,
+                    void* stream) {
+  DSTAG_CHECK_ARG(in && out && batch > 0 && R > 0 && C > 0 && in_ld >= C && out_ld >= R,
+                  "dstag_transpose: bad arguments");
   DSTAG_CHECK_ARG(batch <= 65535 && (R + 31) / 32 <= 65535, "dstag_transpose: grid too large");
   const dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
-  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, R, C);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, R, C);
   DSTAG_RETURN_LAUNCH("dstag_transpose");
 }
 

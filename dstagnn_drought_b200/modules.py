@@ -28,7 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F_
 
 from . import ops
-from .contraction import contract
+from .contraction import contract, padded_ld
 from .graph import cheb_polynomial, scaled_Laplacian
 
 
@@ -60,9 +60,13 @@ class MultiHeadAttention(nn.Module):
         """e2d: (B*F*T, N) rows (b,f,t).  Returns (LN(fc(ctx) + e), logits (B,F,H,T,T))."""
         H, dk = self.n_heads, self.d_k
         w_qkv = torch.cat([self.W_Q.weight, self.W_K.weight, self.W_V.weight], dim=0)     # (3*H*dk, N)
+        N = w_qkv.shape[1]
+        if padded_ld(N) != N:
+            # rows over the node axis are kept 16-byte aligned (vector / TMA operand loads for odd N)
+            w_qkv = F_.pad(w_qkv, (0, padded_ld(N) - N))[:, :N]
         qkv = contract("rn,on->ro", e2d, w_qkv)                                           # (B,F,T,3,H,dk)
         ctx, logits = ops.TemporalAttention.apply(qkv, res_att, B, Fe, H, T, dk)
-        fc = contract("rk,nk->rn", ctx.view(B * Fe * T, H * dk), self.fc.weight)
+        fc = contract("rk,nk->rn", ctx.view(B * Fe * T, H * dk), self.fc.weight, pad_rows=True)
         out = ops.LayerNormAdd.apply(fc, e2d, self.layer_norm.weight, self.layer_norm.bias, False, 0.0, 0)
         return out, logits
 

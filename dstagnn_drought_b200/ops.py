@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import ACC_ADD, ACC_ATOMIC, ACC_STORE
-from .contraction import _check, colsum, contract_raw
+from .contraction import _check, colsum, contract_raw, dense_rows, empty_rows
 
 _VP = C.c_void_p
 
@@ -45,14 +45,18 @@ def next_seed() -> int:
 # ----------------------------------------------------------------------------------------
 # transpose
 # ----------------------------------------------------------------------------------------
-def transpose_raw(x3: torch.Tensor) -> torch.Tensor:
-    """(b, R, C) contiguous -> (b, C, R) contiguous."""
+def transpose_raw(x3: torch.Tensor, pad_rows: bool = False) -> torch.Tensor:
+    """(b, R, C) -> (b, C, R).  The input may be row padded; with ``pad_rows`` the output rows are
+    padded to 16 bytes (a ``[..., :R]`` view)."""
     lib = _lib.load()
     _check(x3, "transpose input")
-    assert x3.is_contiguous() and x3.dim() == 3
+    assert x3.dim() == 3
+    x3 = dense_rows(x3)
     b, R, Cc = x3.shape
-    out = torch.empty((b, Cc, R), device=x3.device, dtype=torch.float32)
-    _lib.check(lib.dstag_transpose(x3.data_ptr(), out.data_ptr(), b, R, Cc, _stream(x3)), "dstag_transpose")
+    out = empty_rows((b, Cc, R), x3.device) if pad_rows else torch.empty((b, Cc, R), device=x3.device,
+                                                                         dtype=torch.float32)
+    _lib.check(lib.dstag_transpose(x3.data_ptr(), x3.stride(1), out.data_ptr(), out.stride(1), b, R, Cc,
+                                   _stream(x3)), "dstag_transpose")
     return out
 
 
@@ -61,11 +65,11 @@ class Transpose(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x3):
-        return transpose_raw(x3)
+        return transpose_raw(x3, pad_rows=True)
 
     @staticmethod
     def backward(ctx, dy):
-        return transpose_raw(dy.contiguous())
+        return transpose_raw(dy)
 
 
 # ----------------------------------------------------------------------------------------
@@ -86,24 +90,26 @@ class LayerNormAdd(torch.autograd.Function):
         lib = _lib.load()
         for t, n in ((a, "a"), (tab, "tab"), (gamma, "gamma"), (beta, "beta")):
             _check(t, n)
-        a = a.contiguous()
-        tab = tab.contiguous()
         if gather:
+            a = a.contiguous()
             Bz, N, FT = a.shape
             rows, L = Bz * FT, N
             lay = (N * FT, 1, FT, FT)            # a_s0, a_s1, a_div, a_sc
         else:
+            a = dense_rows(a)
             rows, L = a.shape
-            lay = (L, 0, 1, 1)
-        tab_mod = tab.numel() // L
-        assert tab.numel() == tab_mod * L and rows % tab_mod == 0 and gamma.numel() == L
-        y = torch.empty((rows, L), device=a.device, dtype=torch.float32)
+            lay = (a.stride(0), 0, 1, 1)
+        ctx.tab_shape = tab.shape
+        tab = dense_rows(tab.reshape(-1, L) if tab.dim() != 2 else tab)
+        tab_mod = tab.shape[0]
+        assert rows % tab_mod == 0 and gamma.numel() == L
+        y = empty_rows((rows, L), a.device)      # rows padded to 16 B: consumers take the vector load paths
         mean = torch.empty(rows, device=a.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=a.device, dtype=torch.float32)
         _lib.check(lib.dstag_layernorm_fwd(a.data_ptr(), lay[0], lay[1], lay[2], lay[3], tab.data_ptr(),
-                                           tab_mod, gamma.data_ptr(), beta.data_ptr(), 1e-5, y.data_ptr(),
-                                           mean.data_ptr(), rstd.data_ptr(), rows, L, float(drop_p),
-                                           int(seed), _stream(a)), "dstag_layernorm_fwd")
+                                           tab_mod, tab.stride(0), gamma.data_ptr(), beta.data_ptr(), 1e-5,
+                                           y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(), rows, L,
+                                           float(drop_p), int(seed), _stream(a)), "dstag_layernorm_fwd")
         ctx.save_for_backward(a, tab, gamma, mean, rstd)
         ctx.meta = (lay, tab_mod, rows, L, gather, float(drop_p), int(seed))
         return y
@@ -113,15 +119,18 @@ class LayerNormAdd(torch.autograd.Function):
         lib = _lib.load()
         a, tab, gamma, mean, rstd = ctx.saved_tensors
         lay, tab_mod, rows, L, gather, drop_p, seed = ctx.meta
-        dy = dy.contiguous()
-        dpre = torch.empty((rows, L), device=a.device, dtype=torch.float32)
+        dy = dense_rows(dy)
+        # a table gradient is a column sum over row groups: keep those rows dense
+        dense = ctx.needs_input_grad[1] and tab_mod != rows
+        dpre = torch.empty((rows, L), device=a.device, dtype=torch.float32) if dense else empty_rows((rows, L),
+                                                                                                     a.device)
         dgamma = torch.zeros(L, device=a.device, dtype=torch.float32)
         dbeta = torch.zeros(L, device=a.device, dtype=torch.float32)
-        _lib.check(lib.dstag_layernorm_bwd(dy.data_ptr(), a.data_ptr(), lay[0], lay[1], lay[2], lay[3],
-                                           tab.data_ptr(), tab_mod, gamma.data_ptr(), mean.data_ptr(),
-                                           rstd.data_ptr(), dpre.data_ptr(), dgamma.data_ptr(),
-                                           dbeta.data_ptr(), rows, L, drop_p, seed, _stream(a)),
-                   "dstag_layernorm_bwd")
+        _lib.check(lib.dstag_layernorm_bwd(dy.data_ptr(), dy.stride(0), a.data_ptr(), lay[0], lay[1], lay[2],
+                                           lay[3], tab.data_ptr(), tab_mod, tab.stride(0), gamma.data_ptr(),
+                                           mean.data_ptr(), rstd.data_ptr(), dpre.data_ptr(), dpre.stride(0),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), rows, L, drop_p, seed,
+                                           _stream(a)), "dstag_layernorm_bwd")
         da = dtab = None
         if ctx.needs_input_grad[0]:
             if gather:
@@ -131,9 +140,9 @@ class LayerNormAdd(torch.autograd.Function):
                 da = dpre
         if ctx.needs_input_grad[1]:
             if tab_mod == rows:
-                dtab = dpre.view(tab.shape)
+                dtab = dpre.view(ctx.tab_shape)
             else:
-                dtab = colsum(dpre, rows // tab_mod, tab_mod * L).view(tab.shape)
+                dtab = colsum(dpre, rows // tab_mod, tab_mod * L).view(ctx.tab_shape)
         return da, dtab, dgamma, dbeta, None, None, None
 
 

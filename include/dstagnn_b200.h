@@ -93,17 +93,19 @@ int dstag_gemm_uses_tensor_cores(const dstag_gemm_t* g);
  * Replaces Embedding.forward (model/DSTAGNN_my.py:172-182: pos_embed + LayerNorm, both
  * 'T' and 'S' types, tab = the embedding table), the residual LayerNorm of
  * MultiHeadAttention (line 100: tab = residual, tab_mod = rows) and the dropout of
- * line 234.  mean/rstd (rows each) are saved for the backward.
+ * line 234.  mean/rstd (rows each) are saved for the backward.  tab rows and y rows have leading
+ * dimensions tab_ld / y_ld >= L (rows over the node axis are padded to 16-byte multiples so the
+ * contractions that consume them take the vector / TMA load paths).
  * ---------------------------------------------------------------------------------- */
 int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
-                        const float* tab, int32_t tab_mod, const float* gamma, const float* beta,
-                        float eps, float* y, float* mean, float* rstd, int32_t rows, int32_t L,
+                        const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma, const float* beta,
+                        float eps, float* y, int64_t y_ld, float* mean, float* rstd, int32_t rows, int32_t L,
                         float drop_p, uint64_t seed, void* stream);
 /* dpre[r,:] = d(loss)/d(a + tab) (contiguous rows x L); dgamma/dbeta are ACCUMULATED
  * (atomicAdd) into caller-zeroed buffers. */
-int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
-                        int64_t a_sc, const float* tab, int32_t tab_mod, const float* gamma,
-                        const float* mean, const float* rstd, float* dpre, float* dgamma,
+int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
+                        int64_t a_sc, const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma,
+                        const float* mean, const float* rstd, float* dpre, int64_t dpre_ld, float* dgamma,
                         float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
                         void* stream);
 
@@ -112,9 +114,10 @@ int dstag_layernorm_bwd(const float* dy, const float* a, int64_t a_s0, int64_t a
  * zeroed by the caller (partial sums are combined with atomicAdd). */
 int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);
 
-/* out[b, c, r] = in[b, r, c]  (x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 made contiguous,
- * and the transposes of the N x N mask / Chebyshev matrices). */
-int dstag_transpose(const float* in, float* out, int32_t batch, int32_t R, int32_t C, void* stream);
+/* out[(b * C + c) * out_ld + r] = in[(b * R + r) * in_ld + c]  (x.permute(0,2,3,1) of
+ * model/DSTAGNN_my.py:230 made contiguous, and the transposes of the N x N mask / Chebyshev matrices). */
+int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, int32_t batch, int32_t R, int32_t C,
+                    void* stream);
 
 /* In-place row softmax over L entries of rows with leading dimension ld; entries
  * [L, ld) are set to 0.  F.softmax(..., dim=1) of model/DSTAGNN_my.py:127 on the

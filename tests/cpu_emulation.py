@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 3
+        return 4
 
     def dstag_last_error(self):
         return self.err
@@ -85,38 +85,39 @@ class FakeLib:
 
     # ---- row kernels ----
     @staticmethod
-    def _ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L):
+    def _ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, rows, L):
         r = np.arange(rows, dtype=np.int64)
         off = ((r // a_div) * a_s0 + (r % a_div) * a_s1)[:, None] + (np.arange(L, dtype=np.int64) * a_sc)[None, :]
         pre = _arr(a, off.max() + 1)[off].astype(np.float64)
         if tab:
-            pre = pre + _arr(tab, tab_mod * L).reshape(tab_mod, L)[r % tab_mod]
+            pre = pre + _arr(tab, tab_mod * tab_ld).reshape(tab_mod, tab_ld)[r % tab_mod, :L]
         return pre
 
-    def dstag_layernorm_fwd(self, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, beta, eps, y, mean, rstd,
-                            rows, L, drop_p, seed, stream):
+    def dstag_layernorm_fwd(self, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, beta, eps, y, y_ld,
+                            mean, rstd, rows, L, drop_p, seed, stream):
         assert drop_p == 0.0, "emulation has no dropout"
         self.launches += 1
-        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L)
+        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, rows, L)
         mu = pre.mean(1)
         rs = 1.0 / np.sqrt(pre.var(1) + eps)
-        _arr(y, rows * L).reshape(rows, L)[:] = (pre - mu[:, None]) * rs[:, None] * _arr(gamma, L) + _arr(beta, L)
+        _arr(y, rows * y_ld).reshape(rows, y_ld)[:, :L] = ((pre - mu[:, None]) * rs[:, None] * _arr(gamma, L)
+                                                          + _arr(beta, L))
         _arr(mean, rows)[:] = mu
         _arr(rstd, rows)[:] = rs
         return 0
 
-    def dstag_layernorm_bwd(self, dy, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, gamma, mean, rstd, dpre, dgamma,
-                            dbeta, rows, L, drop_p, seed, stream):
+    def dstag_layernorm_bwd(self, dy, dy_ld, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, mean, rstd,
+                            dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed, stream):
         assert drop_p == 0.0
         self.launches += 1
-        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, rows, L)
+        pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, rows, L)
         mu = _arr(mean, rows).astype(np.float64)[:, None]
         rs = _arr(rstd, rows).astype(np.float64)[:, None]
         xh = (pre - mu) * rs
-        d = _arr(dy, rows * L).reshape(rows, L).astype(np.float64)
+        d = _arr(dy, rows * dy_ld).reshape(rows, dy_ld)[:, :L].astype(np.float64)
         g = d * _arr(gamma, L)
-        _arr(dpre, rows * L).reshape(rows, L)[:] = rs * (g - g.mean(1, keepdims=True)
-                                                        - xh * (g * xh).mean(1, keepdims=True))
+        _arr(dpre, rows * dpre_ld).reshape(rows, dpre_ld)[:, :L] = rs * (g - g.mean(1, keepdims=True)
+                                                                        - xh * (g * xh).mean(1, keepdims=True))
         _arr(dgamma, L)[:] += (d * xh).sum(0)
         _arr(dbeta, L)[:] += d.sum(0)
         return 0
@@ -130,9 +131,10 @@ class FakeLib:
         _arr(out, cols)[:] += acc
         return 0
 
-    def dstag_transpose(self, inp, out, batch, R, Cc, stream):
+    def dstag_transpose(self, inp, in_ld, out, out_ld, batch, R, Cc, stream):
         self.launches += 1
-        _arr(out, batch * R * Cc).reshape(batch, Cc, R)[:] = _arr(inp, batch * R * Cc).reshape(batch, R, Cc).transpose(0, 2, 1)
+        src = _arr(inp, batch * R * in_ld).reshape(batch, R, in_ld)[:, :, :Cc]
+        _arr(out, batch * Cc * out_ld).reshape(batch, Cc, out_ld)[:, :, :R] = src.transpose(0, 2, 1)
         return 0
 
     def dstag_softmax_fwd(self, x, rows, L, ld, stream):

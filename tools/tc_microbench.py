@@ -26,15 +26,16 @@ def main():
     FT, X = F * T, B * N
     prec = ct._PRECISION[a.precision]
     r = lambda *s: torch.randn(*s, device=dev)  # noqa: E731
+    rp = lambda *s: ct.empty_rows(s, dev).normal_()  # noqa: E731   (row-padded like the model's node-axis tensors)
     P = torch.zeros(B, K, N, ld, device=dev); P[..., :N] = torch.softmax(r(B, K, N, N), -1)
     Tk = torch.zeros(K, N, ld, device=dev); Tk[..., :N] = r(K, N, N)
     x3, Z, dS = r(B, N, FT), r(K, B, N, FT), torch.zeros(B, K, N, ld, device=dev)
     qk = r(B, N, 2, K, dk)
-    E, Wqkv = r(B * FT, N), r(3 * H * dk, N)
-    O, Wpre, Zs = r(B, F, T, N), r(D, T, 1, F), r(B, N, D)
-    g3 = r(X, C, T); w5 = r(2 * C, C, 5); u5 = r(X, 2 * C, T - 4)
-    cat, Wf = r(X * C, 3 * T - 12), r(T, 3 * T - 12)
+    E, Wqkv = rp(B * FT, N), rp(3 * H * dk, N)
+    O, Wpre, Zs = rp(B, F, T, N), r(D, T, 1, F), r(B, N, D)
+    g = r(X, T, C)                                     # channels-last graph-conv output
     theta = r(K, F, C)
+    cat, dtc = r(X * C, 3 * T - 12), r(X * C, T)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     cases = [
         ("cheb_fwd", "bkji,bie->kbje", P[..., :N], x3, dict(a_mul=("kji", Tk[..., :N]))),
@@ -44,24 +45,31 @@ def main():
         ("sat_dq", "bkji,bjkd->bikd", dS[..., :N], qk[:, :, 1], {}),
         ("sat_dk", "bkji,bikd->bjkd", dS[..., :N], qk[:, :, 0], {}),
         ("qkv", "rn,on->ro", E, Wqkv, {}),
-        ("qkv_dx", "ro,on->rn", r(B * FT, 3 * H * dk), Wqkv, {}),
-        ("qkv_dw", "rn,ro->on", E, r(B * FT, 3 * H * dk), {}),
+        ("qkv_dx", "ro,on->rn", r(B * FT, 3 * H * dk), Wqkv, dict(out=rp(B * FT, N))),
+        ("qkv_dw", "ro,rn->on", r(B * FT, 3 * H * dk), E, dict(out=rp(3 * H * dk, N))),
         ("pre_conv", "bftn,dtf->bnd", O, Wpre[:, :, 0, :], {}),
-        ("pre_conv_dx", "bnd,dtf->bftn", Zs, Wpre[:, :, 0, :], {}),
+        ("pre_conv_dx", "bnd,dtf->bftn", Zs, Wpre[:, :, 0, :], dict(out=rp(B, F, T, N))),
         ("pre_conv_dw", "bftn,bnd->dtf", O, Zs, {}),
-        ("theta_mix", "kxft,kfc->xct", Z.view(K, X, F, T), theta, dict(relu=True)),
-        ("theta_dz", "xct,kfc->kxft", g3, theta, {}),
-        ("theta_dth", "kxft,xct->kfc", Z.view(K, X, F, T), g3, {}),
-        ("gtu5_fwd", "xctd,ocd->xot", g3.unfold(2, 5, 1), w5, {}),
-        ("gtu5_dw", "xot,xctd->ocd", u5, g3.unfold(2, 5, 1), {}),
-        ("gtu5_dx", "xot,ocd->xctd", u5, w5, dict(out=torch.zeros_like(g3).unfold(2, 5, 1), accumulate=ACC_ATOMIC, split_k=1)),
-        ("fcmy", "rs,ts->rt", cat, Wf, {}),
-        ("fcmy_dx", "rt,ts->rs", r(X * C, T), Wf, {}),
-        ("fcmy_dw", "rs,rt->ts", cat, r(X * C, T), {}),
+        ("sat_proj", "rd,od->ro", r(X, D), r(2 * K * dk, D), {}),
+        ("theta_mix", "kxft,kfc->xtc", Z.view(K, X, F, T), theta, dict(relu=True)),
+        ("theta_dz", "xtc,kfc->kxft", g, theta, {}),
+        ("theta_dth", "kxft,xtc->kfc", Z.view(K, X, F, T), g, {}),
+        ("fcmy_dw", "rt,rs->ts", dtc, cat, {}),
     ]
+    for ks in (3, 5, 7):
+        tp, pad = T - ks + 1, ks - 1
+        tpad = tp + 2 * pad
+        gv = g.as_strided((X, tp, ks * C), (T * C, C, 1))
+        dup = r(X, tpad, 2 * C)
+        dview = dup.as_strided((X, T, ks * 2 * C), (tpad * 2 * C, 2 * C, 1))
+        cases += [
+            (f"gtu{ks}_fwd", "xtk,ok->xto", gv, r(2 * C, ks * C), {}),
+            (f"gtu{ks}_dw", "xto,xtk->ok", dup[:, pad:pad + tp, :], gv, {}),
+            (f"gtu{ks}_dx", "xtk,ck->xtc", dview, r(C, ks * 2 * C), dict(split_k=1)),
+        ]
     print(f"{'case':14s} {'engine':6s} {'ms':>9s} {'TFLOP/s':>9s}   (precision {a.precision}, batch {B})")
     for name, spec, A, Bm, kw in cases:
-        if a.only and a.only not in name:
+        if a.only and not any(o == name or (o.endswith("*") and name.startswith(o[:-1])) for o in a.only.split(",")):
             continue
         kw = dict(kw)
         out = kw.get("out")
@@ -73,6 +81,7 @@ def main():
                                  precision=prec)
         tc = bool(_lib.load().dstag_gemm_uses_tensor_cores(ctypes.byref(gd)))
         flops = 2.0 * gd.M * gd.N * gd.K * gd.batch
+        kw.setdefault("split_k", None)
         ts = []
         for _ in range(a.reps):
             flush.zero_()
