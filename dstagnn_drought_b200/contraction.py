@@ -123,6 +123,20 @@ def _check(t: torch.Tensor, name: str):
         raise RuntimeError(f"dstagnn_drought_b200: {name} must be float32, got {t.dtype}")
 
 
+def _k_order(pl: Plan, A, B):
+    """Enumeration order of a two-letter reduction index.  Any order is correct; prefer the one whose
+    inner letter is memory-contiguous in more operands (K-contiguous tiles load by vector / TMA)."""
+    if len(pl.k) != 2:
+        return pl.k
+
+    def score(order):
+        lo = order[1]
+        return sum(1 for sub, t in ((pl.a, A), (pl.b, B)) if t.stride(sub.index(lo)) == 1)
+
+    fwd, rev = pl.k, [pl.k[1], pl.k[0]]
+    return rev if score(rev) > score(fwd) else fwd
+
+
 def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, alpha=1.0,
                      relu=False, accumulate=ACC_STORE, split_k=1, precision=None) -> Gemm:
     """Pure host logic (no CUDA call): used directly by the CPU tests."""
@@ -140,10 +154,11 @@ def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, a
     g = Gemm()
     g.M, g.N, g.K, g.batch = (_prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size),
                               _prod(pl.batch, size))
-    g.A = _operand(A, pl.a, pl.batch, pl.m, pl.k, size)
-    g.B = _operand(B, pl.b, pl.batch, pl.k, pl.n, size)
+    kl = _k_order(pl, A, B)
+    g.A = _operand(A, pl.a, pl.batch, pl.m, kl, size)
+    g.B = _operand(B, pl.b, pl.batch, kl, pl.n, size)
     g.C = _operand(out, pl.c, pl.batch, pl.m, pl.n, size)
-    g.Amul = _operand(a_mul[1], a_mul[0], pl.batch, pl.m, pl.k, size) if a_mul else _operand(None, "", [], [], [], size)
+    g.Amul = _operand(a_mul[1], a_mul[0], pl.batch, pl.m, kl, size) if a_mul else _operand(None, "", [], [], [], size)
     g.Cmul = _operand(c_mul[1], c_mul[0], pl.batch, pl.m, pl.n, size) if c_mul else _operand(None, "", [], [], [], size)
     g.Cadd = _operand(c_add[1], c_add[0], pl.batch, pl.m, pl.n, size) if c_add else _operand(None, "", [], [], [], size)
     g.alpha, g.relu, g.accumulate, g.split_k = float(alpha), int(bool(relu)), int(accumulate), int(split_k)

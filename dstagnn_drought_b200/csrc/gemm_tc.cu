@@ -1146,6 +1146,40 @@ static bool make_tmap(CUtensorMap* map, int* bdim, const dstag_operand_t& o, con
   return r == CUDA_SUCCESS;
 }
 
+// A row axis (b, n) whose inner level is contiguous (an activation stored (..., N) with the batch index
+// further out) defeats the row-contiguous vector path, because 4-row groups would straddle the level
+// boundary.  Such a problem is the same as a batched one over the outer level: M' = d1 rows per batch,
+// batch' = batch * M / d1.  Rewrites the descriptor in place; false = left untouched.
+static bool split_rows_to_batch(dstag_gemm_t& g) {
+  const int d1 = g.A.row.d1;
+  if (d1 < 128 || g.A.row.s1 != 1 || g.M % d1 != 0 || g.M == d1) return false;
+  const int q = g.M / d1;
+  dstag_operand_t* rowops[] = {&g.A, &g.Amul, &g.C, &g.Cadd, &g.Cmul};
+  for (dstag_operand_t* o : rowops) {
+    if (!o->ptr) continue;
+    if (o->row.d1 != d1 && o->row.d1 != 1) return false;
+    if (g.batch > 1 && o->batch.d1 != 1) return false;
+  }
+  if (g.batch > 1 && g.B.batch.d1 != 1) return false;
+  for (dstag_operand_t* o : rowops) {
+    if (!o->ptr) continue;
+    const long long outer = o->row.d1 == d1 ? o->row.s0 : o->row.s0 * d1;
+    const long long inner = o->row.d1 == d1 ? o->row.s1 : o->row.s0;
+    o->batch.s0 = g.batch > 1 ? o->batch.s0 : 0;
+    o->batch.s1 = outer;
+    o->batch.d1 = q;
+    o->row.s0 = inner;
+    o->row.s1 = 0;
+    o->row.d1 = 1;
+  }
+  g.B.batch.s0 = g.batch > 1 ? g.B.batch.s0 : 0;
+  g.B.batch.s1 = 0;
+  g.B.batch.d1 = q;
+  g.batch *= q;
+  g.M = d1;
+  return true;
+}
+
 static int g_num_sms = 0;
 
 template <int BN, bool X3, bool AMUL>
@@ -1165,7 +1199,7 @@ static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream)
   DSTAG_RETURN_LAUNCH("dstag_gemm(tcgen05)");
 }
 
-int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
+int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1173,7 +1207,9 @@ int gemm_tc(const dstag_gemm_t* g, cudaStream_t stream) {
     if (g_num_sms <= 0) g_num_sms = kNumSMs;
   }
   TcParams p;
-  p.g = *g;
+  p.g = *g_in;
+  split_rows_to_batch(p.g);
+  const dstag_gemm_t* g = &p.g;
   const int bn = g->N > 64 ? 128 : (g->N > 32 ? 64 : 32);
   p.ntm = (g->M + TC_BM - 1) / TC_BM;
   p.ntn = (g->N + bn - 1) / bn;

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional
 
 import torch
@@ -233,7 +234,8 @@ class SpatialChebConv(torch.autograd.Function):
         Qs, Ks = qk[:, :, 0], qk[:, :, 1]                      # (B,N,K,dk) views
         P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
         biasT = biasT.contiguous()
-        rc = lib.dstag_sat_softmax_fwd(qk.data_ptr(), biasT.data_ptr(), P.data_ptr(), B, N, K, dk, ld, _stream(P))
+        rc = -3 if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
+            qk.data_ptr(), biasT.data_ptr(), P.data_ptr(), B, N, K, dk, ld, _stream(P))
         if rc == -3:      # DSTAG_ERR_SMEM: N too large for the fused row strip -> GEMM + row softmax
             contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
                          c_add=("kji", biasT[..., :N]))

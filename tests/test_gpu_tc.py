@@ -138,3 +138,28 @@ def test_tc_many_tiles_persistent_loop():
     B = torch.randn(6, 520, 200, device=dev)
     out = _run("bmk,bnk->bmn", A, B, "tf32x3")
     assert rel_err(out, torch.einsum("bmk,bnk->bmn", A.double(), B.double())) < TOL["tf32x3"]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("N", [130, 256, 883])
+def test_tc_two_level_rows_split_to_batch(N, precision):
+    """pre_conv's shape: A (b,f,t,n) has rows (b,n) with n contiguous (row padded to 16 bytes) -- the
+    engine reruns it as a batched problem over b so the row-contiguous vector path applies; with a
+    bias epilogue and an odd N."""
+    from dstagnn_drought_b200 import contraction as ct
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    Bz, F, T, D = 3, 4, 12, 72
+    A = ct.empty_rows((Bz, F, T, N), dev).normal_()
+    W = torch.randn(D, T, F, device=dev)
+    bias = torch.randn(D, device=dev)
+    out = _run("bftn,dtf->bnd", A, W, precision, c_add=("d", bias))
+    ref = torch.einsum("bftn,dtf->bnd", A.double(), W.double()) + bias.double()
+    assert rel_err(out, ref) < TOL[precision]
+    # and its weight gradient (K = (b,n) two-level) / input gradient (output rows padded)
+    dZ = torch.randn(Bz, N, D, device=dev)
+    dW = _run("bnd,bftn->dtf", dZ, A, precision)
+    assert rel_err(dW, torch.einsum("bnd,bftn->dtf", dZ.double(), A.double())) < TOL[precision]
+    dA = ct.empty_rows((Bz, F, T, N), dev)
+    _run("dtf,bnd->bftn", W, dZ, precision, out=dA)
+    assert rel_err(dA, torch.einsum("dtf,bnd->bftn", W.double(), dZ.double())) < TOL[precision]

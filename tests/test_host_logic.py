@@ -104,7 +104,8 @@ def test_descriptor_plain_and_permuted_views():
     ref = torch.einsum("bftn,dtf->bnd", O, W[:, :, 0, :]) + bias
     assert torch.allclose(out, ref, atol=1e-5)
     assert (g.M, g.N, g.K, g.batch) == (B_ * N_, D_, F_ * T_, 1)
-    assert g.A.col.d1 == 1 and g.B.row.d1 == T_          # (f,t) merges in O, not in the conv weight
+    # the reduction index is enumerated (t,f): contiguous in the conv weight, two-level in O
+    assert (g.B.row.s0, g.B.row.d1) == (1, 1) and (g.A.col.d1, g.A.col.s0, g.A.col.s1) == (F_, N_, T_ * N_)
 
 
 def test_descriptor_batch_pair_amul_and_padded_output():
