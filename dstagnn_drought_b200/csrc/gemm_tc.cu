@@ -45,7 +45,6 @@ struct TcParams {
   int ntm, ntn, kblocks, kb_per_split, nsplit, total_items;
   int a_mode, b_mode;      // MODE_* (see Producer)
   int a_tma, b_tma;        // operand tile arrives by TMA (cp.async.bulk.tensor) instead of LDG
-  int a_async, b_async;    // operand chunks arrive by cp.async (vector modes without a tensor map)
   int a_bdim[2], b_bdim[2];  // which of the two batch levels are real tensor-map dimensions
 };
 
@@ -224,54 +223,39 @@ struct Walk {
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
-// Round-to-nearest TF32 (the tensor core itself truncates the low 13 mantissa bits): adding half a
-// TF32 ulp before masking halves the residual, so the lo term carries one more useful bit and its
-// own truncation error drops to ~2^-23 relative.
-__device__ __forceinline__ float tf32_hi(float v) {
-  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+// 3xTF32 split.  The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
+// value IS the hi term (hi = trunc(v)); the lo term is the exact residual v - trunc(v) (13 significant
+// bits, of which the tensor core keeps 11: relative error of hi + lo below 2^-21).  Two ALU operations
+// per element -- the producers are instruction-issue bound, so the split must stay this cheap.
+__device__ __forceinline__ float tf32_lo(float v) {
+  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
 }
-
-template <bool X3>
-__device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float4 v) {
-  if (X3) {
-    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    *reinterpret_cast<float4*>(plane_hi + off) = h;
-    *reinterpret_cast<float4*>(plane_lo + off) =
-        make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
-  } else {
-    *reinterpret_cast<float4*>(plane_hi + off) = v;
-  }
-}
-template <bool X3>
-__device__ __forceinline__ void store_scalar(uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, float v) {
-  if (X3) {
-    const float h = tf32_hi(v);
-    *reinterpret_cast<float*>(plane_hi + off) = h;
-    *reinterpret_cast<float*>(plane_lo + off) = tf32_hi(v - h);
-  } else {
-    *reinterpret_cast<float*>(plane_hi + off) = v;
-  }
+__device__ __forceinline__ float4 tf32_lo4(float4 v) {
+  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
 
 // ---------------------------------------------------------------------------------------
-// Operand producer.  NT threads fill one ROWS x 32 operand tile (hi [+ lo] plane) per k-block,
-// one k-block ahead in registers (the next block's global loads are in flight while the
-// current block is split / swizzled into shared memory).  Load modes, chosen per launch:
-//   KVEC  K contiguous, 16B aligned   : float4 along K   -> K-major tile,  thread = (chunk, rows)
-//   MVEC  rows contiguous, aligned    : float4 along M/N -> MN-major tile, thread = (row quad, k's)
-//   KSC   K contiguous, unaligned     : scalar, lanes along K (coalesced)  -> K-major tile
-//   ROWG  rows contiguous / anything  : scalar, lanes along rows           -> K-major tile
+// Operand producer.  NT threads copy one ROWS x 32 operand tile per k-block from global memory
+// straight into its final (swizzled) place in shared memory with cp.async, STAGES-1 k-blocks ahead;
+// no registers are held across the copy.  Load modes, chosen per launch:
+//   KVEC  K contiguous, 16B aligned   : 16-byte copies along K   -> K-major tile,  thread = (chunk, rows)
+//   MVEC  rows contiguous, aligned    : 16-byte copies along M/N -> MN-major tile, thread = (row quad, k's)
+//   KSC   K contiguous, unaligned     : 4-byte copies, lanes along K (coalesced)  -> K-major tile
+//   ROWG  rows contiguous / anything  : 4-byte copies, lanes along rows           -> K-major tile
+// Row offsets are computed once per output tile (begin_item) and kept in registers, so a k-block
+// costs a handful of instructions per copy.
 // ---------------------------------------------------------------------------------------
-template <int ROWS, int NT, bool X3, bool MUL>
+template <int ROWS, int NT, bool MUL>
 struct Producer {
-  static constexpr int NV = ROWS * 8 / NT;     // float4 (or 4 scalars) per thread per k-block
-  static constexpr int NM = MUL ? NV : 1;      // multiplier registers (unused without a Hadamard factor)
+  static constexpr int NV = ROWS * 8 / NT;     // 16-byte chunks per thread per k-block
+  static constexpr int NM = MUL ? NV : 1;
   static constexpr int RB = NT / 8;            // KVEC: rows per pass
   static constexpr int QPK = ROWS / 4;         // MVEC: row quads per k
   static constexpr int KPTM = TC_BK / (NT / QPK);   // MVEC: k's per thread (== NV)
   static constexpr int KPTR = TC_BK / (NT / ROWS);  // ROWG: scalars per thread (== 4 NV)
   static constexpr int NW = NT / 32;           // KSC : warps; rows per thread = ROWS / NW (== 4 NV)
   static_assert(KPTM == NV && KPTR == 4 * NV && ROWS / RB == NV && ROWS / NW == 4 * NV, "producer tiling mismatch");
+  static_assert(RB % 8 == 0, "KVEC swizzle phase must not depend on the pass");
 
   const float* base;
   const float* mbase;
@@ -281,6 +265,7 @@ struct Producer {
   const dstag_axis_t* mcolax;
   int K, t, mode, row0, limit;
   int r_off, r_lo, m_off, m_lo;   // row walk start (this thread's first row) for A and Amul
+  int ro[NV], mo[NM];             // KVEC: element offset of this thread's row in pass i (-1: out of range)
 
   __device__ __forceinline__ int first_row() const {
     if (mode == MODE_KVEC) return row0 + (t >> 3);
@@ -299,11 +284,25 @@ struct Producer {
     limit = lim;
     const int fr = first_row();
     Walk w;
-    w.init(*rowax, fr < lim ? fr : 0, 0);
+    w.init(*rowax, fr < lim ? fr : 0, mode == MODE_KVEC ? RB : 0);
     r_off = w.off; r_lo = w.lo;
+    if (mode == MODE_KVEC) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        ro[i] = (fr + RB * i < lim) ? w.off : -1;
+        w.next();
+      }
+    }
     if (MUL && mb) {
-      w.init(*mrowax, fr < lim ? fr : 0, 0);
+      w.init(*mrowax, fr < lim ? fr : 0, mode == MODE_KVEC ? RB : 0);
       m_off = w.off; m_lo = w.lo;
+      if (mode == MODE_KVEC) {
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+          mo[i] = (fr + RB * i < lim) ? w.off : -1;
+          w.next();
+        }
+      }
     }
   }
   __device__ __forceinline__ void row_walk(Walk& w, const dstag_axis_t& ax, int off, int lo) const {
@@ -312,129 +311,63 @@ struct Producer {
     w.lo = lo;
   }
 
-  // One operand stream (the tile itself, or its Hadamard factor): issue the global loads of
-  // k-block kb into v[].  Nothing here consumes a loaded value, so the loads stay in flight.
+  // Issue the asynchronous copies of k-block kb of one operand stream (the tile itself, or its
+  // Hadamard factor) into `plane`.
   template <int N>
-  __device__ __forceinline__ void load_stream(int kb, float4 (&v)[N], const float* bp, const dstag_axis_t& rax,
-                                              const dstag_axis_t& cax, int roff, int rlo) const {
-    static_assert(N == NV, "stream width");
-    const int k0 = kb * TC_BK;
-    const int fr = first_row();
-    if (mode == MODE_KVEC) {
-      const int k = k0 + 4 * (t & 7);
-      Walk rw;
-      row_walk(rw, rax, roff, rlo);
-      if (k + 3 < K) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (fr + RB * i < limit) v[i] = __ldg(reinterpret_cast<const float4*>(bp + rw.off + k));
-          rw.next();
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          float e[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) e[j] = (fr + RB * i < limit && k + j < K) ? __ldg(bp + rw.off + k + j) : 0.f;
-          v[i] = make_float4(e[0], e[1], e[2], e[3]);
-          rw.next();
-        }
-      }
-    } else if (mode == MODE_MVEC) {
-      const int kf = k0 + (t / QPK) * KPTM;
-      Walk w;
-      w.init(cax, kf, 1);
-      int nv = limit - fr;
-      nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kf + j < K) {
-          const float* ptr = bp + roff + w.off;
-          if (nv == 4) {
-            v[j] = __ldg(reinterpret_cast<const float4*>(ptr));
-          } else {
-            if (nv > 0) v[j].x = __ldg(ptr);
-            if (nv > 1) v[j].y = __ldg(ptr + 1);
-            if (nv > 2) v[j].z = __ldg(ptr + 2);
-          }
-        }
-        w.next();
-      }
-    } else if (mode == MODE_KSC) {
-      // lane <-> k (32 consecutive k: one coalesced line per row), thread walks 4*NV rows
-      const int k = k0 + (t & 31);
-      const bool kok = k < K;
-      const int ko = kok ? axoff32(cax, k) : 0;
-      Walk rw;
-      row_walk(rw, rax, roff, rlo);
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        float e[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          e[j] = (kok && fr + NW * (4 * c + j) < limit) ? __ldg(bp + rw.off + ko) : 0.f;
-          rw.next();
-        }
-        v[c] = make_float4(e[0], e[1], e[2], e[3]);
-      }
-    } else {
-      const int kf = k0 + (t / ROWS) * KPTR;
-      Walk w;
-      w.init(cax, kf, 1);
-      const bool rok = fr < limit;
-      const float* rp = bp + roff;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        float e[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          e[j] = (rok && kf + 4 * c + j < K) ? __ldg(rp + w.off) : 0.f;
-          w.next();
-        }
-        v[c] = make_float4(e[0], e[1], e[2], e[3]);
-      }
-    }
-  }
-
-  // Asynchronous variant of load_stream for the vector modes: the 16-byte chunks go straight from
-  // global memory to their final (swizzled) place in the shared-memory plane with cp.async, so any
-  // number of k-blocks can be in flight without holding registers.
   __device__ __forceinline__ void issue_stream(int kb, uint8_t* plane, const float* bp, const dstag_axis_t& rax,
-                                               const dstag_axis_t& cax, int roff, int rlo) const {
+                                               const dstag_axis_t& cax, int roff, int rlo, const int (&rows)[N]) const {
     const int k0 = kb * TC_BK;
-    const int fr = first_row();
     const uint32_t pbase = smem_u32(plane);
     if (mode == MODE_KVEC) {
-      const int c = t & 7, rb = t >> 3;
+      const int c = t & 7;
       const int k = k0 + 4 * c;
       int kbytes = 4 * (K - k);
       kbytes = kbytes < 0 ? 0 : (kbytes > 16 ? 16 : kbytes);
-      Walk rw;
-      row_walk(rw, rax, roff, rlo);
+      const uint32_t d0 = pbase + swz(t >> 3, c);
+      const float* kp = bp + k;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const uint32_t bytes = (fr + RB * i < limit) ? (uint32_t)kbytes : 0u;
-        cp_async16(pbase + swz(rb + RB * i, c), bytes ? (const void*)(bp + rw.off + k) : (const void*)bp, bytes);
-        rw.next();
+      for (int i = 0; i < N; ++i) {
+        const bool ok = rows[i] >= 0 && kbytes > 0;
+        cp_async16(d0 + i * (RB * 128), ok ? (const void*)(kp + rows[i]) : (const void*)bp, ok ? (uint32_t)kbytes : 0u);
       }
-    } else if (mode == MODE_MVEC) {
+      return;
+    }
+    const int fr = first_row();
+    if (mode == MODE_MVEC) {
       const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
       const int mb = mq >> 3, mc = mq & 7;
       const int kf = k0 + kl0;
-      Walk w;
-      w.init(cax, kf, 1);
       int nv = limit - fr;
       nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+      // byte offset of (k = kl0 + j, row quad mq) in the MN-major tile: 512-byte atoms of 32 rows x 4 k,
+      // atom (ka, mb) at (ka * ROWS/32 + mb) * 512, 128-byte k-rows inside, 32-byte swizzle on the quad.
+      // kl0 is a multiple of NV: for NV >= 4 the k part of the offset is a compile-time function of j.
+      const int kr0 = NV >= 4 ? 0 : (kl0 & 3);
+      const uint32_t d0 = pbase + (uint32_t)((((kl0 >> 2) * (ROWS / 32) + mb) << 9) + ((mc & 1) << 4));
+      auto koff = [&](int j) -> uint32_t {
+        const int kr = kr0 + (j & 3);      // NV == 2: kr0 in {0, 2}, j in {0, 1}: no carry into the atom index
+        return (uint32_t)((((j >> 2) * (ROWS / 32)) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5));
+      };
+      const float* rp = bp + roff;
+      if (cax.d1 == 1) {
+        const int ks = (int)cax.s0;
+        const float* kp = rp + kf * ks;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int kl = kl0 + j, ka = kl >> 2, kr = kl & 3;
-        const uint32_t off = (uint32_t)(((ka * (ROWS / 32) + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) +
-                                        ((mc & 1) << 4));
-        const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
-        cp_async16(pbase + off, bytes ? (const void*)(bp + roff + w.off) : (const void*)bp, bytes);
-        w.next();
+        for (int j = 0; j < NV; ++j) {
+          const uint32_t off = koff(j);
+          const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
+          cp_async16(d0 + off, bytes ? (const void*)(kp + j * ks) : (const void*)bp, bytes);
+        }
+      } else {
+        Walk w;
+        w.init(cax, kf, 1);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const uint32_t off = koff(j);
+          const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
+          cp_async16(d0 + off, bytes ? (const void*)(rp + w.off) : (const void*)bp, bytes);
+          w.next();
+        }
       }
     } else if (mode == MODE_KSC) {
       // unaligned K-contiguous rows: 4-byte copies, lane <-> k (one coalesced line per row)
@@ -472,67 +405,21 @@ struct Producer {
     }
   }
   __device__ __forceinline__ void issue(int kb, uint8_t* plane_hi, uint8_t* plane_lo) const {
-    issue_stream(kb, plane_hi, base, *rowax, *colax, r_off, r_lo);
+    issue_stream<NV>(kb, plane_hi, base, *rowax, *colax, r_off, r_lo, ro);
     if constexpr (MUL) {
-      if (mbase) issue_stream(kb, plane_lo, mbase, *mrowax, *mcolax, m_off, m_lo);   // factor parks in the lo plane
-    }
-  }
-
-  __device__ __forceinline__ void load(int kb, float4 (&v)[NV], float4 (&m)[NM]) const {
-    load_stream<NV>(kb, v, base, *rowax, *colax, r_off, r_lo);
-    if constexpr (MUL) {
-      if (mbase) load_stream<NV>(kb, m, mbase, *mrowax, *mcolax, m_off, m_lo);
-    }
-  }
-
-  // [x Hadamard factor], split and swizzle the staged registers into the shared-memory tile
-  __device__ __forceinline__ void store(float4 (&v)[NV], const float4 (&m)[NM], uint8_t* plane_hi,
-                                        uint8_t* plane_lo) const {
-    if constexpr (MUL) {
-      if (mbase) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = mul4(v[i], m[i]);
-      }
-    }
-    if (mode == MODE_KVEC) {
-      const int c = t & 7, rb = t >> 3;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) store_chunk<X3>(plane_hi, plane_lo, swz(rb + RB * i, c), v[i]);
-    } else if (mode == MODE_MVEC) {
-      const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
-      const int mb = mq >> 3, mc = mq & 7;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int kl = kl0 + j, ka = kl >> 2, kr = kl & 3;
-        const uint32_t off = (uint32_t)(((ka * (ROWS / 32) + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) +
-                                        ((mc & 1) << 4));
-        store_chunk<X3>(plane_hi, plane_lo, off, v[j]);
-      }
-    } else if (mode == MODE_KSC) {
-      const int kl = t & 31, w = t >> 5;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        const float e[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = w + NW * (4 * c + j);
-          store_scalar<X3>(plane_hi, plane_lo, swz(r, kl >> 2) + ((kl & 3) << 2), e[j]);
-        }
-      }
-    } else {
-      const int r = t % ROWS, c0 = (t / ROWS) * NV;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) store_chunk<X3>(plane_hi, plane_lo, swz(r, c0 + c), v[c]);
+      if (mbase) issue_stream<NM>(kb, plane_lo, mbase, *mrowax, *mcolax, m_off, m_lo, mo);   // factor parks in the lo plane
     }
   }
 };
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool AMUL>
 struct TcCfg {
   static constexpr int A_PLANE = TC_BM * 128;
   static constexpr int B_PLANE = BN * 128;
   static constexpr int PLANES = X3 ? 2 : 1;
-  static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
+  static constexpr int A_PLANES = (X3 || AMUL) ? 2 : 1;   // the Hadamard factor lands in a second A plane
+  static constexpr int B_OFF = A_PLANES * A_PLANE;        // B planes follow the A planes in a stage
+  static constexpr int STAGE = A_PLANES * A_PLANE + PLANES * B_PLANE;
   static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int BAR_OFF = STAGES * STAGE;
@@ -588,13 +475,7 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
 #pragma unroll
       for (int i = 0; i < ROWS * 8 / NT; ++i) {
         const uint32_t off = (uint32_t)(t + i * NT) * 16u;
-        const float4 v = *reinterpret_cast<const float4*>(hi + off);
-        float4 l;
-        l.x = tf32_hi(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-        l.y = tf32_hi(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-        l.z = tf32_hi(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-        l.w = tf32_hi(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-        *reinterpret_cast<float4*>(lo + off) = l;
+        *reinterpret_cast<float4*>(lo + off) = tf32_lo4(*reinterpret_cast<const float4*>(hi + off));
       }
       fence_proxy_async_smem();
     }
@@ -603,16 +484,15 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
   }
 }
 
-// Asynchronous producer for the vector load modes (K- or row-contiguous, 16B aligned): cp.async drops
-// the raw fp32 chunks directly into the stage's hi plane (the Hadamard factor, if any, into the lo plane)
-// STAGES-1 k-blocks ahead; when a block has landed the same warps finish it in place:
+// Operand fed by cp.async (any load mode; an optional Hadamard factor lands in the lo plane):
+// the copies run STAGES-1 k-blocks ahead; when a block has landed the same warps finish it in place:
 //   plain   : lo = v - trunc_tf32(v)               (the raw tile IS the hi operand)
-//   Hadamard: v = p * t ; hi = rn_tf32(v) ; lo = rn_tf32(v - hi)
+//   Hadamard: v = p * t ; hi = v ; lo = v - trunc_tf32(v)
 template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES, bool IS_A>
 __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, uint32_t plane_off,
                                               uint32_t plane_bytes, uint64_t* full_bar, uint64_t* empty_bar,
                                               uint64_t* raw_bar, int t, int lane) {
-  using P = Producer<ROWS, NT, X3, MUL>;
+  using P = Producer<ROWS, NT, MUL>;
   const dstag_gemm_t& g = p.g;
   P pr;
   pr.t = t;
@@ -666,32 +546,17 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
       for (int i = 0; i < ROWS * 8 / NT; ++i) {
         const uint32_t off = (uint32_t)(t + i * NT) * 16u;
         const float4 v = mul4(*reinterpret_cast<const float4*>(hi + off), *reinterpret_cast<const float4*>(lo + off));
-        if (X3) {
-          const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) =
-              make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
-        } else {
-          *reinterpret_cast<float4*>(hi + off) = v;
-        }
+        *reinterpret_cast<float4*>(hi + off) = v;
+        if (X3) *reinterpret_cast<float4*>(lo + off) = tf32_lo4(v);
       }
-      fence_proxy_async_smem();
     } else if (X3) {
 #pragma unroll
       for (int i = 0; i < ROWS * 8 / NT; ++i) {
         const uint32_t off = (uint32_t)(t + i * NT) * 16u;
-        const float4 v = *reinterpret_cast<const float4*>(hi + off);
-        float4 l;
-        l.x = tf32_hi(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-        l.y = tf32_hi(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-        l.z = tf32_hi(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-        l.w = tf32_hi(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-        *reinterpret_cast<float4*>(lo + off) = l;
+        *reinterpret_cast<float4*>(lo + off) = tf32_lo4(*reinterpret_cast<const float4*>(hi + off));
       }
-      fence_proxy_async_smem();
-    } else {
-      fence_proxy_async_smem();      // cp.async wrote through the generic proxy
     }
+    fence_proxy_async_smem();        // generic-proxy writes (cp.async, st.shared) -> visible to the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar + s);
     okx = px.next(p);
@@ -700,86 +565,10 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
   }
 }
 
-// Flat producer pipeline over the CTA's (item, k-block) sequence: iteration i issues the global loads
-// of position i + 1 -- which may already belong to the NEXT output tile -- and then stores position i,
-// so load latency is hidden across tile boundaries too (tiles with a single k-block, e.g. Q K^T with
-// d_k = 32, would otherwise expose one full DRAM round trip per tile).
-template <int ROWS, int NT, bool X3, bool MUL, int STAGES, int STAGE_BYTES, bool IS_A>
-__device__ __forceinline__ void produce_all(const TcParams& p, uint8_t* smem, uint32_t plane_off,
-                                            uint32_t plane_bytes, uint64_t* full_bar, uint64_t* empty_bar,
-                                            int t, int lane) {
-  using P = Producer<ROWS, NT, X3, MUL>;
-  const dstag_gemm_t& g = p.g;
-  P pr;
-  pr.t = t;
-  pr.K = g.K;
-  if (IS_A) {
-    pr.mode = p.a_mode;
-    pr.rowax = &g.A.row; pr.colax = &g.A.col;
-    pr.mrowax = &g.Amul.row; pr.mcolax = &g.Amul.col;
-  } else {
-    pr.mode = p.b_mode;
-    pr.rowax = &g.B.col; pr.colax = &g.B.row;      // B tile rows = n (B.col axis), columns = k (B.row axis)
-    pr.mrowax = &g.B.col; pr.mcolax = &g.B.row;
-  }
-  auto enter_item = [&](int w, int& kb0, int& kb1) {
-    int q = w;
-    const int ks = q % p.nsplit; q /= p.nsplit;
-    const int tn = q % p.ntn; q /= p.ntn;
-    const int tm = q % p.ntm;
-    const int batch = q / p.ntm;
-    kb0 = ks * p.kb_per_split;
-    kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-    if (IS_A) {
-      const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, batch);
-      const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, batch) : nullptr;
-      pr.begin_item(ab, mb, tm * TC_BM, g.M);
-    } else {
-      const float* bb = (const float*)g.B.ptr + axoff64(g.B.batch, batch);
-      pr.begin_item(bb, nullptr, tn * ROWS, g.N);
-    }
-  };
-  float4 cur[P::NV], nxt[P::NV], curm[P::NM], nxtm[P::NM];
-#pragma unroll
-  for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-  int w = blockIdx.x;
-  if (w >= p.total_items) return;
-  int kb, kb1;
-  enter_item(w, kb, kb1);
-  pr.load(kb, nxt, nxtm);                        // position 0
-  uint32_t it = 0;
-  bool more = true;
-#pragma unroll 1
-  while (more) {
-#pragma unroll
-    for (int i = 0; i < P::NV; ++i) cur[i] = nxt[i];
-#pragma unroll
-    for (int i = 0; i < P::NM; ++i) curm[i] = nxtm[i];
-    // advance to the next position and put its loads in flight
-    if (++kb >= kb1) {
-      w += gridDim.x;
-      more = w < p.total_items;
-      if (more) enter_item(w, kb, kb1);
-    }
-    if (more) pr.load(kb, nxt, nxtm);
-    // store the current position
-    const int s = it % STAGES;
-    const uint32_t ph = (it / STAGES) & 1;
-    if (lane == 0) mbar_wait(empty_bar + s, ph ^ 1, 0);
-    __syncwarp();
-    uint8_t* st = smem + s * STAGE_BYTES + plane_off;
-    pr.store(cur, curm, st, st + plane_bytes);
-    fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar + s);
-    ++it;
-  }
-}
-
 template <int BN, bool X3, bool AMUL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p,
                                                                 const __grid_constant__ TcMaps maps) {
-  using Cfg = TcCfg<BN, X3>;
+  using Cfg = TcCfg<BN, X3, AMUL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -798,8 +587,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar + s, TC_A_WARPS + TC_B_WARPS);
       mbar_init(empty_bar + s, 1);
-      mbar_init(rawa_bar + s, p.a_async ? TC_A_WARPS * 32 : 1);
-      mbar_init(rawb_bar + s, p.b_async ? TC_B_WARPS * 32 : 1);
+      mbar_init(rawa_bar + s, (!AMUL && p.a_tma) ? 1 : TC_A_WARPS * 32);
+      mbar_init(rawb_bar + s, p.b_tma ? 1 : TC_B_WARPS * 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
@@ -819,24 +608,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (!AMUL && p.a_tma)
         transform_all<TC_BM, TC_A_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(p, smem, 0, Cfg::A_PLANE, full_bar,
                                                                           rawa_bar, threadIdx.x, lane);
-      else if (p.a_async)
+      else
         produce_async<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
             p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, rawa_bar, threadIdx.x, lane);
-      else
-        produce_all<TC_BM, TC_A_WARPS * 32, X3, AMUL, Cfg::STAGES, Cfg::STAGE, true>(
-            p, smem, 0, Cfg::A_PLANE, full_bar, empty_bar, threadIdx.x, lane);
     } else {
       if (p.b_tma)
         transform_all<BN, TC_B_WARPS * 32, X3, Cfg::STAGES, Cfg::STAGE>(
-            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, lane);
-      else if (p.b_async)
-        produce_async<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
-            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar, rawb_bar,
-            threadIdx.x - TC_A_WARPS * 32, lane);
+            p, smem, Cfg::B_OFF, Cfg::B_PLANE, full_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, lane);
       else
-        produce_all<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
-            p, smem, Cfg::PLANES * Cfg::A_PLANE, Cfg::B_PLANE, full_bar, empty_bar,
-            threadIdx.x - TC_A_WARPS * 32, lane);
+        produce_async<BN, TC_B_WARPS * 32, X3, false, Cfg::STAGES, Cfg::STAGE, false>(
+            p, smem, Cfg::B_OFF, Cfg::B_PLANE, full_bar, empty_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, lane);
     }
   } else if (warp == TC_TMA_WARP) {
     // =============================== TMA issuer ========================================
@@ -863,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         if (p.b_tma) {
           const int bl = p.b_bdim[1] ? pos.batch % g.B.batch.d1 : 0, bh = p.b_bdim[0] ? pos.batch / g.B.batch.d1 : 0;
-          uint8_t* sb = st + Cfg::PLANES * Cfg::A_PLANE;
+          uint8_t* sb = st + Cfg::B_OFF;
           mbar_expect_tx(rawb_bar + s, Cfg::B_PLANE);
           if (b_mn) {
 #pragma unroll
@@ -900,7 +681,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_wait(full_bar + s, ph, 0);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE);
-          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE;
+          const uint32_t sb = sa + Cfg::B_OFF;
           const uint64_t a_hi = a_mn ? make_desc_mn(sa, (TC_BM / 32) * 512) : make_desc_k(sa);
           const uint64_t a_lo = a_mn ? make_desc_mn(sa + Cfg::A_PLANE, (TC_BM / 32) * 512) : make_desc_k(sa + Cfg::A_PLANE);
           const uint64_t b_hi = b_mn ? make_desc_mn(sb, (BN / 32) * 512) : make_desc_k(sb);
@@ -1184,7 +965,7 @@ static int g_num_sms = 0;
 
 template <int BN, bool X3, bool AMUL>
 static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream) {
-  using Cfg = TcCfg<BN, X3>;
+  using Cfg = TcCfg<BN, X3, AMUL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3, AMUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -1230,20 +1011,6 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
   p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
   p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
-  static int async_on = -1;
-  if (async_on < 0) {
-    const char* env = getenv("DSTAG_TC_ASYNC");
-    async_on = (env && env[0] == '0') ? 0 : 1;
-  }
-  // the Hadamard factor parks in the lo plane: only possible in the 3-pass mode (which has one)
-  static int async_scalar = -1;
-  if (async_scalar < 0) {
-    const char* env = getenv("DSTAG_TC_ASYNC_SCALAR");
-    async_scalar = (env && env[0] == '0') ? 0 : 1;
-  }
-  auto vec = [](int m) { return m == MODE_KVEC || m == MODE_MVEC; };
-  p.a_async = (async_on && !p.a_tma && (vec(p.a_mode) || async_scalar) && (!am || x3)) ? 1 : 0;
-  p.b_async = (async_on && !p.b_tma && (vec(p.b_mode) || async_scalar)) ? 1 : 0;
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
             : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))

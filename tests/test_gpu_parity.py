@@ -88,11 +88,19 @@ def test_net_matches_oracle_at_config_shapes(shape):
     torch.nn.SmoothL1Loss()(y, tgt.to(dev)).backward()
     assert rel_err(y.detach(), y_ref.detach()) < TOL_PRED
     ograds = {k: v.grad for k, v in onet.named().items()}
+    # yardstick for the ill-conditioned gradients (attention projections: tiny sums of cancelling
+    # terms): the error the SAME algorithm makes in plain fp32 on the CPU, against its fp64 run
+    onet32 = O.build_oracle(N, T, K, H, Dm, nb, dtype=torch.float32, faithful=False)
+    for k, v in onet32.named().items():
+        v.data.copy_(onet.named()[k].data.float())
+    torch.nn.SmoothL1Loss()(onet32(x.float()), tgt.float()).backward()
+    fp32_err = {k: (rel_err(v.grad, ograds[k]) if v.grad is not None else 0.0) for k, v in onet32.named().items()}
     for k, p in net.named_parameters():
         if ograds[k] is None:
             assert p.grad is None, k
         else:
-            assert rel_err(p.grad, ograds[k]) < 5e-4, k
+            e = rel_err(p.grad, ograds[k])
+            assert e < max(5e-4, 3 * fp32_err[k]), f"{k}: {e:.3e} (fp32 oracle itself: {fp32_err[k]:.3e})"
 
 
 def test_train_mode_runs_and_dropout_is_active():

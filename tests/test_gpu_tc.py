@@ -163,3 +163,18 @@ def test_tc_two_level_rows_split_to_batch(N, precision):
     dA = ct.empty_rows((Bz, F, T, N), dev)
     _run("dtf,bnd->bftn", W, dZ, precision, out=dA)
     assert rel_err(dA, torch.einsum("dtf,bnd->bftn", W.double(), dZ.double())) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("shape", [(6, 70, 32, 70), (4, 200, 24, 130), (2, 300, 64, 96), (2, 129, 16, 257)])
+def test_tc_row_contiguous_operands_narrow_n(shape, precision):
+    """MN-major operands with the 32- and 64-wide N tiles (the spatial-attention dq/dk shapes):
+    the row-quad producer has 2 (N tile 32) or 4 (N tile 64) k's per thread."""
+    b, m, n, k = shape
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    A = torch.randn(b, k, m + 2, device=dev)[..., :m] if m % 4 == 2 else torch.randn(b, k, m, device=dev)
+    B = torch.randn(b, k, n, device=dev)
+    out = _run("bkm,bkn->bmn", A, B, precision)
+    ref = torch.einsum("bkm,bkn->bmn", A.double(), B.double())
+    assert rel_err(out, ref) < TOL[precision]
