@@ -36,7 +36,7 @@ constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
 constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;         // one thread issues the TMA bulk-tensor loads
 constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // 576
 constexpr int TC_SMEM_BUDGET = 196 * 1024;            // operand stages
-constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 32 * 33 * 4;   // per-warp 32 x 33 transpose buffers
+constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 32 * 36 * 4;   // per-warp 32 x 32 transpose buffers (row stride 33 or 36)
 
 enum { MODE_KVEC = 0, MODE_MVEC = 1, MODE_ROWG = 2, MODE_KSC = 3 };
 
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else {
     // =============================== epilogue ==========================================
     const int q4 = warp & 3;                   // TMEM lane quarter this warp may access
-    float* tbuf = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + q4 * (32 * 33);
+    float* tbuf = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + q4 * (32 * 36);
     const bool c_unit = g.C.col.d1 == 1 && g.C.col.s0 == 1;
     const bool ca_unit = !g.Cadd.ptr || (g.Cadd.col.d1 == 1 && g.Cadd.col.s0 == 1);
     const bool cm_unit = !g.Cmul.ptr || (g.Cmul.col.d1 == 1 && g.Cmul.col.s0 == 1);
@@ -714,6 +714,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const bool c_inner1 = inner1(g.C.col);
     const bool ca_inner1 = !g.Cadd.ptr || inner1(g.Cadd.col) || (g.Cadd.col.s0 == 0 && g.Cadd.col.d1 == 1);
     const bool cm_inner1 = !g.Cmul.ptr || inner1(g.Cmul.col) || (g.Cmul.col.s0 == 0 && g.Cmul.col.d1 == 1);
+    // 4 consecutive columns (starting at a multiple of 4) are 4 consecutive, 16-byte aligned floats
+    auto quad = [](const dstag_operand_t& o) {
+      const dstag_axis_t& a = o.col;
+      const bool runs = a.d1 == 1 ? a.s0 == 1 : (a.s1 == 1 && a.d1 % 4 == 0 && a.s0 % 4 == 0);
+      return runs && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && o.batch.s0 % 4 == 0 &&
+             (o.batch.d1 == 1 || o.batch.s1 % 4 == 0);
+    };
+    const bool c_quad = g.accumulate != DSTAG_ACC_ATOMIC && quad(g.C) && (!g.Cadd.ptr || quad(g.Cadd)) &&
+                        (!g.Cmul.ptr || quad(g.Cmul));
     uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
       int q = w;
@@ -768,6 +777,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               *dst = o;
             }
           }
+        } else if (c_quad && full && __all_sync(0xffffffffu, ((c_ro | ca_ro | cm_ro) & 3) == 0)) {
+          // (b4) columns contiguous in 16-byte aligned runs of a multiple of 4 (e.g. n = (x, t), t innermost):
+          //      transpose the 32 x 32 block through shared memory; every lane then stores float4s,
+          //      8 lanes covering the 32 columns of one row, 4 rows per instruction
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int q = lane & 7, rsub = lane >> 3;
+          const int n = n0 + 4 * q;
+          const int co = axoff32(g.C.col, n);
+          const int cao = Cab ? axoff32(g.Cadd.col, n) : 0;
+          const int cmo = Cmb ? axoff32(g.Cmul.col, n) : 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = rsub + 4 * i;
+            const int mr = tm * TC_BM + q4 * 32 + rr;
+            const int ro = __shfl_sync(0xffffffffu, c_ro, rr);
+            const int rao = __shfl_sync(0xffffffffu, ca_ro, rr);
+            const int rmo = __shfl_sync(0xffffffffu, cm_ro, rr);
+            if (mr < g.M) {
+              const float4 tv = *reinterpret_cast<const float4*>(tbuf + rr * 36 + 4 * q);
+              float4 o = make_float4(g.alpha * tv.x, g.alpha * tv.y, g.alpha * tv.z, g.alpha * tv.w);
+              if (Cab) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(Cab + rao + cao));
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              if (Cmb) o = mul4(o, __ldg(reinterpret_cast<const float4*>(Cmb + rmo + cmo)));
+              if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              float4* dst = reinterpret_cast<float4*>(Cb + ro + co);
+              if (g.accumulate == DSTAG_ACC_ADD) {
+                const float4 old = *dst;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *dst = o;
+            }
+          }
+          __syncwarp();
         } else if (c_inner1 && ca_inner1 && cm_inner1) {
           // (b) columns contiguous in memory but unaligned / narrow / atomic / two-level (e.g. n = (x, t)):
           //     transpose the 32 x 32 block through shared memory so that consecutive lanes touch

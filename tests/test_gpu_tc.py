@@ -178,3 +178,26 @@ def test_tc_row_contiguous_operands_narrow_n(shape, precision):
     out = _run("bkm,bkn->bmn", A, B, precision)
     ref = torch.einsum("bkm,bkn->bmn", A.double(), B.double())
     assert rel_err(out, ref) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("T", [12, 8, 6])
+def test_tc_epilogue_aligned_runs_of_columns(T, precision):
+    """Output columns n = (x, t) with t innermost and the m index in between (the theta-mix input
+    gradient): runs of T contiguous floats.  T % 4 == 0 takes the float4 transposed epilogue, T = 6
+    the scalar one; with an epilogue multiplier / accumulate in the same layout."""
+    from dstagnn_drought_b200._lib import ACC_ADD
+    dev = torch.device("cuda:0")
+    torch.manual_seed(9)
+    X, M, K = 301, 96, 32
+    th = torch.randn(M, K, device=dev)
+    gx = torch.randn(X, T, K, device=dev)
+    ref = torch.einsum("mk,xtk->xmt", th.double(), gx.double())
+    out = _run("mk,xtk->xmt", th, gx, precision)
+    assert rel_err(out, ref) < TOL[precision]
+    mul = torch.randn(X, M, T, device=dev)
+    out2 = torch.ones(X, M, T, device=dev)
+    _run("mk,xtk->xmt", th, gx, precision, out=out2, c_mul=("xmt", mul), accumulate=ACC_ADD)
+    assert rel_err(out2, ref * mul.double() + 1.0) < TOL[precision]
+    out3 = _run("mk,xtk->xmt", th, gx, precision, relu=True, alpha=0.5)
+    assert rel_err(out3, torch.relu(0.5 * ref)) < TOL[precision]

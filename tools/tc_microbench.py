@@ -56,6 +56,14 @@ def main():
         ("theta_dth", "kxft,xtc->kfc", Z.view(K, X, F, T), g, {}),
         ("fcmy_dw", "rt,rs->ts", dtc, cat, {}),
     ]
+    # epilogue calibration: same GEMM (M=96, N=X*T, K=32), three output layouts
+    th2, g2 = r(96, 32), r(X * T, 32)
+    obuf = torch.empty(96 * X * T + 8, device=dev)
+    cases += [
+        ("epi_vec", "mk,nk->mn", th2, g2, dict(out=obuf[:96 * X * T].view(96, X * T))),            # (a) float4 rows
+        ("epi_unal", "mk,nk->mn", th2, g2, dict(out=obuf[1:96 * X * T + 1].view(96, X * T))),       # (b) unaligned rows
+        ("epi_2lvl", "mk,xtk->xmt", th2, g2.view(X, T, 32), dict(out=obuf[:96 * X * T].view(X, 96, T))),  # (b) runs of T
+    ]
     for ks in (3, 5, 7):
         tp, pad = T - ks + 1, ks - 1
         tpad = tp + 2 * pad
