@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -57,7 +57,9 @@ SIGNATURES = {
     "dstag_tattn_fwd": (C.c_int, [_F, _F, _i32, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tattn_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_fwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
-    "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_outer_sum_supported": (C.c_int, [_i32, _i32]),
+    "dstag_outer_sum": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _F]),
     "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F]),
     "dstag_tail_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i32, _i32, _f32,
                                  _u64, _F]),
@@ -98,7 +100,8 @@ class _Profiled:
     a CUDA-event pair named after the function."""
 
     _PLAIN = ("dstag_abi_version", "dstag_last_error", "dstag_launch_count", "dstag_reset_launch_count",
-              "dstag_gemm", "dstag_gemm_uses_tensor_cores", "dstag_tail_fused_supported")
+              "dstag_gemm", "dstag_gemm_uses_tensor_cores", "dstag_tail_fused_supported",
+              "dstag_outer_sum_supported")
 
     def __init__(self, lib):
         self._cdll = lib

@@ -28,13 +28,18 @@ __global__ void gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restri
   }
 }
 
-__global__ void gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
-                                    float* __restrict__ dup, long long total, int C, int Tp, int pad,
-                                    int out_ld, int out_off) {
+__global__ void __launch_bounds__(256)
+gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout, float* __restrict__ dup,
+                    float* __restrict__ db, long long total, int C, int Tp, int pad, int out_ld, int out_off) {
   // dup: (X, Tp + 2 pad, 2C) channels-last gradient of the conv output, zero in the pad rows.
   // One thread per (x, padded t, c): evaluates the gate once and writes both halves (p and q).
+  // db (2C, optional): the conv bias gradient = column sums of dup.  When the grid stride is a
+  // multiple of C every thread keeps one channel, so the sums stay in registers until the end.
+  __shared__ float red[2][256];
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int Tpad = Tp + 2 * pad;
+  const bool fixed_c = db && (256 % C == 0);
+  float sp = 0.f, sq = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long xt = i / C;                        // c fastest: coalesced reads of u, writes of dup
     const int c = (int)(i - xt * C);
@@ -47,9 +52,88 @@ __global__ void gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __
       const float d = __ldg(dout + (x * C + c) * out_ld + out_off + t);
       rp = d * sg * (1.f - th * th);
       rq = d * th * sg * (1.f - sg);
+      if (db && !fixed_c) {
+        atomicAdd(db + c, rp);
+        atomicAdd(db + C + c, rq);
+      }
     }
+    sp += rp;
+    sq += rq;
     dup[xt * 2 * C + c] = rp;
     dup[xt * 2 * C + C + c] = rq;
+  }
+  if (fixed_c) {
+    red[0][threadIdx.x] = sp;
+    red[1][threadIdx.x] = sq;
+    __syncthreads();
+    if (threadIdx.x < C) {                             // thread c sums the 256 / C threads of its channel
+      float a = 0.f, b = 0.f;
+      for (int j = threadIdx.x; j < 256; j += C) { a += red[0][j]; b += red[1][j]; }
+      atomicAdd(db + threadIdx.x, a);
+      atomicAdd(db + C + threadIdx.x, b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// out[m, n] += sum_r a[r, m] * b[r, n] for two tall, narrow row-major matrices (m * n / 4 <= 256):
+// the fcmy weight gradient (T x (3T-12) outputs, B*N*C rows).  A tensor-core tile would be 98% padding;
+// this is a streaming reduction: a CTA stages 256-row slabs in shared memory, thread (row phase, m,
+// n quad) keeps 4 accumulators, the row phases are folded through shared memory at the end.
+// ---------------------------------------------------------------------------------------
+constexpr int kOsRows = 256;
+__global__ void __launch_bounds__(256)
+outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long rows,
+                 int m, int n, int phases) {
+  extern __shared__ float sm[];
+  float* as = sm;                     // kOsRows x m
+  float* bs = sm + kOsRows * m;       // kOsRows x n
+  const int nq = n >> 2, per = m * nq;               // outputs quads
+  const int ph = threadIdx.x / per, id = threadIdx.x - ph * per;
+  const bool active = ph < phases;
+  const int mi = id / nq, q = id - mi * nq;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long nslab = (rows + kOsRows - 1) / kOsRows;
+  const bool vec = (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);   // n % 4 == 0, b aligned: checked by the host
+  for (long long sl = blockIdx.x; sl < nslab; sl += gridDim.x) {
+    const long long r0 = sl * kOsRows;
+    const int nr = (int)min((long long)kOsRows, rows - r0);
+    __syncthreads();
+    if (vec) {                                            // whole slabs are 16-byte aligned: float4 streams
+      const float4* a4 = reinterpret_cast<const float4*>(a + r0 * m);
+      const float4* b4 = reinterpret_cast<const float4*>(b + r0 * n);
+      const int na = nr * m / 4, nb = nr * n / 4;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < na; i += 256) reinterpret_cast<float4*>(as)[i] = __ldg(a4 + i);
+#pragma unroll 8
+      for (int i = threadIdx.x; i < nb; i += 256) reinterpret_cast<float4*>(bs)[i] = __ldg(b4 + i);
+    } else {
+      for (int i = threadIdx.x; i < nr * m; i += blockDim.x) as[i] = __ldg(a + r0 * m + i);
+      for (int i = threadIdx.x; i < nr * n; i += blockDim.x) bs[i] = __ldg(b + r0 * n + i);
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int r = ph; r < nr; r += phases) {
+        const float av = as[r * m + mi];
+        const float4 bv = *reinterpret_cast<const float4*>(bs + r * n + 4 * q);
+        acc.x = fmaf(av, bv.x, acc.x); acc.y = fmaf(av, bv.y, acc.y);
+        acc.z = fmaf(av, bv.z, acc.z); acc.w = fmaf(av, bv.w, acc.w);
+      }
+    }
+  }
+  __syncthreads();
+  float4* red = reinterpret_cast<float4*>(sm);
+  if (active) red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < per) {
+    float4 t = red[threadIdx.x];
+    for (int p2 = 1; p2 < phases; ++p2) {
+      const float4 o = red[p2 * per + threadIdx.x];
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    float* dst = out + mi * n + 4 * q;
+    atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
   }
 }
 
@@ -244,7 +328,7 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
   DSTAG_RETURN_LAUNCH("dstag_gtu_gate_fwd");
 }
 
-int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X, int32_t C, int32_t Tp,
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C, int32_t Tp,
                        int32_t pad, int32_t out_ld, int32_t out_off, void* stream) {
   DSTAG_CHECK_ARG(u && dout && dup && X > 0 && C > 0 && Tp > 0 && pad >= 0 && out_off >= 0 &&
                       out_off + Tp <= out_ld,
@@ -252,9 +336,28 @@ int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X,
   const long long total = (long long)X * (Tp + 2 * pad) * C;
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, dup, total, C, Tp, pad,
+  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(u, dout, dup, db, total, C, Tp, pad,
                                                                           out_ld, out_off);
   DSTAG_RETURN_LAUNCH("dstag_gtu_gate_bwd");
+}
+
+int dstag_outer_sum_supported(int32_t m, int32_t n) {
+  return (m > 0 && n > 0 && n % 4 == 0 && m * (n / 4) <= 256 && (size_t)kOsRows * (m + n) * 4 <= 96 * 1024) ? 1 : 0;
+}
+
+int dstag_outer_sum(const float* a, const float* b, float* out, int64_t rows, int32_t m, int32_t n, void* stream) {
+  DSTAG_CHECK_ARG(a && b && out && rows > 0, "dstag_outer_sum: bad arguments");
+  DSTAG_CHECK_ARG(dstag_outer_sum_supported(m, n), "dstag_outer_sum: unsupported shape m=%d n=%d", m, n);
+  DSTAG_CHECK_ARG((reinterpret_cast<uintptr_t>(b) & 15) == 0, "dstag_outer_sum: b must be 16-byte aligned");
+  const int per = m * (n / 4);
+  const int phases = 256 / per;
+  const size_t smem = (size_t)kOsRows * (m + n) * sizeof(float);
+  int rc = opt_in_smem((const void*)outer_sum_kernel, smem, "dstag_outer_sum");
+  if (rc) return rc;
+  const long long nslab = (rows + kOsRows - 1) / kOsRows;
+  const int grid = (int)(nslab < kNumSMs * 4 ? nslab : kNumSMs * 4);
+  outer_sum_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, out, rows, m, n, phases);
+  DSTAG_RETURN_LAUNCH("dstag_outer_sum");
 }
 
 int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,

@@ -328,12 +328,12 @@ class GtuStack(torch.autograd.Function):
             tp, pad = T - ks + 1, ks - 1
             tpad = tp + 2 * pad
             dup = torch.empty((X, tpad, 2 * Cc), device=g.device, dtype=torch.float32)
-            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), X, Cc, tp, pad,
-                                              total, off, _stream(g)), "dstag_gtu_gate_bwd")
+            db = torch.zeros(2 * Cc, device=g.device, dtype=torch.float32)           # bias gradient, fused
+            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), db.data_ptr(), X, Cc,
+                                              tp, pad, total, off, _stream(g)), "dstag_gtu_gate_bwd")
             du = dup[:, pad:pad + tp, :]                                             # valid rows (view)
             dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
             dw = dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1).reshape(w.shape)
-            db = colsum(dup, X * tpad, 2 * Cc)                                       # pad rows are zero
             if dg is not None:
                 wflip = w[:, :, 0, :].flip(-1).permute(1, 2, 0).reshape(Cc, ks * 2 * Cc).contiguous()
                 dview = dup.as_strided((X, T, ks * 2 * Cc), (tpad * 2 * Cc, 2 * Cc, 1))
@@ -439,6 +439,12 @@ class FusedTail(torch.autograd.Function):
                                             dcat.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
                                             dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
                                             _stream(r)), "dstag_tail_fused_bwd")
-        dwf = contract_raw("rt,rs->ts", dtc.view(X * Cc, T), cat.view(X * Cc, S), tag="fcmy_dw")
+        if lib.dstag_outer_sum_supported(T, S):
+            # T x S outputs reduced over B*N*C rows: a streaming reduction, not a tensor-core shape
+            dwf = torch.zeros((T, S), device=r.device, dtype=torch.float32)
+            _lib.check(lib.dstag_outer_sum(dtc.data_ptr(), cat.data_ptr(), dwf.data_ptr(), X * Cc, T, S,
+                                           _stream(r)), "dstag_outer_sum")
+        else:
+            dwf = contract_raw("rt,rs->ts", dtc.view(X * Cc, T), cat.view(X * Cc, S), tag="fcmy_dw")
         dbf = colsum(dtc, X * Cc, T)
         return dcat, dwf, dbf, dg, dr, dgamma, dbeta, None, None

@@ -166,9 +166,17 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
                        int32_t out_off, void* stream);
 /* dup (X, Tp + 2*pad, 2C): gradient w.r.t. u, written with `pad` zero rows before and after the
  * Tp valid time steps, so that the conv input gradient is a gather-only correlation over an
- * unfolded view of dup (no atomics). */
-int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, int64_t X, int32_t C, int32_t Tp,
-                       int32_t pad, int32_t out_ld, int32_t out_off, void* stream);
+ * unfolded view of dup (no atomics).  db (2C, nullable, zeroed by the caller): the conv bias
+ * gradient (column sums of dup) is ACCUMULATED into it. */
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C,
+                       int32_t Tp, int32_t pad, int32_t out_ld, int32_t out_off, void* stream);
+
+/* out[m, n] += sum_r a[r, m] * b[r, n]  (a: rows x m, b: rows x n, row-major, b 16-byte aligned;
+ * out zeroed by the caller).  The fcmy weight gradient (autograd of model/DSTAGNN_my.py:243):
+ * a T x (3T-12) result reduced over B*N*C rows -- a streaming reduction, not a tensor-core shape.
+ * Supported when n % 4 == 0 and m * n / 4 <= 256 (dstag_outer_sum_supported). */
+int dstag_outer_sum_supported(int32_t m, int32_t n);
+int dstag_outer_sum(const float* a, const float* b, float* out, int64_t rows, int32_t m, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Block tail (model/DSTAGNN_my.py:243-252):

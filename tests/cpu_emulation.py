@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 4
+        return 5
 
     def dstag_last_error(self):
         return self.err
@@ -214,7 +214,17 @@ class FakeLib:
         O[:, :, out_off:out_off + Tp] = (np.tanh(U[:, :, :Cc]) / (1 + np.exp(-U[:, :, Cc:]))).transpose(0, 2, 1)
         return 0
 
-    def dstag_gtu_gate_bwd(self, u, dout, dup, X, Cc, Tp, pad, out_ld, out_off, stream):
+    def dstag_outer_sum_supported(self, m, n):
+        return int(m > 0 and n > 0 and n % 4 == 0 and m * (n // 4) <= 256)
+
+    def dstag_outer_sum(self, a, b, out, rows, m, n, stream):
+        self.launches += 1
+        A = _arr(a, rows * m).reshape(rows, m).astype(np.float64)
+        Bm = _arr(b, rows * n).reshape(rows, n).astype(np.float64)
+        _arr(out, m * n).reshape(m, n)[:] += A.T @ Bm
+        return 0
+
+    def dstag_gtu_gate_bwd(self, u, dout, dup, db, X, Cc, Tp, pad, out_ld, out_off, stream):
         self.launches += 1
         U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
         d = _arr(dout, X * Cc * out_ld).reshape(X, Cc, out_ld)[:, :, out_off:out_off + Tp].astype(np.float64)
@@ -224,6 +234,8 @@ class FakeLib:
         D[:] = 0
         D[:, pad:pad + Tp, :Cc] = d * sg * (1 - th * th)
         D[:, pad:pad + Tp, Cc:] = d * th * sg * (1 - sg)
+        if db:
+            _arr(db, 2 * Cc)[:] += D.reshape(-1, 2 * Cc).astype(np.float64).sum(0)
         return 0
 
     def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, stream):
