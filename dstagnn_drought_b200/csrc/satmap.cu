@@ -107,6 +107,125 @@ sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ b
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Register-resident variant for ld <= 1024 (all PEMS / drought graph sizes): a warp owns 4 output
+// rows j and keeps their complete logit rows in registers (4 x 4*NT values per lane, NT column tiles
+// of 128), so the softmax needs no shared-memory round trip at all: 16 FMAs per pair of
+// shared-memory loads in the product loop, row max / sum by warp shuffles, one float4 store per value.
+// CTA = 4 warps = 16 rows of one (b, k); the W_Q projection streams through shared memory in
+// transposed 128-column tiles.
+// ---------------------------------------------------------------------------------------
+constexpr int kSatRowsCta = 16;
+constexpr int kSatRowThreads = 128;
+
+template <int NT>
+__global__ void __launch_bounds__(kSatRowThreads)
+sat_softmax_rows_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, float* __restrict__ P, int N,
+                        int K, int dk, int ld, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* KsT = sm;                               // [dk][16]
+  float* QsT = sm + dk * kSatRowsCta;            // [dk][kSatQld]
+  const int bk = blockIdx.y, b = bk / K, k = bk - b * K;
+  const int j0 = blockIdx.x * kSatRowsCta;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long nstride = 2LL * K * dk;                        // qk: (B, N, 2, K, dk)
+  const float* qbase = qk + (long long)b * N * nstride + (long long)k * dk;
+  const float* kbase = qbase + (long long)K * dk;
+  const int dq = dk >> 2;                                         // float4 per projection row (dk % 4 == 0)
+
+  for (int e = tid; e < kSatRowsCta * dq; e += kSatRowThreads) {
+    const int r = e / dq, d4 = e - r * dq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j0 + r < N) v = __ldg(reinterpret_cast<const float4*>(kbase + (long long)(j0 + r) * nstride) + d4);
+    KsT[(4 * d4 + 0) * kSatRowsCta + r] = v.x;
+    KsT[(4 * d4 + 1) * kSatRowsCta + r] = v.y;
+    KsT[(4 * d4 + 2) * kSatRowsCta + r] = v.z;
+    KsT[(4 * d4 + 3) * kSatRowsCta + r] = v.w;
+  }
+  float acc[4][4 * NT];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4 * NT; ++c) acc[r][c] = 0.f;
+
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int i0 = t * kSatTileI;
+    __syncthreads();
+    for (int e = tid; e < kSatTileI * dq; e += kSatRowThreads) {
+      const int il = e / dq, d4 = e - il * dq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + il < N) v = __ldg(reinterpret_cast<const float4*>(qbase + (long long)(i0 + il) * nstride) + d4);
+      QsT[(4 * d4 + 0) * kSatQld + il] = v.x;
+      QsT[(4 * d4 + 1) * kSatQld + il] = v.y;
+      QsT[(4 * d4 + 2) * kSatQld + il] = v.z;
+      QsT[(4 * d4 + 3) * kSatQld + il] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int d = 0; d < dk; ++d) {
+      const float4 q = *reinterpret_cast<const float4*>(QsT + d * kSatQld + 4 * lane);
+      const float4 kv = *reinterpret_cast<const float4*>(KsT + d * kSatRowsCta + 4 * w);   // warp-uniform: broadcast
+      const float kr[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r][4 * t + 0] = fmaf(q.x, kr[r], acc[r][4 * t + 0]);
+        acc[r][4 * t + 1] = fmaf(q.y, kr[r], acc[r][4 * t + 1]);
+        acc[r][4 * t + 2] = fmaf(q.z, kr[r], acc[r][4 * t + 2]);
+        acc[r][4 * t + 3] = fmaf(q.w, kr[r], acc[r][4 * t + 3]);
+      }
+    }
+  }
+  // logits = acc * scale + bias; softmax over the row; columns [N, ld) are written as zeros
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = j0 + 4 * w + r;
+    if (j >= N) continue;                                          // warp-uniform
+    const float* brow = biasT + ((long long)k * N + j) * ld;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int i = t * kSatTileI + 4 * lane;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < ld) bb = __ldg(reinterpret_cast<const float4*>(brow + i));
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float v = (i + c < N) ? fmaf(acc[r][4 * t + c], scale, bv[c]) : -INFINITY;
+        acc[r][4 * t + c] = v;
+        mx = fmaxf(mx, v);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4 * NT; ++c) {
+      const float e = __expf(acc[r][c] - mx);                      // exp(-inf) = 0 for the masked columns
+      acc[r][c] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    float* out = P + (((long long)b * K + k) * N + j) * ld;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int i = t * kSatTileI + 4 * lane;
+      if (i < ld)
+        *reinterpret_cast<float4*>(out + i) = make_float4(acc[r][4 * t] * inv, acc[r][4 * t + 1] * inv,
+                                                          acc[r][4 * t + 2] * inv, acc[r][4 * t + 3] * inv);
+    }
+  }
+}
+
+template <int NT>
+static int launch_sat_rows(const float* qk, const float* biasT, float* P, int B, int N, int K, int dk, int ld,
+                           float scale, cudaStream_t stream) {
+  const size_t smem = (size_t)dk * (kSatRowsCta + kSatQld) * sizeof(float);
+  const dim3 grid((N + kSatRowsCta - 1) / kSatRowsCta, B * K);
+  sat_softmax_rows_kernel<NT><<<grid, kSatRowThreads, smem, stream>>>(qk, biasT, P, N, K, dk, ld, scale);
+  DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd(rows)");
+}
+
 }  // namespace dstag
 
 using namespace dstag;
@@ -118,9 +237,25 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float*
                   "dstag_sat_softmax_fwd: bad sizes");
   DSTAG_CHECK_ARG(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(biasT) & 15) == 0,
                   "dstag_sat_softmax_fwd: ld must be a multiple of 4 and biasT 16-byte aligned");
+  const float scale = 1.0f / sqrtf((float)dk);
+  const int nt = (ld + kSatTileI - 1) / kSatTileI;
+  const bool rows_ok = nt <= 8 && dk % 4 == 0 && (size_t)dk * (kSatRowsCta + kSatQld) * 4 <= 48 * 1024 &&
+                       (reinterpret_cast<uintptr_t>(qk) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+  if (rows_ok) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nt) {
+      case 1: return launch_sat_rows<1>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 2: return launch_sat_rows<2>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 3: return launch_sat_rows<3>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 4: return launch_sat_rows<4>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 5: return launch_sat_rows<5>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 6: return launch_sat_rows<6>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 7: return launch_sat_rows<7>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      default: return launch_sat_rows<8>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+    }
+  }
   const size_t fixed = (size_t)(dk * kSatQld) * sizeof(float);
   auto need = [&](int R) { return fixed + (size_t)R * (dk + ld) * sizeof(float); };
-  const float scale = 1.0f / sqrtf((float)dk);
   const size_t budget = 200 * 1024;
 #define DSTAG_SAT_LAUNCH(R_)                                                                                     \
   do {                                                                                                           \

@@ -170,7 +170,7 @@ def test_temporal_attention(dev, cfg):
         assert rel_err(a.grad, b.grad) < 5e-5
 
 
-@pytest.mark.parametrize("cfg", [(2, 9, 3, 1), (2, 70, 3, 12), (1, 200, 2, 40)])
+@pytest.mark.parametrize("cfg", [(2, 9, 3, 1), (2, 70, 3, 12), (1, 200, 2, 40), (1, 883, 2, 8), (1, 1100, 1, 4)])
 def test_spatial_cheb_conv(dev, precision, cfg):
     from dstagnn_drought_b200.ops import SpatialChebConv, _pad_ld
     Bz, N, K, FT = cfg
