@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
+# A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
+LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
 ABI_VERSION = 5
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
