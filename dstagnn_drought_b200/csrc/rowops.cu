@@ -256,106 +256,158 @@ __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __rest
 // ======================================================================================
 constexpr int kWR = 32;                 // register elements per lane -> rows up to 1024
 
+// Warp-per-row LayerNorm for rows of up to 128 * NV floats whose storage is 16-byte aligned (row-padded
+// tensors): a lane keeps NV float4 of the row in registers, statistics by warp shuffles, no shared
+// memory and no block barriers, so many rows are in flight per SM.  Columns >= L (the padding of the
+// last float4) are masked out of the statistics; whatever is written there is never read.
+__device__ __forceinline__ void ld4_guard(float (&o)[4], const float* __restrict__ p, int c, int L) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = (c + j < L) ? __ldg(p + c + j) : 0.f;
+}
+
+template <int NV>
 __global__ void __launch_bounds__(256)
-ln_fwd_warp_kernel(const float* __restrict__ a, const float* __restrict__ tab, int tab_mod,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, int L,
-                   float drop_p, unsigned long long seed) {
+ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __restrict__ tab, int tab_mod,
+                   long long tab_ld, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ y, long long y_ld, float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                   int L, float drop_p, unsigned long long seed) {
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const float invL = 1.f / (float)L;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float gm[NV][4], bt[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    ld4_guard(gm[i], gamma, 4 * (lane + 32 * i), L);
+    ld4_guard(bt[i], beta, 4 * (lane + 32 * i), L);
+  }
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
-    const float* ap = a + (long long)r * L;
-    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
-    float v[kWR];
+    const float* ap = a + (long long)r * a_ld;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * tab_ld : nullptr;
+    float v[NV][4];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = 0.f;
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < L) {
-        v[i] = __ldg(ap + c);
-        if (tp) v[i] += __ldg(tp + c);
-        s += v[i];
+        x = __ldg(reinterpret_cast<const float4*>(ap + c));
+        if (tp) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + c));
+          x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+        }
       }
+      v[i][0] = x.x; v[i][1] = (c + 1 < L) ? x.y : 0.f; v[i][2] = (c + 2 < L) ? x.z : 0.f; v[i][3] = (c + 3 < L) ? x.w : 0.f;
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
     const float mu = warp_sum(s) * invL;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      if (c < L) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = (c + j < L) ? v[i][j] - mu : 0.f;
+        q = fmaf(d, d, q);
+      }
     }
     const float rs = rsqrtf(warp_sum(q) * invL + eps);
-    float* yp = y + (long long)r * L;
+    float* yp = y + (long long)r * y_ld;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lane + 32 * i);
       if (c < L) {
-        float o = (v[i] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c);
-        if (drop_p > 0.f) o *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
-        yp[c] = o;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = fmaf((v[i][j] - mu) * rs, gm[i][j], bt[i][j]);
+          if (drop_p > 0.f) o[j] *= dropout_scale((unsigned long long)r * L + c + j, seed, drop_p, inv_keep);
+        }
+        *reinterpret_cast<float4*>(yp + c) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256)
-ln_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ tab,
-                   int tab_mod, const float* __restrict__ gamma, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, float* __restrict__ dpre, float* __restrict__ dgamma,
-                   float* __restrict__ dbeta, int rows, int L, float drop_p, unsigned long long seed) {
-  extern __shared__ float sm[];          // [2][L] CTA-level d gamma / d beta accumulators
+ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ a, long long a_ld,
+                   const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dpre,
+                   long long dpre_ld, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int L,
+                   float drop_p, unsigned long long seed) {
+  extern __shared__ float sm[];          // [2][128 * NV] CTA-level d gamma / d beta accumulators
+  constexpr int W = 128 * NV;
   float* sg = sm;
-  float* sb = sm + L;
-  for (int c = threadIdx.x; c < L; c += blockDim.x) { sg[c] = 0.f; sb[c] = 0.f; }
+  float* sb = sm + W;
+  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const float invL = 1.f / (float)L;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float ag[kWR], ab[kWR];
+  float gm[NV][4], ag[NV][4], ab[NV][4];
 #pragma unroll
-  for (int i = 0; i < kWR; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int i = 0; i < NV; ++i) {
+    ld4_guard(gm[i], gamma, 4 * (lane + 32 * i), L);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+  }
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
-    const float* ap = a + (long long)r * L;
-    const float* tp = tab ? tab + (long long)(r % tab_mod) * L : nullptr;
-    const float* dyp = dy + (long long)r * L;
+    const float* ap = a + (long long)r * a_ld;
+    const float* tp = tab ? tab + (long long)(r % tab_mod) * tab_ld : nullptr;
+    const float* dyp = dy + (long long)r * dy_ld;
     const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float xh[kWR], gg[kWR];
+    float xh[NV][4], gg[NV][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      xh[i] = 0.f; gg[i] = 0.f;
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), d4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < L) {
-        float v = __ldg(ap + c);
-        if (tp) v += __ldg(tp + c);
-        const float x = (v - mu) * rs;
-        float d = __ldg(dyp + c);
-        if (drop_p > 0.f) d *= dropout_scale((unsigned long long)r * L + c, seed, drop_p, inv_keep);
-        const float g = d * __ldg(gamma + c);
-        xh[i] = x; gg[i] = g;
-        ag[i] = fmaf(d, x, ag[i]);
-        ab[i] += d;
+        x = __ldg(reinterpret_cast<const float4*>(ap + c));
+        if (tp) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + c));
+          x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+        }
+        d4 = __ldg(reinterpret_cast<const float4*>(dyp + c));
+      }
+      const float xv[4] = {x.x, x.y, x.z, x.w};
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = c + j < L;
+        float d = ok ? dv[j] : 0.f;
+        if (drop_p > 0.f && ok) d *= dropout_scale((unsigned long long)r * L + c + j, seed, drop_p, inv_keep);
+        const float xn = ok ? (xv[j] - mu) * rs : 0.f;
+        const float g = d * gm[i][j];
+        xh[i][j] = xn;
+        gg[i][j] = g;
+        ag[i][j] = fmaf(d, xn, ag[i][j]);
+        ab[i][j] += d;
         s1 += g;
-        s2 = fmaf(g, x, s2);
+        s2 = fmaf(g, xn, s2);
       }
     }
     const float m1 = warp_sum(s1) * invL, m2 = warp_sum(s2) * invL;
-    float* op = dpre + (long long)r * L;
+    float* op = dpre + (long long)r * dpre_ld;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      if (c < L) op[c] = rs * (gg[i] - m1 - xh[i] * m2);
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < L)
+        *reinterpret_cast<float4*>(op + c) =
+            make_float4(rs * (gg[i][0] - m1 - xh[i][0] * m2), rs * (gg[i][1] - m1 - xh[i][1] * m2),
+                        rs * (gg[i][2] - m1 - xh[i][2] * m2), rs * (gg[i][3] - m1 - xh[i][3] * m2));
     }
   }
 #pragma unroll
-  for (int i = 0; i < kWR; ++i) {
-    const int c = lane + 32 * i;
-    if (c < L) { atomicAdd(sg + c, ag[i]); atomicAdd(sb + c, ab[i]); }
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * (lane + 32 * i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < L) { atomicAdd(sg + c + j, ag[i][j]); atomicAdd(sb + c + j, ab[i][j]); }
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < L; c += blockDim.x) {
@@ -419,12 +471,24 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_fwd: bad sizes rows=%d L=%d", rows, L);
   DSTAG_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dstag_layernorm_fwd: bad dropout p");
-  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && y_ld == L && tab_ld == L &&
-      L <= 32 * kWR) {   // measured slower than block-per-row
+  // rows in 16-byte aligned storage of up to 1024 floats: warp-per-row kernel
+  const int nv = (L + 127) / 128;
+  const bool al = a_sc == 1 && a_div == 1 && a_s0 % 4 == 0 && y_ld % 4 == 0 && (tab == nullptr || tab_ld % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(tab)) & 15) == 0 &&
+                  a_s0 >= 4 * ((L + 3) / 4) && y_ld >= 4 * ((L + 3) / 4) && (tab == nullptr || tab_ld >= 4 * ((L + 3) / 4));
+  if (al && nv <= 8) {
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
-    ln_fwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, tab, tab_mod, gamma, beta, eps, y, mean, rstd, rows, L,
-                                                              drop_p, seed);
+#define DSTAG_LN_FWD(NV_)                                                                                       \
+  case NV_:                                                                                                     \
+    ln_fwd_warp_kernel<NV_><<<grid, 256, 0, (cudaStream_t)stream>>>(a, a_s0, tab, tab_mod, tab_ld, gamma, beta, eps, y, \
+                                                                    y_ld, mean, rstd, rows, L, drop_p, seed);    \
+    break
+    switch (nv) {
+      DSTAG_LN_FWD(1); DSTAG_LN_FWD(2); DSTAG_LN_FWD(3); DSTAG_LN_FWD(4);
+      DSTAG_LN_FWD(5); DSTAG_LN_FWD(6); DSTAG_LN_FWD(7); DSTAG_LN_FWD(8);
+    }
+#undef DSTAG_LN_FWD
     DSTAG_RETURN_LAUNCH("dstag_layernorm_fwd(warp)");
   }
   const size_t smem = (size_t)(L + 40) * sizeof(float);
@@ -447,12 +511,27 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
                   "dstag_layernorm_bwd: null pointer");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
                   "dstag_layernorm_bwd: bad sizes rows=%d L=%d", rows, L);
-  if (false && a_sc == 1 && a_div == 1 && a_s0 == L && dy_ld == L && dpre_ld == L && tab_ld == L &&
-      L <= 32 * kWR) {   // measured slower than block-per-row
+  const int nv = (L + 127) / 128;
+  const long long lq = 4 * ((L + 3) / 4);
+  const bool al = a_sc == 1 && a_div == 1 && a_s0 % 4 == 0 && dy_ld % 4 == 0 && dpre_ld % 4 == 0 &&
+                  (tab == nullptr || tab_ld % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dpre) |
+                    reinterpret_cast<uintptr_t>(tab)) & 15) == 0 &&
+                  a_s0 >= lq && dy_ld >= lq && dpre_ld >= lq && (tab == nullptr || tab_ld >= lq);
+  if (al && nv <= 8) {
     const int blocks = (rows + 7) / 8;
     const int grid = blocks < kNumSMs * 2 ? blocks : kNumSMs * 2;
-    ln_bwd_warp_kernel<<<grid, 256, (size_t)2 * L * sizeof(float), (cudaStream_t)stream>>>(
-        dy, a, tab, tab_mod, gamma, mean, rstd, dpre, dgamma, dbeta, rows, L, drop_p, seed);
+    const size_t sm_bytes = (size_t)2 * 128 * nv * sizeof(float);
+#define DSTAG_LN_BWD(NV_)                                                                                        \
+  case NV_:                                                                                                      \
+    ln_bwd_warp_kernel<NV_><<<grid, 256, sm_bytes, (cudaStream_t)stream>>>(                                      \
+        dy, dy_ld, a, a_s0, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed); \
+    break
+    switch (nv) {
+      DSTAG_LN_BWD(1); DSTAG_LN_BWD(2); DSTAG_LN_BWD(3); DSTAG_LN_BWD(4);
+      DSTAG_LN_BWD(5); DSTAG_LN_BWD(6); DSTAG_LN_BWD(7); DSTAG_LN_BWD(8);
+    }
+#undef DSTAG_LN_BWD
     DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd(warp)");
   }
   const size_t smem = (size_t)(4 * L + 40) * sizeof(float);
