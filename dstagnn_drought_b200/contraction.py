@@ -137,9 +137,43 @@ def _k_order(pl: Plan, A, B):
     return rev if score(rev) > score(fwd) else fwd
 
 
+_desc_cache = {}
+
+
+def _layout_key(t):
+    return None if t is None else (t.shape, t.stride())
+
+
 def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, alpha=1.0,
                      relu=False, accumulate=ACC_STORE, split_k=1, precision=None) -> Gemm:
-    """Pure host logic (no CUDA call): used directly by the CPU tests."""
+    """Pure host logic (no CUDA call): used directly by the CPU tests.  A training step repeats the
+    same ~100 contractions with the same layouts: the filled struct is cached per (spec, layouts,
+    flags) and only the six data pointers are refreshed on a hit."""
+    prec = _precision if precision is None else precision
+    am_t = a_mul[1] if a_mul else None
+    ca_t = c_add[1] if c_add else None
+    cm_t = c_mul[1] if c_mul else None
+    key = (spec, _layout_key(A), _layout_key(B), _layout_key(out),
+           a_mul[0] if a_mul else None, _layout_key(am_t), c_add[0] if c_add else None, _layout_key(ca_t),
+           c_mul[0] if c_mul else None, _layout_key(cm_t), float(alpha), bool(relu), int(accumulate), int(split_k), prec)
+    hit = _desc_cache.get(key)
+    if hit is None:
+        g = _build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, prec)
+        if len(_desc_cache) < 4096:
+            _desc_cache[key] = bytes(g)
+        return g
+    g = Gemm.from_buffer_copy(hit)
+    g.A.ptr, g.B.ptr, g.C.ptr = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    if am_t is not None:
+        g.Amul.ptr = am_t.data_ptr()
+    if ca_t is not None:
+        g.Cadd.ptr = ca_t.data_ptr()
+    if cm_t is not None:
+        g.Cmul.ptr = cm_t.data_ptr()
+    return g
+
+
+def _build_descriptor(spec: str, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision) -> Gemm:
     pl = plan(spec)
     extra = [(pl.c, out)]
     for opt in (a_mul, c_add, c_mul):
@@ -162,7 +196,7 @@ def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, a
     g.Cmul = _operand(c_mul[1], c_mul[0], pl.batch, pl.m, pl.n, size) if c_mul else _operand(None, "", [], [], [], size)
     g.Cadd = _operand(c_add[1], c_add[0], pl.batch, pl.m, pl.n, size) if c_add else _operand(None, "", [], [], [], size)
     g.alpha, g.relu, g.accumulate, g.split_k = float(alpha), int(bool(relu)), int(accumulate), int(split_k)
-    g.precision = _precision if precision is None else precision
+    g.precision = precision
     return g
 
 
