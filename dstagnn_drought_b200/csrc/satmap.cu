@@ -19,8 +19,8 @@ constexpr int kSatQld = kSatTileI + 4;   // padded row of the transposed Qs tile
 
 template <int R>
 __global__ void __launch_bounds__(kSatThreads)
-sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, float* __restrict__ P,
-                       int N, int K, int dk, int ld, float scale) {
+sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, const float* __restrict__ tkT,
+                       float* __restrict__ P, float* __restrict__ TP, int N, int K, int dk, int ld, float scale) {
   static_assert(R % 8 == 0 && R <= 32, "strip height");
   constexpr int MR = R / 8;             // rows per thread: 8 row groups (one per warp) x 32 column quads
   extern __shared__ __align__(16) float sm[];
@@ -102,8 +102,13 @@ sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ b
       s += e;
     }
     const float inv = 1.f / warp_sum(s);
-    float* out = P + (((long long)b * K + k) * N + j) * ld;
-    for (int c = lane; c < ld; c += 32) out[c] = c < N ? row[c] * inv : 0.f;
+    const long long orow = (((long long)b * K + k) * N + j) * ld;
+    const float* trow = tkT + ((long long)k * N + j) * ld;
+    for (int c = lane; c < ld; c += 32) {
+      const float pv = c < N ? row[c] * inv : 0.f;
+      P[orow + c] = pv;
+      if (TP) TP[orow + c] = pv * __ldg(trow + c);
+    }
   }
 }
 
@@ -116,13 +121,16 @@ sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ b
 // CTA = 4 warps = 16 rows of one (b, k); the W_Q projection streams through shared memory in
 // transposed 128-column tiles.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mul4s(float4 a, float4 b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
 constexpr int kSatRowsCta = 16;
 constexpr int kSatRowThreads = 128;
 
 template <int NT>
 __global__ void __launch_bounds__(kSatRowThreads)
-sat_softmax_rows_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, float* __restrict__ P, int N,
-                        int K, int dk, int ld, float scale) {
+sat_softmax_rows_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, const float* __restrict__ tkT,
+                        float* __restrict__ P, float* __restrict__ TP, int N, int K, int dk, int ld, float scale) {
   extern __shared__ __align__(16) float sm[];
   float* KsT = sm;                               // [dk][16]
   float* QsT = sm + dk * kSatRowsCta;            // [dk][kSatQld]
@@ -206,23 +214,27 @@ sat_softmax_rows_kernel(const float* __restrict__ qk, const float* __restrict__ 
       sum += e;
     }
     const float inv = 1.f / warp_sum(sum);
-    float* out = P + (((long long)b * K + k) * N + j) * ld;
+    const long long orow = (((long long)b * K + k) * N + j) * ld;
+    const float* trow = tkT + ((long long)k * N + j) * ld;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int i = t * kSatTileI + 4 * lane;
-      if (i < ld)
-        *reinterpret_cast<float4*>(out + i) = make_float4(acc[r][4 * t] * inv, acc[r][4 * t + 1] * inv,
-                                                          acc[r][4 * t + 2] * inv, acc[r][4 * t + 3] * inv);
+      if (i < ld) {
+        const float4 pv = make_float4(acc[r][4 * t] * inv, acc[r][4 * t + 1] * inv, acc[r][4 * t + 2] * inv,
+                                      acc[r][4 * t + 3] * inv);
+        *reinterpret_cast<float4*>(P + orow + i) = pv;
+        if (TP) *reinterpret_cast<float4*>(TP + orow + i) = mul4s(pv, __ldg(reinterpret_cast<const float4*>(trow + i)));
+      }
     }
   }
 }
 
 template <int NT>
-static int launch_sat_rows(const float* qk, const float* biasT, float* P, int B, int N, int K, int dk, int ld,
-                           float scale, cudaStream_t stream) {
+static int launch_sat_rows(const float* qk, const float* biasT, const float* tkT, float* P, float* TP, int B, int N,
+                           int K, int dk, int ld, float scale, cudaStream_t stream) {
   const size_t smem = (size_t)dk * (kSatRowsCta + kSatQld) * sizeof(float);
   const dim3 grid((N + kSatRowsCta - 1) / kSatRowsCta, B * K);
-  sat_softmax_rows_kernel<NT><<<grid, kSatRowThreads, smem, stream>>>(qk, biasT, P, N, K, dk, ld, scale);
+  sat_softmax_rows_kernel<NT><<<grid, kSatRowThreads, smem, stream>>>(qk, biasT, tkT, P, TP, N, K, dk, ld, scale);
   DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd(rows)");
 }
 
@@ -230,9 +242,13 @@ static int launch_sat_rows(const float* qk, const float* biasT, float* P, int B,
 
 using namespace dstag;
 
-extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float* P, int32_t B, int32_t N, int32_t K,
+extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, const float* tkT, float* P, float* TP,
+                                     int32_t B, int32_t N, int32_t K,
                                      int32_t dk, int32_t ld, void* stream) {
   DSTAG_CHECK_ARG(qk && biasT && P, "dstag_sat_softmax_fwd: null pointer");
+  DSTAG_CHECK_ARG((TP == nullptr) || (tkT != nullptr && (reinterpret_cast<uintptr_t>(tkT) & 15) == 0 &&
+                                      (reinterpret_cast<uintptr_t>(TP) & 15) == 0),
+                  "dstag_sat_softmax_fwd: TP needs a 16-byte aligned tkT");
   DSTAG_CHECK_ARG(B > 0 && N > 0 && K > 0 && dk > 0 && ld >= N && (long long)B * K <= 65535,
                   "dstag_sat_softmax_fwd: bad sizes");
   DSTAG_CHECK_ARG(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(biasT) & 15) == 0,
@@ -244,14 +260,14 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float*
   if (rows_ok) {
     cudaStream_t st = (cudaStream_t)stream;
     switch (nt) {
-      case 1: return launch_sat_rows<1>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 2: return launch_sat_rows<2>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 3: return launch_sat_rows<3>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 4: return launch_sat_rows<4>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 5: return launch_sat_rows<5>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 6: return launch_sat_rows<6>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      case 7: return launch_sat_rows<7>(qk, biasT, P, B, N, K, dk, ld, scale, st);
-      default: return launch_sat_rows<8>(qk, biasT, P, B, N, K, dk, ld, scale, st);
+      case 1: return launch_sat_rows<1>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 2: return launch_sat_rows<2>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 3: return launch_sat_rows<3>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 4: return launch_sat_rows<4>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 5: return launch_sat_rows<5>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 6: return launch_sat_rows<6>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      case 7: return launch_sat_rows<7>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
+      default: return launch_sat_rows<8>(qk, biasT, tkT, P, TP, B, N, K, dk, ld, scale, st);
     }
   }
   const size_t fixed = (size_t)(dk * kSatQld) * sizeof(float);
@@ -267,7 +283,8 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float*
       return (int)e;                                                                                             \
     }                                                                                                            \
     const dim3 grid((N + R_ - 1) / R_, B * K);                                                                   \
-    sat_softmax_fwd_kernel<R_><<<grid, kSatThreads, smem, (cudaStream_t)stream>>>(qk, biasT, P, N, K, dk, ld, scale); \
+    sat_softmax_fwd_kernel<R_><<<grid, kSatThreads, smem, (cudaStream_t)stream>>>(qk, biasT, tkT, P, TP, N, K, dk, ld, \
+                                                                                  scale);                           \
     DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd");                                                                \
   } while (0)
   if (2 * need(32) <= budget + 24 * 1024) DSTAG_SAT_LAUNCH(32);   // two CTAs per SM preferred

@@ -233,24 +233,29 @@ class SpatialChebConv(torch.autograd.Function):
         FT = x3.shape[-1]
         Qs, Ks = qk[:, :, 0], qk[:, :, 1]                      # (B,N,K,dk) views
         P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
-        biasT = biasT.contiguous()
+        biasT, tkT = biasT.contiguous(), tkT.contiguous()
+        # TP = T_k (.) P is written by the same kernel: the two contractions that need the masked operator
+        # (forward, input gradient) then stream one N x N operand instead of two
+        TP = torch.empty_like(P)
         rc = -3 if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
-            qk.data_ptr(), biasT.data_ptr(), P.data_ptr(), B, N, K, dk, ld, _stream(P))
+            qk.data_ptr(), biasT.data_ptr(), tkT.data_ptr(), P.data_ptr(), TP.data_ptr(), B, N, K, dk, ld, _stream(P))
+        Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
         if rc == -3:      # DSTAG_ERR_SMEM: N too large for the fused row strip -> GEMM + row softmax
+            TP = None
             contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
                          c_add=("kji", biasT[..., :N]))
             _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+            contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd")
         else:
             _lib.check(rc, "dstag_sat_softmax_fwd")
-        Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
-        contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd")
-        ctx.save_for_backward(qk, P, tkT, x3)
+            contract_raw("bkji,bie->kbje", TP[..., :N], x3, out=Z, tag="cheb_fwd")
+        ctx.save_for_backward(qk, P, tkT, x3, TP)
         return Z
 
     @staticmethod
     def backward(ctx, dZ):
         lib = _lib.load()
-        qk, P, tkT, x3 = ctx.saved_tensors
+        qk, P, tkT, x3, TP = ctx.saved_tensors
         B, N, _, K, dk = qk.shape
         ld = P.shape[-1]
         dZ = dZ.contiguous()
@@ -258,7 +263,10 @@ class SpatialChebConv(torch.autograd.Function):
         Pv, Tv = P[..., :N], tkT[..., :N]
         dx = None
         if ctx.needs_input_grad[3]:
-            dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv), tag="cheb_bwd_dx")
+            if TP is not None:
+                dx = contract_raw("bkji,kbje->bie", TP[..., :N], dZ, tag="cheb_bwd_dx")
+            else:
+                dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv), tag="cheb_bwd_dx")
         dS = torch.empty_like(P)
         contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], c_mul=("kji", Tv), tag="cheb_bwd_dmap")
         _lib.check(lib.dstag_softmax_bwd(P.data_ptr(), dS.data_ptr(), B * K * N, N, ld, _stream(P)),

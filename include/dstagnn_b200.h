@@ -130,10 +130,13 @@ int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_
  * (SScaledDotProductAttention, model/DSTAGNN_my.py:19, and lines 126-127 of cheb_conv_withSAt):
  *   P[b,k,j,i] = softmax_i( Qs[b,i,k,:] . Ks[b,j,k,:] / sqrt(dk) + biasT[k,j,i] ),  pad columns = 0
  *   qk (B, N, 2, K, dk) packed [W_Q | W_K] projections; biasT (K, N, ld); P (B, K, N, ld); ld % 4 == 0.
+ * TP (nullable, same shape as P): second output TP = tkT (.) P with tkT (K, N, ld) the transposed
+ * Chebyshev polynomials -- the masked operator of line 128, so that the Chebyshev contraction and its
+ * input gradient read ONE operand stream instead of two.
  * Returns DSTAG_ERR_SMEM when a strip of 16 rows of N logits does not fit in shared memory (N > ~2900)
  * (then use dstag_gemm + dstag_softmax_fwd). */
-int dstag_sat_softmax_fwd(const float* qk, const float* biasT, float* P, int32_t B, int32_t N, int32_t K,
-                          int32_t dk, int32_t ld, void* stream);
+int dstag_sat_softmax_fwd(const float* qk, const float* biasT, const float* tkT, float* P, float* TP, int32_t B,
+                          int32_t N, int32_t K, int32_t dk, int32_t ld, void* stream);
 
 /* dx = dy * (y > 0)  (backward of the ReLUs at model/DSTAGNN_my.py:133,245-247). */
 int dstag_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 5
+        return 6
 
     def dstag_last_error(self):
         return self.err
@@ -155,7 +155,7 @@ class FakeLib:
         D[:, L:] = 0
         return 0
 
-    def dstag_sat_softmax_fwd(self, qk, biasT, P, B, N, K, dk, ld, stream):
+    def dstag_sat_softmax_fwd(self, qk, biasT, tkT, P, TP, B, N, K, dk, ld, stream):
         self.launches += 1
         q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk).astype(np.float64)
         s = np.einsum("bjkd,bikd->bkji", q[:, :, 1], q[:, :, 0]) / math.sqrt(dk)
@@ -164,6 +164,8 @@ class FakeLib:
         out = _arr(P, B * K * N * ld).reshape(B, K, N, ld)
         out[..., :N] = e / e.sum(-1, keepdims=True)
         out[..., N:] = 0
+        if TP:
+            _arr(TP, B * K * N * ld).reshape(B, K, N, ld)[:] = out * _arr(tkT, K * N * ld).reshape(1, K, N, ld)
         return 0
 
     def dstag_relu_bwd(self, y, dy, dx, n, stream):
