@@ -200,6 +200,35 @@ def _build_descriptor(spec: str, A, B, out, a_mul, c_add, c_mul, alpha, relu, ac
     return g
 
 
+def _fold_k_outer_into_batch(g: Gemm) -> bool:
+    """A reduction index (b, n) whose inner level is contiguous but of odd length (N = 883 nodes) cannot
+    be walked in aligned 32-wide k-blocks.  Such a problem equals a batch over the outer level whose
+    members all accumulate (atomically) into the same output: K' = d1, batch' = K / d1, C batch stride 0.
+    Restores the 16-byte operand load paths for the pre_conv weight gradient.  Rewrites g in place."""
+    if g.batch != 1 or g.relu or g.Cadd.ptr or g.Cmul.ptr or g.Amul.ptr:
+        return False
+    ka, kb = g.A.col, g.B.row
+    d1 = max(ka.d1, kb.d1)
+    if d1 < 64 or g.K % d1 or any(ax.d1 not in (1, d1) for ax in (ka, kb)):
+        return False
+    if not ((ka.d1 == d1 and ka.s1 == 1) or (kb.d1 == d1 and kb.s1 == 1)):
+        return False
+    q = g.K // d1
+    if q < 2:
+        return False
+
+    def levels(ax):
+        return (ax.s0, ax.s1) if ax.d1 == d1 else (ax.s0 * d1, ax.s0)
+
+    (oa, ia), (ob, ib) = levels(ka), levels(kb)
+    g.A.batch, g.A.col = Axis(oa, 0, 1, 0), Axis(ia, 0, 1, 0)
+    g.B.batch, g.B.row = Axis(ob, 0, 1, 0), Axis(ib, 0, 1, 0)
+    g.C.batch = Axis(0, 0, 1, 0)
+    g.batch, g.K = q, d1
+    g.accumulate, g.split_k = ACC_ATOMIC, 1
+    return True
+
+
 def auto_split_k(M: int, N: int, K: int, batch: int) -> int:
     """Split the reduction when the output grid cannot fill the 148 SMs (weight gradients:
     tiny M x N, K = batch * nodes * time)."""
@@ -267,6 +296,9 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             pass  # existing contents are kept; partial sums are added atomically
         accumulate = ACC_ATOMIC
     g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
+    if _fold_k_outer_into_batch(g):
+        if accumulate == ACC_STORE:        # (ACC_ATOMIC here means split-K already zeroed the output)
+            out.zero_()
     if _lib._prof is None:
         _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
     else:
