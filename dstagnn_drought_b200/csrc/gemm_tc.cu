@@ -1042,6 +1042,36 @@ static bool split_rows_to_batch(dstag_gemm_t& g) {
   return true;
 }
 
+// The same for a column index (b, n) of the output / second operand (the pre_conv input gradient writes
+// rows of N = 883 nodes per (b, f, t)): as a batch over b the output columns are one contiguous,
+// 16-byte aligned run, so the epilogue streams float4 rows instead of transposing scalar stores.
+static bool split_cols_to_batch(dstag_gemm_t& g) {
+  const int d1 = g.C.col.d1;
+  if (d1 < 128 || g.C.col.s1 != 1 || g.N % d1 != 0 || g.N == d1) return false;
+  const int q = g.N / d1;
+  if (g.batch > 1) return false;                       // keep it simple: only un-batched problems
+  dstag_operand_t* colops[] = {&g.C, &g.Cadd, &g.Cmul};
+  for (dstag_operand_t* o : colops) {
+    if (!o->ptr) continue;
+    if (o->col.d1 != d1 && o->col.d1 != 1) return false;
+  }
+  if (g.B.col.d1 != d1 && g.B.col.d1 != 1) return false;
+  auto split = [&](dstag_operand_t* o) {
+    const long long outer = o->col.d1 == d1 ? o->col.s0 : o->col.s0 * d1;
+    const long long inner = o->col.d1 == d1 ? o->col.s1 : o->col.s0;
+    o->batch.s0 = outer; o->batch.s1 = 0; o->batch.d1 = 1;
+    o->col.s0 = inner; o->col.s1 = 0; o->col.d1 = 1;
+  };
+  for (dstag_operand_t* o : colops)
+    if (o->ptr) split(o);
+  split(&g.B);
+  g.A.batch.s0 = 0; g.A.batch.s1 = 0; g.A.batch.d1 = 1;
+  if (g.Amul.ptr) { g.Amul.batch.s0 = 0; g.Amul.batch.s1 = 0; g.Amul.batch.d1 = 1; }
+  g.batch = q;
+  g.N = d1;
+  return true;
+}
+
 static int g_num_sms = 0;
 
 template <int BN, bool X3, bool AMUL>
@@ -1070,7 +1100,7 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   }
   TcParams p;
   p.g = *g_in;
-  split_rows_to_batch(p.g);
+  if (!split_rows_to_batch(p.g)) split_cols_to_batch(p.g);
   const dstag_gemm_t* g = &p.g;
   const int bn = g->N > 64 ? 128 : (g->N > 32 ? 64 : 32);
   p.ntm = (g->M + TC_BM - 1) / TC_BM;
