@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -53,7 +53,7 @@ SIGNATURES = {
     "dstag_colsum": (C.c_int, [_F, _F, _i64, _i64, _i64, _F]),
     "dstag_transpose": (C.c_int, [_F, _i64, _F, _i64, _i32, _i32, _i32, _F]),
     "dstag_softmax_fwd": (C.c_int, [_F, _i64, _i32, _i32, _F]),
-    "dstag_softmax_bwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _F]),
+    "dstag_softmax_bwd": (C.c_int, [_F, _F, _F, _i64, _i64, _i32, _i32, _F]),
     "dstag_relu_bwd": (C.c_int, [_F, _F, _F, _i64, _F]),
     "dstag_sat_softmax_fwd": (C.c_int, [_F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_tattn_fwd": (C.c_int, [_F, _F, _i32, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),

@@ -222,7 +222,8 @@ softmax_fwd_kernel(float* __restrict__ x, long long rows, int L, int ld) {
 }
 
 __global__ void __launch_bounds__(kRowThreads)
-softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int L, int ld) {
+softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, const float* __restrict__ mul,
+                   long long mul_rows, long long rows, int L, int ld) {
   extern __shared__ float sm[];
   float* pr = sm;
   float* dr = sm + L;
@@ -230,9 +231,12 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long lon
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* pp = p + r * ld;
     float* dpp = dp + r * ld;
+    const float* mp = mul ? mul + (r % mul_rows) * ld : nullptr;
     float s = 0.f;
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
-      const float a = __ldg(pp + c), b = dpp[c];
+      const float a = __ldg(pp + c);
+      float b = dpp[c];
+      if (mp) b *= __ldg(mp + c);
       pr[c] = a;
       dr[c] = b;
       s = fmaf(a, b, s);
@@ -416,26 +420,49 @@ ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* _
   }
 }
 
+// dp <- p (.) (g - sum(p (.) g)), g = dp (.) mul: warp per row, NV float4 per lane (ld <= 128 NV, ld % 4 == 0,
+// 16-byte aligned rows; columns [L, ld) of p are zero, so they drop out of the sum and are written as zero)
+template <int NV>
 __global__ void __launch_bounds__(256)
-softmax_bwd_warp_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int L, int ld) {
+softmax_bwd_warp_kernel(const float* __restrict__ p, float* __restrict__ dp, const float* __restrict__ mul,
+                        long long mul_rows, long long rows, int L, int ld) {
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
-    const float* pp = p + r * ld;
-    float* dpp = dp + r * ld;
-    float pv[kWR], dv[kWR];
+    const float4* pp = reinterpret_cast<const float4*>(p + r * ld);
+    float4* dpp = reinterpret_cast<float4*>(dp + r * ld);
+    const float4* mp = mul ? reinterpret_cast<const float4*>(mul + (r % mul_rows) * ld) : nullptr;
+    float4 pv[NV], dv[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      pv[i] = 0.f; dv[i] = 0.f;
-      if (c < L) { pv[i] = __ldg(pp + c); dv[i] = dpp[c]; s = fmaf(pv[i], dv[i], s); }
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[i] = pv[i];
+      if (4 * c4 < ld) {
+        pv[i] = __ldg(pp + c4);
+        dv[i] = dpp[c4];
+        if (mp) {
+          const float4 m = __ldg(mp + c4);
+          dv[i].x *= m.x; dv[i].y *= m.y; dv[i].z *= m.z; dv[i].w *= m.w;
+        }
+        const int c = 4 * c4;
+        if (c + 3 >= L) {                         // ragged end: the padding of dp may hold anything
+          if (c >= L) dv[i].x = 0.f;
+          if (c + 1 >= L) dv[i].y = 0.f;
+          if (c + 2 >= L) dv[i].z = 0.f;
+          dv[i].w = 0.f;
+        }
+        s = fmaf(pv[i].x, dv[i].x, fmaf(pv[i].y, dv[i].y, fmaf(pv[i].z, dv[i].z, fmaf(pv[i].w, dv[i].w, s))));
+      }
     }
     s = warp_sum(s);
 #pragma unroll
-    for (int i = 0; i < kWR; ++i) {
-      const int c = lane + 32 * i;
-      if (c < ld) dpp[c] = c < L ? pv[i] * (dv[i] - s) : 0.f;
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (4 * c4 < ld)
+        dpp[c4] = make_float4(pv[i].x * (dv[i].x - s), pv[i].y * (dv[i].y - s), pv[i].z * (dv[i].z - s),
+                              pv[i].w * (dv[i].w - s));
     }
   }
 }
@@ -594,19 +621,31 @@ int dstag_softmax_fwd(float* x, int64_t rows, int32_t L, int32_t ld, void* strea
   DSTAG_RETURN_LAUNCH("dstag_softmax_fwd");
 }
 
-int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_t ld, void* stream) {
-  DSTAG_CHECK_ARG(p && dp && rows > 0 && L > 0 && ld >= L, "dstag_softmax_bwd: bad arguments");
-  if (ld <= 32 * kWR) {
+int dstag_softmax_bwd(const float* p, float* dp, const float* mul, int64_t mul_rows, int64_t rows, int32_t L,
+                      int32_t ld, void* stream) {
+  DSTAG_CHECK_ARG(p && dp && rows > 0 && L > 0 && ld >= L && (mul == nullptr || mul_rows > 0),
+                  "dstag_softmax_bwd: bad arguments");
+  const int nv = (ld + 127) / 128;
+  const bool al = ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(dp) |
+                                   reinterpret_cast<uintptr_t>(mul)) & 15) == 0;
+  if (al && nv <= 8) {
     const long long blocks = (rows + 7) / 8;
     const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
-    softmax_bwd_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, dp, rows, L, ld);
+#define DSTAG_SMB(NV_)                                                                                               \
+  case NV_:                                                                                                          \
+    softmax_bwd_warp_kernel<NV_><<<grid, 256, 0, (cudaStream_t)stream>>>(p, dp, mul, mul_rows, rows, L, ld);         \
+    break
+    switch (nv) {
+      DSTAG_SMB(1); DSTAG_SMB(2); DSTAG_SMB(3); DSTAG_SMB(4); DSTAG_SMB(5); DSTAG_SMB(6); DSTAG_SMB(7); DSTAG_SMB(8);
+    }
+#undef DSTAG_SMB
     DSTAG_RETURN_LAUNCH("dstag_softmax_bwd(warp)");
   }
   const size_t smem = (size_t)(2 * L + 40) * sizeof(float);
   int rc = ensure_smem((const void*)softmax_bwd_kernel, smem, "dstag_softmax_bwd");
   if (rc) return rc;
   const int grid = (int)(rows < kNumSMs * 8 ? rows : kNumSMs * 8);
-  softmax_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(p, dp, rows, L, ld);
+  softmax_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(p, dp, mul, mul_rows, rows, L, ld);
   DSTAG_RETURN_LAUNCH("dstag_softmax_bwd");
 }
 

@@ -268,9 +268,10 @@ class SpatialChebConv(torch.autograd.Function):
             else:
                 dx = contract_raw("bkji,kbje->bie", Pv, dZ, a_mul=("kji", Tv), tag="cheb_bwd_dx")
         dS = torch.empty_like(P)
-        contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], c_mul=("kji", Tv), tag="cheb_bwd_dmap")
-        _lib.check(lib.dstag_softmax_bwd(P.data_ptr(), dS.data_ptr(), B * K * N, N, ld, _stream(P)),
-                   "dstag_softmax_bwd")
+        # dP = T_k (.) (dZ X^T): the Hadamard factor is applied while the softmax backward reads the product
+        contract_raw("kbje,bie->bkji", dZ, x3, out=dS[..., :N], tag="cheb_bwd_dmap")
+        _lib.check(lib.dstag_softmax_bwd(P.data_ptr(), dS.data_ptr(), tkT.data_ptr(), K * N, B * K * N, N, ld,
+                                         _stream(P)), "dstag_softmax_bwd")
         dSv = dS[..., :N]
         dqk = torch.empty_like(qk)
         alpha = 1.0 / math.sqrt(dk)

@@ -123,8 +123,12 @@ int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, 
  * [L, ld) are set to 0.  F.softmax(..., dim=1) of model/DSTAGNN_my.py:127 on the
  * transposed map layout (row = output node j, column = i). */
 int dstag_softmax_fwd(float* x, int64_t rows, int32_t L, int32_t ld, void* stream);
-/* In place on dp: dp <- p * (dp - sum(p * dp)). */
-int dstag_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t L, int32_t ld, void* stream);
+/* In place on dp: g = dp (.) mul ; dp <- p * (g - sum(p * g)).  mul (nullable): mul_rows rows of
+ * leading dimension ld, row r uses mul[r % mul_rows] -- the transposed Chebyshev polynomial T_k that
+ * follows the softmax in model/DSTAGNN_my.py:128, so the contraction that produces dp needs no
+ * multiplier epilogue. */
+int dstag_softmax_bwd(const float* p, float* dp, const float* mul, int64_t mul_rows, int64_t rows, int32_t L,
+                      int32_t ld, void* stream);
 
 /* Spatial attention maps, forward, fused: logits + bias + softmax in one kernel
  * (SScaledDotProductAttention, model/DSTAGNN_my.py:19, and lines 126-127 of cheb_conv_withSAt):

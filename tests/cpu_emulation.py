@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 6
+        return 7
 
     def dstag_last_error(self):
         return self.err
@@ -146,11 +146,13 @@ class FakeLib:
         m[:, L:] = 0
         return 0
 
-    def dstag_softmax_bwd(self, p, dp, rows, L, ld, stream):
+    def dstag_softmax_bwd(self, p, dp, mul, mul_rows, rows, L, ld, stream):
         self.launches += 1
         P = _arr(p, rows * ld).reshape(rows, ld)[:, :L].astype(np.float64)
         D = _arr(dp, rows * ld).reshape(rows, ld)
         d = D[:, :L].astype(np.float64)
+        if mul:
+            d = d * _arr(mul, mul_rows * ld).reshape(mul_rows, ld)[np.arange(rows) % mul_rows, :L]
         D[:, :L] = P * (d - (P * d).sum(1, keepdims=True))
         D[:, L:] = 0
         return 0
