@@ -324,7 +324,7 @@ struct Producer {
       int kbytes = 4 * (K - k);
       kbytes = kbytes < 0 ? 0 : (kbytes > 16 ? 16 : kbytes);
       const uint32_t d0 = pbase + swz(t >> 3, c);
-      const float* kp = bp + k;
+      const float* kp = bp + (cax.d1 == 1 ? k : (k < K ? axoff32(cax, k) : 0));   // two-level K: runs of d1 % 4 == 0
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         const bool ok = rows[i] >= 0 && kbytes > 0;
@@ -943,11 +943,16 @@ static bool aligned16(const dstag_operand_t& o) {
 static int pick_mode(const dstag_operand_t& o, const dstag_axis_t& kax, const dstag_axis_t& rowax,
                      const dstag_operand_t* m, const dstag_axis_t* mkax, const dstag_axis_t* mrowax) {
   const bool has_m = m && m->ptr;
-  auto kvec = [](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
-    return k.d1 == 1 && k.s0 == 1 && axis_mult4(r) && aligned16(x);
+  // "contiguous in aligned runs": single-level stride 1, or two-level with a contiguous inner level whose
+  // length is a multiple of 4 (16-byte chunks never straddle a run), e.g. K = (k, f) with f innermost
+  auto runs4 = [](const dstag_axis_t& a) {
+    return a.d1 == 1 ? a.s0 == 1 : (a.s1 == 1 && a.d1 % 4 == 0 && a.s0 % 4 == 0);
   };
-  auto mvec = [](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
-    return r.d1 == 1 && r.s0 == 1 && axis_mult4(k) && aligned16(x);
+  auto kvec = [&](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
+    return runs4(k) && axis_mult4(r) && aligned16(x);
+  };
+  auto mvec = [&](const dstag_operand_t& x, const dstag_axis_t& k, const dstag_axis_t& r) {
+    return runs4(r) && axis_mult4(k) && aligned16(x);
   };
   if (kvec(o, kax, rowax) && (!has_m || kvec(*m, *mkax, *mrowax))) return MODE_KVEC;
   if (mvec(o, kax, rowax) && (!has_m || mvec(*m, *mkax, *mrowax))) return MODE_MVEC;

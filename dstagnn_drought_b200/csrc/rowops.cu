@@ -175,7 +175,10 @@ colsum_kernel(const float* __restrict__ in, float* __restrict__ out, long long r
 // ======================================================================================
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, long long in_ld, float* __restrict__ out, long long out_ld, int R,
-                 int C) {
+                 int C, int r_d, int c_d) {
+  // out[b, pc(c), pr(r)] = in[b, r, c] with p(i) = (i % d) * (n / d) + i / d  (d = 1: identity): the index
+  // pair (t, f) <-> (f, t) swap between the channels-last block layout and the (b, f, t) row order of
+  // the temporal attention is folded into the transpose
   __shared__ float tile[32][33];
   const long long ibase = (long long)blockIdx.z * R * in_ld, obase = (long long)blockIdx.z * C * out_ld;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -189,7 +192,11 @@ transpose_kernel(const float* __restrict__ in, long long in_ld, float* __restric
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int c = c0 + ty + j, r = r0 + tx;
-    if (r < R && c < C) out[obase + (long long)c * out_ld + r] = tile[tx][ty + j];
+    if (r < R && c < C) {
+      const int pc = c_d > 1 ? (c % c_d) * (C / c_d) + c / c_d : c;
+      const int pr = r_d > 1 ? (r % r_d) * (R / r_d) + r / r_d : r;
+      out[obase + (long long)pc * out_ld + pr] = tile[tx][ty + j];
+    }
   }
 }
 
@@ -602,12 +609,13 @@ int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_
 }
 
 int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, int32_t batch, int32_t R, int32_t C,
-                    void* stream) {
+                    int32_t r_d, int32_t c_d, void* stream) {
   DSTAG_CHECK_ARG(in && out && batch > 0 && R > 0 && C > 0 && in_ld >= C && out_ld >= R,
                   "dstag_transpose: bad arguments");
+  DSTAG_CHECK_ARG(r_d >= 1 && c_d >= 1 && R % r_d == 0 && C % c_d == 0, "dstag_transpose: bad permutation factors");
   DSTAG_CHECK_ARG(batch <= 65535 && (R + 31) / 32 <= 65535, "dstag_transpose: grid too large");
   const dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
-  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, R, C);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, R, C, r_d, c_d);
   DSTAG_RETURN_LAUNCH("dstag_transpose");
 }
 

@@ -172,8 +172,14 @@ class DSTAGNN_block(nn.Module):
                                f"model/DSTAGNN_my.py:247-252 needs 1 or {self.C} input features")
         C, K, D, dk = self.C, self.K, self.d_model, self.d_k
         train = self.training
-        x = x.contiguous().float()
-        x3 = x.view(B, N, Fin * T)
+        # Activations are kept CHANNELS-LAST (B, N, T, F) inside and between blocks; the reference's
+        # (B, N, F, T) tensor is the permuted view of that buffer.  A block output of this package arrives
+        # as such a view (no copy); any other input is converted once.
+        x = x.float()
+        xcl = x.permute(0, 1, 3, 2)
+        if not xcl.is_contiguous():
+            xcl = xcl.contiguous()
+        x3 = xcl.view(B, N, T * Fin)                                                   # e = (t, f)
         if isinstance(res_att, (int, float)):
             if res_att != 0:
                 raise RuntimeError("res_att must be 0 or a tensor")
@@ -184,7 +190,7 @@ class DSTAGNN_block(nn.Module):
             e2d = ops.LayerNormAdd.apply(x3, self.EmbedT.pos_embed.weight, self.EmbedT.norm.weight,
                                          self.EmbedT.norm.bias, True, 0.0, 0)             # (B*T, N)
         else:
-            e2d = ops.Transpose.apply(x3).view(B * Fin * T, N)
+            e2d = ops.Transpose.apply(x3, Fin).view(B * Fin * T, N)                      # rows (b, f, t)
         # 2. temporal attention                                                      (line 231)
         o2d, logits = self.TAt(e2d, res_att, B, Fin, T)
         # 3. pre_conv: per-node Linear over (t, f)                                   (line 232)
@@ -197,13 +203,13 @@ class DSTAGNN_block(nn.Module):
         # 5+6. spatial attention maps and the Chebyshev contraction                  (lines 235-236)
         w_sat = torch.cat([self.SAt.W_Q.weight, self.SAt.W_K.weight], dim=0)           # (2*K*dk, D)
         qk = contract("rd,od->ro", se, w_sat).view(B, N, 2, K, dk)
-        zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)             # (K, B, N, F*T)
+        zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)             # (K, B, N, (t,f))
         theta = torch.stack(list(self.cheb_conv_SAt.Theta))                             # (K, F, C)
-        g = contract("kxft,kfc->xtc", zc.view(K, B * N, Fin, T), theta, relu=True)      # (B*N, T, C) channels-last
+        g = contract("kxtf,kfc->xtc", zc.view(K, B * N, T, Fin), theta, relu=True)      # (B*N, T, C)
         # 7. gated temporal convolutions                                             (lines 237-242)
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
                                  self.gtu5.con2out.weight, self.gtu5.con2out.bias,
-                                 self.gtu7.con2out.weight, self.gtu7.con2out.bias)       # (B*N, C, 3T-12)
+                                 self.gtu7.con2out.weight, self.gtu7.con2out.bias)       # (B*N, 3T-12, C)
         # 8-11. fcmy over the concatenated time axis, combine, residual, LayerNorm over channels
         #       (lines 243-252); one fused kernel for the PEMS shapes, GEMM + tail kernel otherwise
         lin = self.fcmy[0]
@@ -211,17 +217,18 @@ class DSTAGNN_block(nn.Module):
         seed = ops.next_seed() if train else 0
         if Fin == 1:
             w_res = self.residual_conv.weight.view(C, Fin)
-            r = contract("xft,cf->xct", x.view(B * N, Fin, T), w_res, c_add=("c", self.residual_conv.bias))
+            r = contract("xtf,cf->xtc", xcl.view(B * N, T, Fin), w_res, c_add=("c", self.residual_conv.bias))
             g_res = None
         else:
-            r = x.view(B * N, C, T)
+            r = xcl.view(B * N, T, C)
             g_res = g
         if ops.FusedTail.supported(C, T):
             out = ops.FusedTail.apply(cat, lin.weight, lin.bias, g_res, r, self.ln.weight, self.ln.bias, p_fc, seed)
         else:
-            tc = contract("rs,ts->rt", cat.view(B * N * C, 3 * T - 12), lin.weight, c_add=("t", lin.bias))
-            out = ops.BlockTail.apply(tc.view(B * N, C, T), g_res, r, self.ln.weight, self.ln.bias, p_fc, seed)
-        return out.view(B, N, C, T), logits
+            tc = contract("xsc,ts->xtc", cat, lin.weight, c_add=("t", lin.bias))
+            out = ops.BlockTail.apply(tc, g_res, r, self.ln.weight, self.ln.bias, p_fc, seed)
+        # (B, N, T, C) buffer handed back in the reference's (B, N, C, T) index order
+        return out.view(B, N, T, C).permute(0, 1, 3, 2), logits
 
 
 class DSTAGNN_submodule(nn.Module):
@@ -255,7 +262,7 @@ class DSTAGNN_submodule(nn.Module):
             # final_conv is a per-node Linear over (t_cat, c); summing one slice per block
             # avoids materialising the concatenation of line 277.
             w_i = self.final_conv.weight[:, i * T:(i + 1) * T, 0, :]                    # (128, T, C) view
-            part = contract("xct,otc->xo", x.view(B * N, C, T), w_i,
+            part = contract("xtc,otc->xo", x.permute(0, 1, 3, 2).reshape(B * N, T, C), w_i,
                             c_add=("o", self.final_conv.bias) if i == 0 else None)
             h = part if h is None else h + part
         y = contract("xo,po->xp", h, self.final_fc.weight, c_add=("p", self.final_fc.bias))

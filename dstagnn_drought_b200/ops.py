@@ -46,9 +46,10 @@ def next_seed() -> int:
 # ----------------------------------------------------------------------------------------
 # transpose
 # ----------------------------------------------------------------------------------------
-def transpose_raw(x3: torch.Tensor, pad_rows: bool = False) -> torch.Tensor:
+def transpose_raw(x3: torch.Tensor, pad_rows: bool = False, r_d: int = 1, c_d: int = 1) -> torch.Tensor:
     """(b, R, C) -> (b, C, R).  The input may be row padded; with ``pad_rows`` the output rows are
-    padded to 16 bytes (a ``[..., :R]`` view)."""
+    padded to 16 bytes (a ``[..., :R]`` view).  ``c_d`` / ``r_d`` additionally swap an index pair inside
+    the column / row index of the INPUT: index i = (hi, lo) with lo of size d lands at (lo, hi)."""
     lib = _lib.load()
     _check(x3, "transpose input")
     assert x3.dim() == 3
@@ -56,21 +57,25 @@ def transpose_raw(x3: torch.Tensor, pad_rows: bool = False) -> torch.Tensor:
     b, R, Cc = x3.shape
     out = empty_rows((b, Cc, R), x3.device) if pad_rows else torch.empty((b, Cc, R), device=x3.device,
                                                                          dtype=torch.float32)
-    _lib.check(lib.dstag_transpose(x3.data_ptr(), x3.stride(1), out.data_ptr(), out.stride(1), b, R, Cc,
+    _lib.check(lib.dstag_transpose(x3.data_ptr(), x3.stride(1), out.data_ptr(), out.stride(1), b, R, Cc, r_d, c_d,
                                    _stream(x3)), "dstag_transpose")
     return out
 
 
 class Transpose(torch.autograd.Function):
-    """x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 materialised ((B,N,FT) -> (B,FT,N))."""
+    """x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 materialised from the channels-last block layout:
+    (B, N, (t,f)) -> (B, (f,t), N) rows for the temporal attention (row-padded)."""
 
     @staticmethod
-    def forward(ctx, x3):
-        return transpose_raw(x3, pad_rows=True)
+    def forward(ctx, x3, F):
+        ctx.F = F
+        return transpose_raw(x3, pad_rows=True, c_d=F)
 
     @staticmethod
     def backward(ctx, dy):
-        return transpose_raw(dy)
+        # dy (B, (f,t), N) -> (B, N, (t,f)): swap the pair back in the row index of the input
+        FT = dy.shape[1]
+        return transpose_raw(dy, r_d=FT // ctx.F), None
 
 
 # ----------------------------------------------------------------------------------------
@@ -288,7 +293,7 @@ class SpatialChebConv(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------
 class GtuStack(torch.autograd.Function):
     """gtu3/gtu5/gtu7 + torch.cat (lines 192-197, 238-242).
-    g: (X, T, C) CHANNELS-LAST graph-conv output -> (X, C, 3T-12) (time innermost, fcmy's layout).
+    g: (X, T, C) CHANNELS-LAST graph-conv output -> cat (X, 3T-12, C), channels-last as well.
 
     With channels last, the window of ks time steps that a Conv2d(C->2C, (1,ks)) output reads is
     ks*C *contiguous* floats, so the convolution is a plain K-contiguous contraction over an
@@ -312,7 +317,7 @@ class GtuStack(torch.autograd.Function):
         X, T, Cc = g.shape
         widths = [T - ks + 1 for ks in GtuStack.KS]
         total = sum(widths)
-        out = torch.empty((X, Cc, total), device=g.device, dtype=torch.float32)
+        out = torch.empty((X, total, Cc), device=g.device, dtype=torch.float32)
         us, off = [], 0
         for ks, w, b, tp in zip(GtuStack.KS, (w3, w5, w7), (b3, b5, b7), widths):
             wk = w[:, :, 0, :].permute(0, 2, 1).reshape(2 * Cc, ks * Cc).contiguous()      # (o, (d, c))
@@ -330,7 +335,7 @@ class GtuStack(torch.autograd.Function):
         g, w3, w5, w7, u3, u5, u7 = ctx.saved_tensors
         X, T, Cc = g.shape
         dout = dout.contiguous()
-        total = dout.shape[-1]
+        total = dout.shape[1]
         dg = torch.empty_like(g) if ctx.needs_input_grad[0] else None
         grads, off, first = [], 0, True
         for ks, w, u in zip(GtuStack.KS, (w3, w5, w7), (u3, u5, u7)):
@@ -358,8 +363,7 @@ class GtuStack(torch.autograd.Function):
 # block tail
 # ----------------------------------------------------------------------------------------
 class BlockTail(torch.autograd.Function):
-    """out = LN_C(relu(r + relu(dropout(tc) [+ g])))  (lines 243-252).
-    tc, r, out: (X, C, T);  g (and its gradient): (X, T, C) channels-last."""
+    """out = LN_C(relu(r + relu(dropout(tc) [+ g])))  (lines 243-252).  All (X, T, C) channels-last."""
 
     @staticmethod
     def forward(ctx, tc, g, r, gamma, beta, drop_p, seed):
@@ -369,7 +373,7 @@ class BlockTail(torch.autograd.Function):
         tc, r = tc.contiguous(), r.contiguous()
         if g is not None:
             g = g.contiguous()
-        X, Cc, T = tc.shape
+        X, T, Cc = tc.shape
         out = torch.empty_like(tc)
         mean = torch.empty((X, T), device=tc.device, dtype=torch.float32)
         rstd = torch.empty((X, T), device=tc.device, dtype=torch.float32)
@@ -385,7 +389,7 @@ class BlockTail(torch.autograd.Function):
         lib = _lib.load()
         tc, g, r, gamma, mean, rstd = ctx.saved_tensors
         drop_p, seed = ctx.meta
-        X, Cc, T = tc.shape
+        X, T, Cc = tc.shape
         dout = dout.contiguous()
         dtc = torch.empty_like(tc)
         dr = torch.empty_like(tc)
@@ -401,9 +405,9 @@ class BlockTail(torch.autograd.Function):
 
 class FusedTail(torch.autograd.Function):
     """fcmy + BlockTail in one kernel for C = 32, T = 12 (lines 243-252): the Linear over the
-    concatenated GTU time axis is evaluated per (node, channel) row in registers, so tc / dtc never make
+    concatenated GTU time axis is evaluated per (node, channel) in registers, so tc never makes
     an HBM round trip in the forward, and the backward emits dcat directly.
-    cat (X, C, S); wf (T, S); bf (T); g (X, T, C) or None; r (X, C, T) -> out (X, C, T)."""
+    cat (X, S, C); wf (T, S); bf (T); g (X, T, C) or None; r (X, T, C) -> out (X, T, C)."""
 
     @staticmethod
     def supported(C_, T_):
@@ -417,7 +421,7 @@ class FusedTail(torch.autograd.Function):
         cat, wf, bf, r = cat.contiguous(), wf.contiguous(), bf.contiguous(), r.contiguous()
         if g is not None:
             g = g.contiguous()
-        X, Cc, T = r.shape
+        X, T, Cc = r.shape
         out = torch.empty_like(r)
         mean = torch.empty((X, T), device=r.device, dtype=torch.float32)
         rstd = torch.empty((X, T), device=r.device, dtype=torch.float32)
@@ -434,8 +438,8 @@ class FusedTail(torch.autograd.Function):
         lib = _lib.load()
         cat, wf, bf, g, r, gamma, mean, rstd = ctx.saved_tensors
         drop_p, seed = ctx.meta
-        X, Cc, T = r.shape
-        S = cat.shape[-1]
+        X, T, Cc = r.shape
+        S = cat.shape[1]
         dout = dout.contiguous()
         dcat = torch.empty_like(cat)
         dtc = torch.empty_like(r)
@@ -448,12 +452,22 @@ class FusedTail(torch.autograd.Function):
                                             dcat.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
                                             dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
                                             _stream(r)), "dstag_tail_fused_bwd")
-        if lib.dstag_outer_sum_supported(T, S):
-            # T x S outputs reduced over B*N*C rows: a streaming reduction, not a tensor-core shape
-            dwf = torch.zeros((T, S), device=r.device, dtype=torch.float32)
-            _lib.check(lib.dstag_outer_sum(dtc.data_ptr(), cat.data_ptr(), dwf.data_ptr(), X * Cc, T, S,
-                                           _stream(r)), "dstag_outer_sum")
-        else:
-            dwf = contract_raw("rt,rs->ts", dtc.view(X * Cc, T), cat.view(X * Cc, S), tag="fcmy_dw")
-        dbf = colsum(dtc, X * Cc, T)
+        dwf, dbf = fcmy_param_grads(dtc, cat)
         return dcat, dwf, dbf, dg, dr, dgamma, dbeta, None, None
+
+
+def fcmy_param_grads(dtc: torch.Tensor, cat: torch.Tensor):
+    """dW[t,s] = sum_{x,c} dtc[x,t,c] cat[x,s,c], db[t] = sum_{x,c} dtc[x,t,c] (channels-last operands):
+    T x S outputs reduced over B*N*C -- a streaming reduction kernel when the shape allows it."""
+    lib = _lib.load()
+    X, T, Cc = dtc.shape
+    S = cat.shape[1]
+    if lib.dstag_outer_sum_supported(T, S, Cc):
+        dwf = torch.zeros((T, S), device=dtc.device, dtype=torch.float32)
+        dbf = torch.zeros(T, device=dtc.device, dtype=torch.float32)
+        _lib.check(lib.dstag_outer_sum(dtc.data_ptr(), cat.data_ptr(), dwf.data_ptr(), dbf.data_ptr(), X, T, S, Cc,
+                                       _stream(dtc)), "dstag_outer_sum")
+        return dwf, dbf
+    dwf = contract_raw("xtc,xsc->ts", dtc, cat, tag="fcmy_dw")
+    dbf = colsum(dtc, X, T * Cc).view(T, Cc).sum(1)
+    return dwf, dbf

@@ -114,10 +114,13 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
  * zeroed by the caller (partial sums are combined with atomicAdd). */
 int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);
 
-/* out[(b * C + c) * out_ld + r] = in[(b * R + r) * in_ld + c]  (x.permute(0,2,3,1) of
- * model/DSTAGNN_my.py:230 made contiguous, and the transposes of the N x N mask / Chebyshev matrices). */
+/* out[(b * C + pc(c)) * out_ld + pr(r)] = in[(b * R + r) * in_ld + c], p(i) = (i % d) * (n / d) + i / d
+ * with d = r_d (n = R) for rows and d = c_d (n = C) for columns; d = 1 is the identity.
+ * x.permute(0,2,3,1) of model/DSTAGNN_my.py:230 made contiguous: the block keeps its activations
+ * channels-last (B, N, T, F), the temporal attention wants rows (b, f, t) -- c_d = F swaps the pair while
+ * transposing (and r_d = T swaps it back in the backward). */
 int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, int32_t batch, int32_t R, int32_t C,
-                    void* stream);
+                    int32_t r_d, int32_t c_d, void* stream);
 
 /* In-place row softmax over L entries of rows with leading dimension ld; entries
  * [L, ld) are set to 0.  F.softmax(..., dim=1) of model/DSTAGNN_my.py:127 on the
@@ -163,57 +166,54 @@ int dstag_tattn_bwd(const float* qkv, const float* scores, const float* dctx,
                     int32_t H, int32_t T, int32_t dk, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * GTU gate (model/DSTAGNN_my.py:194-196) on the CHANNELS-LAST conv output u (X, Tp, 2C):
- *   out[x, c, off + t] = tanh(u[x, t, c]) * sigmoid(u[x, t, C + c])
- * out rows have leading dimension out_ld (the concatenated time axis 3T-12 of line 242).
+ * Block tail.  ALL tensors are channels-last (X = B*N, time, C): the graph-conv output g, the GTU conv
+ * outputs u, the concatenated gate outputs cat (X, S = 3T-12, C), the residual r, the block output
+ * and their gradients.  (The block hands its output back as a permuted (B, N, C, T) view.)
+ *
+ * GTU gate (model/DSTAGNN_my.py:194-196) + torch.cat (line 242):
+ *   out[x, off + t, c] = tanh(u[x, t, c]) * sigmoid(u[x, t, C + c]),  u (X, Tp, 2C), out (X, S, C).
  * The temporal convolutions themselves run through dstag_gemm on an overlapping strided view
  * of the channels-last activation (K = ks*C contiguous), see ops.GtuStack.
  * ---------------------------------------------------------------------------------- */
-int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t Tp, int32_t out_ld,
-                       int32_t out_off, void* stream);
+int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t Tp, int32_t S, int32_t off,
+                       void* stream);
 /* dup (X, Tp + 2*pad, 2C): gradient w.r.t. u, written with `pad` zero rows before and after the
  * Tp valid time steps, so that the conv input gradient is a gather-only correlation over an
  * unfolded view of dup (no atomics).  db (2C, nullable, zeroed by the caller): the conv bias
  * gradient (column sums of dup) is ACCUMULATED into it. */
 int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C,
-                       int32_t Tp, int32_t pad, int32_t out_ld, int32_t out_off, void* stream);
+                       int32_t Tp, int32_t pad, int32_t S, int32_t off, void* stream);
 
-/* out[m, n] += sum_r a[r, m] * b[r, n]  (a: rows x m, b: rows x n, row-major, b 16-byte aligned;
- * out zeroed by the caller).  The fcmy weight gradient (autograd of model/DSTAGNN_my.py:243):
- * a T x (3T-12) result reduced over B*N*C rows -- a streaming reduction, not a tensor-core shape.
- * Supported when n % 4 == 0 and m * n / 4 <= 256 (dstag_outer_sum_supported). */
-int dstag_outer_sum_supported(int32_t m, int32_t n);
-int dstag_outer_sum(const float* a, const float* b, float* out, int64_t rows, int32_t m, int32_t n, void* stream);
+/* out[m, n] += sum_x sum_c a[x, m, c] * b[x, n, c];  asum[m] += sum_x sum_c a[x, m, c] (nullable).
+ * a (X, m, C), b (X, n, C) channels-last, 16-byte aligned; out / asum zeroed by the caller.
+ * The fcmy weight and bias gradients (autograd of model/DSTAGNN_my.py:243): a T x (3T-12) result
+ * reduced over B*N*C -- a streaming reduction, not a tensor-core shape. */
+int dstag_outer_sum_supported(int32_t m, int32_t n, int32_t C);
+int dstag_outer_sum(const float* a, const float* b, float* out, float* asum, int64_t X, int32_t m, int32_t n,
+                    int32_t C, void* stream);
 
-/* ------------------------------------------------------------------------------------
- * Block tail (model/DSTAGNN_my.py:243-252):
+/* Unfused tail (model/DSTAGNN_my.py:243-252) for any T and C <= 256:
  *   tc' = dropout(tc) ; tco = relu(tc' [+ g]) ; out = LN_C(relu(r + tco)) over the channel axis
- *   tc, r, out: (X, C, T) with X = B*N;  g: (X, T, C) channels-last, NULL in block 0 (line 245).
- *   mean/rstd: (X, T) saved statistics.
- * ---------------------------------------------------------------------------------- */
+ *   tc, g (NULL in block 0, line 245), r, out: (X, T, C);  mean/rstd: (X, T) saved statistics.
+ * Dropout element index = (x*C + c)*T + t (the reference's (B,N,C,T) order). */
 int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
                    const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
                    int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
-/* dtc, dr always written; dg (X, T, C) written when g != NULL (dg == d tco).  dgamma/dbeta
- * accumulated atomically into caller-zeroed buffers. */
+/* dtc, dr, dg (when g != NULL): (X, T, C); accumulates dgamma / dbeta (caller-zeroed). */
 int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
                    const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
                    float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
                    float drop_p, uint64_t seed, void* stream);
 
-/* ------------------------------------------------------------------------------------
- * Fused block tail for C = 32, T = 12 (all PEMS configurations): the fcmy Linear over the
- * concatenated time axis (model/DSTAGNN_my.py:243) is folded into the tail, so tc never touches HBM:
- *   tc = cat . wf^T + bf ; then exactly dstag_tail_fwd.   cat (X, C, S = 3T-12), wf (T, S), bf (T).
- * One warp per node, fcmy weights in the constant bank, LayerNorm by warp shuffles.
- * dstag_tail_fused_supported() tells whether (C, T) is served; otherwise use dstag_gemm + dstag_tail_*.
- * ---------------------------------------------------------------------------------- */
+/* fcmy (Linear over the concatenated time axis, line 243) fused with the tail, for C = 32, T = 12:
+ *   tc[x, t, c] = bf[t] + sum_s wf[t, s] * cat[x, s, c]   evaluated in registers, then the tail above.
+ * cat (X, S, C); wf (T, S); bf (T).  dstag_tail_fused_supported(C, T) tells whether the shape is covered. */
 int dstag_tail_fused_supported(int32_t C, int32_t T);
 int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, const float* g, const float* r,
                          const float* gamma, const float* beta, float eps, float* out, float* mean, float* rstd,
                          int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
-/* Writes dcat (X, C, S), dtc (X, C, T) (needed for the fcmy weight / bias gradients, which are a
- * dstag_gemm over (X*C) and a dstag_colsum), dr, dg (when g != NULL); accumulates dgamma / dbeta. */
+/* Backward: dcat (X, S, C), dtc (X, T, C) (feeds dstag_outer_sum for the fcmy weight / bias gradients),
+ * dr, dg (when g != NULL) (X, T, C); accumulates dgamma / dbeta. */
 int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, const float* bf, const float* g,
                          const float* r, const float* gamma, const float* mean, const float* rstd, float* dcat,
                          float* dtc, float* dg, float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C,

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 7
+        return 8
 
     def dstag_last_error(self):
         return self.err
@@ -131,10 +131,13 @@ class FakeLib:
         _arr(out, cols)[:] += acc
         return 0
 
-    def dstag_transpose(self, inp, in_ld, out, out_ld, batch, R, Cc, stream):
+    def dstag_transpose(self, inp, in_ld, out, out_ld, batch, R, Cc, r_d, c_d, stream):
         self.launches += 1
         src = _arr(inp, batch * R * in_ld).reshape(batch, R, in_ld)[:, :, :Cc]
-        _arr(out, batch * Cc * out_ld).reshape(batch, Cc, out_ld)[:, :, :R] = src.transpose(0, 2, 1)
+        pr = (np.arange(R) % r_d) * (R // r_d) + np.arange(R) // r_d
+        pc = (np.arange(Cc) % c_d) * (Cc // c_d) + np.arange(Cc) // c_d
+        dst = _arr(out, batch * Cc * out_ld).reshape(batch, Cc, out_ld)
+        dst[:, pc[:, None], pr[None, :]] = src.transpose(0, 2, 1)
         return 0
 
     def dstag_softmax_fwd(self, x, rows, L, ld, stream):
@@ -211,28 +214,29 @@ class FakeLib:
         return 0
 
     # ---- GTU gate + tail ----
-    def dstag_gtu_gate_fwd(self, u, out, X, Cc, Tp, out_ld, out_off, stream):
+    def dstag_gtu_gate_fwd(self, u, out, X, Cc, Tp, S, off, stream):
         self.launches += 1
         U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
-        O = _arr(out, X * Cc * out_ld).reshape(X, Cc, out_ld)
-        O[:, :, out_off:out_off + Tp] = (np.tanh(U[:, :, :Cc]) / (1 + np.exp(-U[:, :, Cc:]))).transpose(0, 2, 1)
+        O = _arr(out, X * S * Cc).reshape(X, S, Cc)                                   # channels-last
+        O[:, off:off + Tp, :] = np.tanh(U[:, :, :Cc]) / (1 + np.exp(-U[:, :, Cc:]))
         return 0
 
-    def dstag_outer_sum_supported(self, m, n):
-        return int(m > 0 and n > 0 and n % 4 == 0 and m * (n // 4) <= 256)
+    def dstag_outer_sum_supported(self, m, n, Cc):
+        return int(m > 0 and n > 0 and n % 4 == 0 and Cc % 4 == 0 and m * (n // 4) <= 256)
 
-    def dstag_outer_sum(self, a, b, out, rows, m, n, stream):
+    def dstag_outer_sum(self, a, b, out, asum, X, m, n, Cc, stream):
         self.launches += 1
-        A = _arr(a, rows * m).reshape(rows, m).astype(np.float64)
-        Bm = _arr(b, rows * n).reshape(rows, n).astype(np.float64)
-        _arr(out, m * n).reshape(m, n)[:] += A.T @ Bm
+        A = _arr(a, X * m * Cc).reshape(X, m, Cc).astype(np.float64)
+        Bm = _arr(b, X * n * Cc).reshape(X, n, Cc).astype(np.float64)
+        _arr(out, m * n).reshape(m, n)[:] += np.einsum("xmc,xnc->mn", A, Bm)
+        if asum:
+            _arr(asum, m)[:] += A.sum((0, 2))
         return 0
 
-    def dstag_gtu_gate_bwd(self, u, dout, dup, db, X, Cc, Tp, pad, out_ld, out_off, stream):
+    def dstag_gtu_gate_bwd(self, u, dout, dup, db, X, Cc, Tp, pad, S, off, stream):
         self.launches += 1
         U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
-        d = _arr(dout, X * Cc * out_ld).reshape(X, Cc, out_ld)[:, :, out_off:out_off + Tp].astype(np.float64)
-        d = d.transpose(0, 2, 1)                                                   # (X, Tp, C)
+        d = _arr(dout, X * S * Cc).reshape(X, S, Cc)[:, off:off + Tp, :].astype(np.float64)   # (X, Tp, C)
         th, sg = np.tanh(U[:, :, :Cc]), 1 / (1 + np.exp(-U[:, :, Cc:]))
         D = _arr(dup, X * (Tp + 2 * pad) * 2 * Cc).reshape(X, Tp + 2 * pad, 2 * Cc)
         D[:] = 0
@@ -242,18 +246,18 @@ class FakeLib:
             _arr(db, 2 * Cc)[:] += D.reshape(-1, 2 * Cc).astype(np.float64).sum(0)
         return 0
 
+    # ---- tail: every tensor (X, T, C) channels-last ----
     def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, stream):
         assert drop_p == 0.0
         self.launches += 1
         n = X * Cc * T
-        s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
+        s1 = _arr(tc, n).reshape(X, T, Cc).astype(np.float64)
         if g:
-            s1 = s1 + _arr(g, n).reshape(X, T, Cc).transpose(0, 2, 1)             # g is channels-last
-        v = np.maximum(_arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0), 0)
-        mu = v.mean(1)
-        rs = 1 / np.sqrt(v.var(1) + eps)
-        ga, be = _arr(gamma, Cc)[None, :, None], _arr(beta, Cc)[None, :, None]
-        _arr(out, n).reshape(X, Cc, T)[:] = (v - mu[:, None]) * rs[:, None] * ga + be
+            s1 = s1 + _arr(g, n).reshape(X, T, Cc)
+        v = np.maximum(_arr(r, n).reshape(X, T, Cc) + np.maximum(s1, 0), 0)
+        mu = v.mean(2)
+        rs = 1 / np.sqrt(v.var(2) + eps)
+        _arr(out, n).reshape(X, T, Cc)[:] = (v - mu[..., None]) * rs[..., None] * _arr(gamma, Cc) + _arr(beta, Cc)
         _arr(mean, X * T).reshape(X, T)[:] = mu
         _arr(rstd, X * T).reshape(X, T)[:] = rs
         return 0
@@ -263,49 +267,50 @@ class FakeLib:
         assert drop_p == 0.0
         self.launches += 1
         n = X * Cc * T
-        s1 = _arr(tc, n).reshape(X, Cc, T).astype(np.float64)
+        s1 = _arr(tc, n).reshape(X, T, Cc).astype(np.float64)
         if g:
-            s1 = s1 + _arr(g, n).reshape(X, T, Cc).transpose(0, 2, 1)
-        s2 = _arr(r, n).reshape(X, Cc, T) + np.maximum(s1, 0)
+            s1 = s1 + _arr(g, n).reshape(X, T, Cc)
+        s2 = _arr(r, n).reshape(X, T, Cc) + np.maximum(s1, 0)
         v = np.maximum(s2, 0)
-        mu = _arr(mean, X * T).reshape(X, 1, T).astype(np.float64)
-        rs = _arr(rstd, X * T).reshape(X, 1, T).astype(np.float64)
+        mu = _arr(mean, X * T).reshape(X, T, 1).astype(np.float64)
+        rs = _arr(rstd, X * T).reshape(X, T, 1).astype(np.float64)
         xh = (v - mu) * rs
-        d = _arr(dout, n).reshape(X, Cc, T).astype(np.float64)
-        gy = d * _arr(gamma, Cc)[None, :, None]
-        dv = rs * (gy - gy.mean(1, keepdims=True) - xh * (gy * xh).mean(1, keepdims=True))
+        d = _arr(dout, n).reshape(X, T, Cc).astype(np.float64)
+        gy = d * _arr(gamma, Cc)
+        dv = rs * (gy - gy.mean(2, keepdims=True) - xh * (gy * xh).mean(2, keepdims=True))
         ds2 = dv * (s2 > 0)
         ds1 = ds2 * (s1 > 0)
-        _arr(dr, n).reshape(X, Cc, T)[:] = ds2
-        _arr(dtc, n).reshape(X, Cc, T)[:] = ds1
+        _arr(dr, n).reshape(X, T, Cc)[:] = ds2
+        _arr(dtc, n).reshape(X, T, Cc)[:] = ds1
         if dg:
-            _arr(dg, n).reshape(X, T, Cc)[:] = ds1.transpose(0, 2, 1)
-        _arr(dgamma, Cc)[:] += (d * xh).sum((0, 2))
-        _arr(dbeta, Cc)[:] += d.sum((0, 2))
+            _arr(dg, n).reshape(X, T, Cc)[:] = ds1
+        _arr(dgamma, Cc)[:] += (d * xh).sum((0, 1))
+        _arr(dbeta, Cc)[:] += d.sum((0, 1))
         return 0
-
 
     def dstag_tail_fused_supported(self, Cc, T):
         return 1 if (Cc == 32 and T == 12) else 0
 
+    def _fcmy(self, cat, wf, bf, X, Cc, T):
+        S = 3 * T - 12
+        W = _arr(wf, T * S).reshape(T, S).astype(np.float64)
+        tc = np.einsum("xsc,ts->xtc", _arr(cat, X * S * Cc).reshape(X, S, Cc).astype(np.float64), W)
+        return W, np.ascontiguousarray((tc + _arr(bf, T)[None, :, None]).astype(np.float32))
+
     def dstag_tail_fused_fwd(self, cat, wf, bf, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed,
                              stream):
-        S = 3 * T - 12
-        tc = (_arr(cat, X * Cc * S).reshape(X, Cc, S).astype(np.float64) @ _arr(wf, T * S).reshape(T, S).T
-              + _arr(bf, T)).astype(np.float32)
-        self._tc = np.ascontiguousarray(tc)
+        _, self._tc = self._fcmy(cat, wf, bf, X, Cc, T)
         return self.dstag_tail_fwd(self._tc.ctypes.data, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p,
                                    seed, stream)
 
     def dstag_tail_fused_bwd(self, dout, cat, wf, bf, g, r, gamma, mean, rstd, dcat, dtc, dg, dr, dgamma, dbeta, X,
                              Cc, T, drop_p, seed, stream):
         S = 3 * T - 12
-        W = _arr(wf, T * S).reshape(T, S).astype(np.float64)
-        tc = np.ascontiguousarray((_arr(cat, X * Cc * S).reshape(X, Cc, S).astype(np.float64) @ W.T
-                                   + _arr(bf, T)).astype(np.float32))
+        W, tc = self._fcmy(cat, wf, bf, X, Cc, T)
         rc = self.dstag_tail_bwd(dout, tc.ctypes.data, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma, dbeta, X, Cc, T,
                                  drop_p, seed, stream)
-        _arr(dcat, X * Cc * S).reshape(X, Cc, S)[:] = _arr(dtc, X * Cc * T).reshape(X, Cc, T).astype(np.float64) @ W
+        _arr(dcat, X * S * Cc).reshape(X, S, Cc)[:] = np.einsum(
+            "xtc,ts->xsc", _arr(dtc, X * Cc * T).reshape(X, T, Cc).astype(np.float64), W)
         return rc
 
 

@@ -206,7 +206,7 @@ def test_gtu_stack(dev, precision, cfg):
     g = torch.randn(X, T, Cc, device=dev)                                     # channels-last
     ws = [torch.randn(2 * Cc, Cc, 1, ks, device=dev) * 0.2 for ks in (3, 5, 7)]
     bs = [torch.randn(2 * Cc, device=dev) for _ in range(3)]
-    dout = torch.randn(X, Cc, 3 * T - 12, device=dev)
+    dout = torch.randn(X, 3 * T - 12, Cc, device=dev)                         # cat is channels-last too
 
     def ref_fn(g_, w3, b3, w5, b5, w7, b7):
         xc = g_.permute(2, 0, 1).unsqueeze(0)                                 # (1, C, X, T)
@@ -214,7 +214,7 @@ def test_gtu_stack(dev, precision, cfg):
         for w, b in ((w3, b3), (w5, b5), (w7, b7)):
             u = torch.nn.functional.conv2d(xc, w, b)
             outs.append(torch.tanh(u[:, :Cc]) * torch.sigmoid(u[:, -Cc:]))
-        return torch.cat(outs, dim=-1)[0].permute(1, 0, 2)
+        return torch.cat(outs, dim=-1)[0].permute(1, 2, 0)                    # (C, X, S) -> (X, S, C)
 
     args = [g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2]]
     out, gr = _grads(lambda *xs: GtuStack.apply(*xs), args, dout)
@@ -230,15 +230,13 @@ def test_block_tail(dev, cfg):
     from dstagnn_drought_b200.ops import BlockTail
     X, Cc, T, with_g = cfg
     torch.manual_seed(9)
-    tc, r = (torch.randn(X, Cc, T, device=dev) for _ in range(2))
-    g = torch.randn(X, T, Cc, device=dev)                                     # channels-last
+    tc, r, g = (torch.randn(X, T, Cc, device=dev) for _ in range(3))          # all channels-last
     gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
-    dout = torch.randn(X, Cc, T, device=dev)
+    dout = torch.randn(X, T, Cc, device=dev)
 
     def ref_fn(tc_, g_, r_, ga_, be_):
-        tco = torch.relu(tc_ + g_.permute(0, 2, 1)) if with_g else torch.relu(tc_)
-        v = torch.relu(r_ + tco).permute(0, 2, 1)
-        return torch.nn.functional.layer_norm(v, (Cc,), ga_, be_, 1e-5).permute(0, 2, 1)
+        tco = torch.relu(tc_ + g_) if with_g else torch.relu(tc_)
+        return torch.nn.functional.layer_norm(torch.relu(r_ + tco), (Cc,), ga_, be_, 1e-5)
 
     def fn(tc_, g_, r_, ga_, be_):
         return BlockTail.apply(tc_, g_ if with_g else None, r_, ga_, be_, 0.0, 0)
@@ -256,8 +254,8 @@ def test_block_tail_dropout_is_consistent(dev):
     from dstagnn_drought_b200.ops import BlockTail
     torch.manual_seed(10)
     X, Cc, T, p = 4000, 32, 12, 0.05
-    tc = (torch.rand(X, Cc, T, device=dev) + 0.5).requires_grad_(True)      # strictly positive
-    r = torch.full((X, Cc, T), -100.0, device=dev)                          # second relu sees tco only
+    tc = (torch.rand(X, T, Cc, device=dev) + 0.5).requires_grad_(True)      # strictly positive
+    r = torch.full((X, T, Cc), -100.0, device=dev)                          # second relu sees tco only
     gam, bet = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
     out = BlockTail.apply(tc, None, r + 100.0, gam, bet, p, 77)
     out.sum().backward()
@@ -277,6 +275,13 @@ def test_transpose_softmax_colsum_relu(dev):
     torch.manual_seed(11)
     x = torch.randn(3, 45, 70, device=dev)
     assert torch.equal(transpose_raw(x), x.transpose(1, 2).contiguous())
+    # index-pair swaps folded into the transpose: (b, n, (t,f)) -> (b, (f,t), n) and back
+    Bz, N_, T_, F_ = 2, 45, 6, 5
+    xc = torch.randn(Bz, N_, T_ * F_, device=dev)
+    fwd = transpose_raw(xc, pad_rows=True, c_d=F_)
+    want = xc.view(Bz, N_, T_, F_).permute(0, 3, 2, 1).reshape(Bz, F_ * T_, N_)
+    assert torch.equal(fwd, want)
+    assert torch.equal(transpose_raw(fwd, r_d=T_), xc)
     for rows, cols in ((7, 1), (1000, 64), (64, 5000), (33, 130)):
         m = torch.randn(rows, cols, device=dev)
         assert rel_err(colsum(m, rows, cols), m.double().sum(0)) < TOL
@@ -298,18 +303,16 @@ def test_fused_tail(dev, precision, cfg):
     Cc, T, S = 32, 12, 24
     assert FusedTail.supported(Cc, T) and not FusedTail.supported(32, 18)
     torch.manual_seed(12)
-    cat = torch.randn(X, Cc, S, device=dev)
+    cat = torch.randn(X, S, Cc, device=dev)                                   # everything channels-last
     wf, bf = torch.randn(T, S, device=dev) * 0.3, torch.rand(T, device=dev)
-    g = torch.randn(X, T, Cc, device=dev)
-    r = torch.randn(X, Cc, T, device=dev)
+    g, r = torch.randn(X, T, Cc, device=dev), torch.randn(X, T, Cc, device=dev)
     gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
-    dout = torch.randn(X, Cc, T, device=dev)
+    dout = torch.randn(X, T, Cc, device=dev)
 
     def ref_fn(cat_, wf_, bf_, g_, r_, ga_, be_):
-        tc = cat_ @ wf_.t() + bf_
-        tco = torch.relu(tc + g_.permute(0, 2, 1)) if with_g else torch.relu(tc)
-        v = torch.relu(r_ + tco).permute(0, 2, 1)
-        return torch.nn.functional.layer_norm(v, (Cc,), ga_, be_, 1e-5).permute(0, 2, 1)
+        tc = torch.einsum("xsc,ts->xtc", cat_, wf_) + bf_[None, :, None]
+        tco = torch.relu(tc + g_) if with_g else torch.relu(tc)
+        return torch.nn.functional.layer_norm(torch.relu(r_ + tco), (Cc,), ga_, be_, 1e-5)
 
     def fn(cat_, wf_, bf_, g_, r_, ga_, be_):
         return FusedTail.apply(cat_, wf_, bf_, g_ if with_g else None, r_, ga_, be_, 0.0, 0)
@@ -329,11 +332,11 @@ def test_fused_tail_dropout_matches_unfused_mask(dev):
     from dstagnn_drought_b200.ops import BlockTail, FusedTail
     torch.manual_seed(13)
     X, Cc, T, S, p = 300, 32, 12, 24, 0.05
-    cat = torch.randn(X, Cc, S, device=dev)
+    cat = torch.randn(X, S, Cc, device=dev)
     wf, bf = torch.randn(T, S, device=dev) * 0.3, torch.rand(T, device=dev)
-    r = torch.randn(X, Cc, T, device=dev)
+    r = torch.randn(X, T, Cc, device=dev)
     gam, bet = torch.rand(Cc, device=dev), torch.rand(Cc, device=dev)
-    tc = cat @ wf.t() + bf
+    tc = (torch.einsum("xsc,ts->xtc", cat, wf) + bf[None, :, None]).contiguous()
     a = FusedTail.apply(cat, wf, bf, None, r, gam, bet, p, 4242)
     b = BlockTail.apply(tc, None, r, gam, bet, p, 4242)
     assert rel_err(a, b) < 1e-5
