@@ -125,10 +125,12 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
       for (int e = ph; e < nx * c4n; e += phases) {
         const int xl = e / c4n, cg = e - xl * c4n;
         const float4 av = *reinterpret_cast<const float4*>(as + (xl * m + mi) * Cp + 4 * cg);
-        const float* bp = bs + (xl * n + 4 * q) * Cp + 4 * cg;
+        // the thread's four outputs are n = q, q + nq, q + 2 nq, q + 3 nq: for a fixed j the lanes of a
+        // quarter warp read consecutive padded rows (stride 36 floats = 4 banks): conflict-free float4 loads
+        const float* bp = bs + (xl * n + q) * Cp + 4 * cg;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bv = *reinterpret_cast<const float4*>(bp + j * Cp);
+          const float4 bv = *reinterpret_cast<const float4*>(bp + j * nq * Cp);
           acc[j] = fmaf(av.x, bv.x, fmaf(av.y, bv.y, fmaf(av.z, bv.z, fmaf(av.w, bv.w, acc[j]))));
         }
         if (q == 0) accs += (av.x + av.y) + (av.z + av.w);
@@ -148,9 +150,9 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
     for (int p2 = 0; p2 < phases; ++p2)
 #pragma unroll
       for (int j = 0; j < 5; ++j) t[j] += red[(p2 * per + threadIdx.x) * 5 + j];
-    float* dst = out + mi * n + 4 * q;
+    float* dst = out + mi * n + q;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, t[j]);
+    for (int j = 0; j < 4; ++j) atomicAdd(dst + j * nq, t[j]);
     if (asum && q == 0) atomicAdd(asum + mi, t[4]);
   }
 }
