@@ -144,6 +144,18 @@ def _layout_key(t):
     return None if t is None else (t.shape, t.stride())
 
 
+def _m_order(pl: Plan, A):
+    """Enumeration order of a two-letter output-row index.  Rows of C may be visited in any order (the
+    epilogue addresses every row by its strides); prefer the order in which the first operand's rows are
+    memory-contiguous, so its tiles load by 16-byte copies (e.g. the (t, f) rows of a conv weight)."""
+    if len(pl.m) != 2:
+        return pl.m
+    hi, lo = pl.m
+    if A.stride(pl.a.index(lo)) != 1 and A.stride(pl.a.index(hi)) == 1:
+        return [lo, hi]
+    return pl.m
+
+
 def build_descriptor(spec: str, A, B, out, a_mul=None, c_add=None, c_mul=None, alpha=1.0,
                      relu=False, accumulate=ACC_STORE, split_k=1, precision=None) -> Gemm:
     """Pure host logic (no CUDA call): used directly by the CPU tests.  A training step repeats the
@@ -189,12 +201,13 @@ def _build_descriptor(spec: str, A, B, out, a_mul, c_add, c_mul, alpha, relu, ac
     g.M, g.N, g.K, g.batch = (_prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size),
                               _prod(pl.batch, size))
     kl = _k_order(pl, A, B)
-    g.A = _operand(A, pl.a, pl.batch, pl.m, kl, size)
+    ml = _m_order(pl, A)
+    g.A = _operand(A, pl.a, pl.batch, ml, kl, size)
     g.B = _operand(B, pl.b, pl.batch, kl, pl.n, size)
-    g.C = _operand(out, pl.c, pl.batch, pl.m, pl.n, size)
-    g.Amul = _operand(a_mul[1], a_mul[0], pl.batch, pl.m, kl, size) if a_mul else _operand(None, "", [], [], [], size)
-    g.Cmul = _operand(c_mul[1], c_mul[0], pl.batch, pl.m, pl.n, size) if c_mul else _operand(None, "", [], [], [], size)
-    g.Cadd = _operand(c_add[1], c_add[0], pl.batch, pl.m, pl.n, size) if c_add else _operand(None, "", [], [], [], size)
+    g.C = _operand(out, pl.c, pl.batch, ml, pl.n, size)
+    g.Amul = _operand(a_mul[1], a_mul[0], pl.batch, ml, kl, size) if a_mul else _operand(None, "", [], [], [], size)
+    g.Cmul = _operand(c_mul[1], c_mul[0], pl.batch, ml, pl.n, size) if c_mul else _operand(None, "", [], [], [], size)
+    g.Cadd = _operand(c_add[1], c_add[0], pl.batch, ml, pl.n, size) if c_add else _operand(None, "", [], [], [], size)
     g.alpha, g.relu, g.accumulate, g.split_k = float(alpha), int(bool(relu)), int(accumulate), int(split_k)
     g.precision = precision
     return g
