@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cstdio>
 #include "common.cuh"
 
 namespace dstag {
@@ -1019,7 +1020,9 @@ static bool make_tmap(CUtensorMap* map, int* bdim, const dstag_operand_t& o, con
 // batch' = batch * M / d1.  Rewrites the descriptor in place; false = left untouched.
 static bool split_rows_to_batch(dstag_gemm_t& g) {
   const int d1 = g.A.row.d1;
-  if (d1 < 128 || g.A.row.s1 != 1 || g.M % d1 != 0 || g.M == d1) return false;
+  // (inner level contiguous: restores the row-contiguous vector path; inner level strided, e.g. rows (k, j)
+  //  of the Chebyshev output gradient: each batch member then has single-level rows and can use TMA)
+  if (d1 < 128 || g.M % d1 != 0 || g.M == d1) return false;
   const int q = g.M / d1;
   dstag_operand_t* rowops[] = {&g.A, &g.Amul, &g.C, &g.Cadd, &g.Cmul};
   for (dstag_operand_t* o : rowops) {
@@ -1127,6 +1130,16 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
   p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
   p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
+  {
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("DSTAG_TC_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
+    if (trace) {
+      static const char* mn[] = {"KVEC", "MVEC", "ROWG", "KSC"};
+      fprintf(stderr, "[dstag_gemm tc] M=%d N=%d K=%d batch=%d bn=%d A=%s%s%s B=%s%s split=%d acc=%d\n", g->M, g->N, g->K,
+              g->batch, bn, mn[p.a_mode], p.a_tma ? "+TMA" : "", am ? "+mul" : "", mn[p.b_mode], p.b_tma ? "+TMA" : "",
+              p.nsplit, g->accumulate);
+    }
+  }
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
             : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))
