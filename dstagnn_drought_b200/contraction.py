@@ -263,6 +263,19 @@ def _prefers_swap(spec: str, out, A, B) -> bool:
     pl = plan(spec)
     if not pl.c or not pl.m or not pl.n:
         return False
+    # small outputs (weight gradients: K = all rows of the batch): the epilogue is irrelevant, what counts
+    # is how much of the 128 x {32,64,128} MMA tile is padding -- e.g. (64 x 96) fills 37 % of a
+    # 128 x 128 tile, (96 x 64) fills 75 % of a 128 x 64 one
+    size = _sizes(pl, A, B, ())
+    M, N = _prod(pl.m, size), _prod(pl.n, size)
+    if M * N <= (1 << 16):
+        def padded(m, n):
+            bn = 128 if n > 64 else (64 if n > 32 else 32)
+            return ((m + 127) // 128 * 128) * ((n + bn - 1) // bn * bn)
+        if padded(N, M) * 4 <= padded(M, N) * 3:
+            return True
+        if padded(M, N) * 4 <= padded(N, M) * 3:
+            return False
     if out is not None:
         strides = {l: out.stride(i) for i, l in enumerate(pl.c) if out.shape[i] > 1}
         if not strides:
