@@ -270,7 +270,7 @@ struct Producer {
 
   __device__ __forceinline__ int first_row() const {
     if (mode == MODE_KVEC) return row0 + (t >> 3);
-    if (mode == MODE_MVEC) return row0 + 4 * (t % QPK);
+    if (mode == MODE_MVEC) return row0 + 4 * ((((t >> 5) % (ROWS / 32)) << 3) + (t & 7));
     if (mode == MODE_KSC) return row0 + (t >> 5);
     return row0 + (t % ROWS);
   }
@@ -335,38 +335,35 @@ struct Producer {
     }
     const int fr = first_row();
     if (mode == MODE_MVEC) {
-      const int mq = t % QPK, kl0 = (t / QPK) * KPTM;
-      const int mb = mq >> 3, mc = mq & 7;
-      const int kf = k0 + kl0;
+      // MN-major tile: 512-byte atoms of 32 rows x 4 k, atom (ka, mb) at (ka * ROWS/32 + mb) * 512; inside an
+      // atom 128-byte k-rows with a 32-byte swizzle on the row quad.  One warp instruction fills one atom
+      // (lane = (k in atom, row quad)): 512 contiguous bytes of shared memory -- no bank conflicts -- from
+      // four 128-byte lines of global memory.  A thread keeps its row quad and steps through the k atoms.
+      constexpr int RBLK = ROWS / 32, KSTEP = NW / RBLK;      // atoms: a = ka * RBLK + mb = warp + NW * j
+      static_assert(NW % RBLK == 0 && NV * KSTEP == TC_BK / 4, "MVEC atom tiling");
+      const int lane = t & 31, wq = t >> 5;
+      const int mc = lane & 7, kr = lane >> 3;
+      const int mb = wq % RBLK, ka0 = wq / RBLK;
       int nv = limit - fr;
       nv = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
-      // byte offset of (k = kl0 + j, row quad mq) in the MN-major tile: 512-byte atoms of 32 rows x 4 k,
-      // atom (ka, mb) at (ka * ROWS/32 + mb) * 512, 128-byte k-rows inside, 32-byte swizzle on the quad.
-      // kl0 is a multiple of NV: for NV >= 4 the k part of the offset is a compile-time function of j.
-      const int kr0 = NV >= 4 ? 0 : (kl0 & 3);
-      const uint32_t d0 = pbase + (uint32_t)((((kl0 >> 2) * (ROWS / 32) + mb) << 9) + ((mc & 1) << 4));
-      auto koff = [&](int j) -> uint32_t {
-        const int kr = kr0 + (j & 3);      // NV == 2: kr0 in {0, 2}, j in {0, 1}: no carry into the atom index
-        return (uint32_t)((((j >> 2) * (ROWS / 32)) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5));
-      };
+      const uint32_t d0 = pbase + (uint32_t)(((ka0 * RBLK + mb) << 9) + (kr << 7) + (((mc >> 1) ^ kr) << 5) + ((mc & 1) << 4));
+      const int kf = k0 + 4 * ka0 + kr;                       // this thread's k in pass j: kf + 4 * KSTEP * j
       const float* rp = bp + roff;
       if (cax.d1 == 1) {
         const int ks = (int)cax.s0;
         const float* kp = rp + kf * ks;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          const uint32_t off = koff(j);
-          const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
-          cp_async16(d0 + off, bytes ? (const void*)(kp + j * ks) : (const void*)bp, bytes);
+          const uint32_t bytes = (kf + 4 * KSTEP * j < K) ? (uint32_t)(4 * nv) : 0u;
+          cp_async16(d0 + j * (NW << 9), bytes ? (const void*)(kp + j * (4 * KSTEP) * ks) : (const void*)bp, bytes);
         }
       } else {
         Walk w;
-        w.init(cax, kf, 1);
+        w.init(cax, kf < K ? kf : 0, 4 * KSTEP);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          const uint32_t off = koff(j);
-          const uint32_t bytes = (kf + j < K) ? (uint32_t)(4 * nv) : 0u;
-          cp_async16(d0 + off, bytes ? (const void*)(rp + w.off) : (const void*)bp, bytes);
+          const uint32_t bytes = (kf + 4 * KSTEP * j < K) ? (uint32_t)(4 * nv) : 0u;
+          cp_async16(d0 + j * (NW << 9), bytes ? (const void*)(rp + w.off) : (const void*)bp, bytes);
           w.next();
         }
       }

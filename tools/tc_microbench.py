@@ -38,9 +38,11 @@ def main():
     cat, dtc = r(X * C, 3 * T - 12), r(X * C, T)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     cases = [
-        ("cheb_fwd", "bkji,bie->kbje", P[..., :N], x3, dict(a_mul=("kji", Tk[..., :N]))),
-        ("cheb_bwd_dx", "bkji,kbje->bie", P[..., :N], Z, dict(a_mul=("kji", Tk[..., :N]))),
-        ("cheb_bwd_dmap", "kbje,bie->bkji", Z, x3, dict(out=dS[..., :N], c_mul=("kji", Tk[..., :N]))),
+        # (the model feeds TP = T_k (.) P, written by the map kernel, and applies T_k in the softmax backward)
+        ("cheb_fwd", "bkji,bie->kbje", P[..., :N], x3, {}),
+        ("cheb_bwd_dx", "bkji,kbje->bie", P[..., :N], Z, {}),
+        ("cheb_bwd_dmap", "kbje,bie->bkji", Z, x3, dict(out=dS[..., :N])),
+        ("cheb_fwd_amul", "bkji,bie->kbje", P[..., :N], x3, dict(a_mul=("kji", Tk[..., :N]))),
         ("sat_scores", "bjkd,bikd->bkji", qk[:, :, 1], qk[:, :, 0], dict(out=dS[..., :N], alpha=1 / math.sqrt(dk))),
         ("sat_dq", "bkji,bjkd->bikd", dS[..., :N], qk[:, :, 1], {}),
         ("sat_dk", "bkji,bikd->bjkd", dS[..., :N], qk[:, :, 0], {}),
