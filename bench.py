@@ -186,6 +186,16 @@ def workload_config(args, w, batch):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def ncu_traffic(w, args):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/r01_ncu_cheb_final.md); only valid for the configuration it was taken on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_cheb_traffic.json")
+    if args.workload != "pems07" or args.precision != "tf32x3" or (args.batch or w["B"]) != 64 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)["mean_bytes_per_launch"]
+
+
 def run_ours(args, w):
     import torch.distributed as dist
     from dstagnn_drought_b200 import _lib, make_model, set_precision
@@ -296,7 +306,7 @@ def run_ours(args, w):
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                 "peak_source": f"{pk['src']} dense bf16 (sustained); fp32-grade 3xTF32 issues 6 bf16-equivalent "
                                "MMA passes per algorithmic flop, so its ceiling is peak/6",
-                "traffic": None, "launches_per_step": c_calls / prof_steps,
+                "traffic": ncu_traffic(w, args), "launches_per_step": c_calls / prof_steps,
                 "avg_launch_ms": c_ms / max(c_calls, 1), "share_of_step": (c_ms / prof_steps) / (ms / args.steps),
                 "precision": args.precision}
     breakdown = {t: {"calls_per_step": v[0] / prof_steps, "ms_per_step": round(v[1] / prof_steps, 4),
