@@ -201,3 +201,25 @@ def test_tc_epilogue_aligned_runs_of_columns(T, precision):
     assert rel_err(out2, ref * mul.double() + 1.0) < TOL[precision]
     out3 = _run("mk,xtk->xmt", th, gx, precision, relu=True, alpha=0.5)
     assert rel_err(out3, torch.relu(0.5 * ref)) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_tc_vector_loads_on_aligned_two_level_runs(precision):
+    """Channels-last shapes: a reduction index (k, f) and a row index (x, c) that are contiguous only in
+    runs (f / c innermost, run length % 4 == 0) still take the 16-byte copy paths."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    K_, X, T, F, C = 3, 333, 12, 32, 32
+    Z = torch.randn(K_, X, T, F, device=dev)
+    th = torch.randn(K_, F, C, device=dev)
+    g = _run("kxtf,kfc->xtc", Z, th, precision, relu=True)                      # K = (k, f): runs of F
+    assert rel_err(g, torch.relu(torch.einsum("kxtf,kfc->xtc", Z.double(), th.double()))) < TOL[precision]
+    dZ = _run("xtc,kfc->kxtf", g, th, precision)                                # columns (k, f): runs of F
+    assert rel_err(dZ, torch.einsum("xtc,kfc->kxtf", g.double(), th.double())) < TOL[precision]
+    dth = _run("kxtf,xtc->kfc", Z, g, precision)                                # rows (k, f), K = (x, t)
+    assert rel_err(dth, torch.einsum("kxtf,xtc->kfc", Z.double(), g.double())) < TOL[precision]
+    S = 24
+    cat = torch.randn(X, S, C, device=dev)
+    W = torch.randn(T, S, device=dev)
+    tc = _run("xsc,ts->xtc", cat, W, precision)                                 # rows (x, c): runs of C
+    assert rel_err(tc, torch.einsum("xsc,ts->xtc", cat.double(), W.double())) < TOL[precision]
