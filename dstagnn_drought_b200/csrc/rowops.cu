@@ -265,7 +265,6 @@ __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __rest
 // A warp keeps its row in registers, reduces with shuffles and never touches shared memory or
 // a block barrier, so 8 rows per CTA are in flight and the kernels run at HBM speed.
 // ======================================================================================
-constexpr int kWR = 32;                 // register elements per lane -> rows up to 1024
 
 // Warp-per-row LayerNorm for rows of up to 128 * NV floats whose storage is 16-byte aligned (row-padded
 // tensors): a lane keeps NV float4 of the row in registers, statistics by warp shuffles, no shared

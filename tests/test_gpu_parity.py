@@ -119,3 +119,30 @@ def test_train_mode_runs_and_dropout_is_active():
     assert rel_err(y1.detach(), y0.detach()) < 0.5       # but the same function in expectation
     y1.sum().backward()
     assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+
+
+def test_inference_no_grad_and_block_level_api():
+    """eval / no_grad inference gives the same predictions as the autograd forward; a block
+    called on its own (the reference's `block(x, res_att)` contract) accepts a plain contiguous
+    (B, N, F, T) input as well as the channels-last view a preceding block returns, and returns a
+    (B, N, C, T) tensor plus the (B, F, H, T, T) logits."""
+    dev = torch.device("cuda:0")
+    d, cfg, w, g, cheb = load_golden("g_n20")
+    net = _build(cfg, d, dev)
+    net.load_state_dict(w)
+    net.eval()
+    x = torch.from_numpy(d["x"]).to(dev)
+    y_grad = net(x)
+    with torch.no_grad():
+        y_inf = net(x)
+    assert torch.equal(y_grad.detach(), y_inf)
+    assert rel_err(y_inf, d["y64"]) < TOL_PRED
+    with torch.no_grad():
+        out0, att0 = net.BlockList[0](x, 0)
+        B, N, C, T = out0.shape
+        assert (B, N, T) == (x.shape[0], cfg["N"], cfg["T"]) and C == 32
+        assert att0.shape == (B, 1, cfg["H"], T, T)
+        out1_view, _ = net.BlockList[1](out0, att0)                       # channels-last view from block 0
+        out1_copy, _ = net.BlockList[1](out0.contiguous(), att0)          # the same values, standard layout
+    assert torch.equal(out1_view, out1_copy)
+    assert rel_err(out1_view, d["blk64.1"]) < TOL_PRED
