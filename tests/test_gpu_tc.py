@@ -223,3 +223,38 @@ def test_tc_vector_loads_on_aligned_two_level_runs(precision):
     W = torch.randn(T, S, device=dev)
     tc = _run("xsc,ts->xtc", cat, W, precision)                                 # rows (x, c): runs of C
     assert rel_err(tc, torch.einsum("xsc,ts->xtc", cat.double(), W.double())) < TOL[precision]
+
+
+@pytest.mark.parametrize("case", [
+    ("bmk,bnk->bmn", (2, 130, 70), (2, 45, 70), None),            # path (a)/(b): ragged M, N, K
+    ("bkm,bkn->bmn", (3, 50, 257), (3, 50, 36), None),            # MN-major operands, ragged rows
+    ("mk,xtk->xmt", (96, 32), (77, 12, 32), None),                # (b4) float4 transposed stores
+    ("mk,xtk->xmt", (40, 24), (31, 6, 24), None),                 # scalar transposed stores
+    ("xtk,ok->xto", (61, 10, 96), (64, 96), None),                # two-level rows
+    ("bnd,bftn->dtf", (3, 131, 40), (3, 4, 6, 131), "rows"),      # K outer level folded into an atomic batch
+])
+def test_tc_writes_stay_inside_the_output(case):
+    """Guard bands around the output (and a padded leading dimension inside it) must survive every
+    epilogue path: the engine writes nothing outside the logical output elements."""
+    from dstagnn_drought_b200 import contraction as ct
+    spec, sa, sb, pad = case
+    dev = torch.device("cuda:0")
+    torch.manual_seed(33)
+    A = torch.randn(*sa, device=dev)
+    B = ct.empty_rows(sb, dev).normal_() if pad == "rows" else torch.randn(*sb, device=dev)
+    shape = ct.output_shape(spec, A, B)
+    n = 1
+    for v in shape:
+        n *= v
+    ld = shape[-1] + 3                                            # padded rows: the pad must stay untouched too
+    rows = n // shape[-1]
+    G = 1024
+    buf = torch.full((2 * G + rows * ld,), 12345.0, device=dev)
+    out = buf[G:G + rows * ld].view(*shape[:-1], ld)[..., :shape[-1]]
+    ct.contract_raw(spec, A, B, out=out, precision=ct._PRECISION["tf32x3"])
+    torch.cuda.synchronize()
+    ref = torch.einsum(spec, A.double(), B.double())
+    assert rel_err(out, ref) < TOL["tf32x3"]
+    assert bool((buf[:G] == 12345.0).all()) and bool((buf[G + rows * ld:] == 12345.0).all()), "guard band overwritten"
+    padcols = buf[G:G + rows * ld].view(rows, ld)[:, shape[-1]:]
+    assert bool((padcols == 12345.0).all()), "row padding overwritten"
