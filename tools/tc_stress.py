@@ -13,17 +13,21 @@ r = lambda *s: torch.randn(*s, device=dev)
 P = ct._PRECISION["tf32x3"]
 cases = []
 X, C, T = 99, 32, 12
+g = r(X, T, C)                                            # channels-last graph-conv output
 for ks in (3, 5, 7):
-    Tp = T - ks + 1
-    g3, w, du = r(X, C, T), r(2 * C, C, ks), r(X, 2 * C, Tp)
-    cases += [(f"conv_fwd{ks}", "xctd,ocd->xot", g3.unfold(2, ks, 1), w, {}),
-              (f"conv_dw{ks}", "xot,xctd->ocd", du, g3.unfold(2, ks, 1), {})]
+    Tp, pad = T - ks + 1, ks - 1
+    gv = g.as_strided((X, Tp, ks * C), (T * C, C, 1))     # overlapping conv windows
+    dup = r(X, Tp + 2 * pad, 2 * C)
+    cases += [(f"conv_fwd{ks}", "xtk,ok->xto", gv, r(2 * C, ks * C), {}),
+              (f"conv_dw{ks}", "xto,xtk->ok", dup[:, pad:pad + Tp, :], gv, {}),
+              (f"conv_dx{ks}", "xtk,ck->xtc", dup.as_strided((X, T, ks * 2 * C), ((Tp + 2 * pad) * 2 * C, 2 * C, 1)),
+               r(C, ks * 2 * C), {})]
 N, D, Bz, K, FT = 33, 32, 3, 3, 384
-O, Wp, dZ = r(Bz, 32, 12, N), r(D, 12, 1, 32), r(Bz, N, D)
+O, Wp, dZ = ct.empty_rows((Bz, 32, 12, N), dev).normal_(), r(D, 12, 1, 32), r(Bz, N, D)
 cases += [("pre_conv", "bftn,dtf->bnd", O, Wp[:, :, 0, :], {}),
           ("pre_dx", "bnd,dtf->bftn", dZ, Wp[:, :, 0, :], {}),
           ("pre_dw", "bftn,bnd->dtf", O, dZ, {})]
-E, Wq = r(Bz * FT, N), r(288, N)
+E, Wq = ct.empty_rows((Bz * FT, N), dev).normal_(), ct.empty_rows((288, N), dev).normal_()
 cases += [("qkv", "rn,on->ro", E, Wq, {}), ("qkv_dx", "ro,on->rn", r(Bz * FT, 288), Wq, {}),
           ("qkv_dw", "rn,ro->on", E, r(Bz * FT, 288), {})]
 ld = 64
@@ -34,14 +38,14 @@ cases += [("cheb_fwd", "bkji,bie->kbje", Pm[..., :N], x3, dict(a_mul=("kji", Tk[
           ("cheb_dx", "bkji,kbje->bie", Pm[..., :N], Z, dict(a_mul=("kji", Tk[..., :N]))),
           ("cheb_dmap", "kbje,bie->bkji", Z, x3, dict(c_mul=("kji", Tk[..., :N])))]
 th = r(K, 32, 32)
-cases += [("theta", "kxft,kfc->xct", Z.view(K, Bz * N, 32, 12), th, dict(relu=True)),
-          ("theta_dz", "xct,kfc->kxft", r(Bz * N, 32, 12), th, {}),
-          ("theta_dth", "kxft,xct->kfc", Z.view(K, Bz * N, 32, 12), r(Bz * N, 32, 12), {})]
-cat, Wf = r(Bz * N * 32, 24), r(12, 24)
-cases += [("fcmy", "rs,ts->rt", cat, Wf, {}), ("fcmy_dx", "rt,ts->rs", r(Bz * N * 32, 12), Wf, {})]
-fin, Wfin = r(Bz * N, 32, 12), r(128, 12, 32)
-cases += [("final", "xct,otc->xo", fin, Wfin, {}), ("final_dx", "xo,otc->xct", r(Bz * N, 128), Wfin, {}),
-          ("final_dw", "xct,xo->otc", fin, r(Bz * N, 128), {})]
+cases += [("theta", "kxtf,kfc->xtc", Z.view(K, Bz * N, 12, 32), th, dict(relu=True)),
+          ("theta_dz", "xtc,kfc->kxtf", r(Bz * N, 12, 32), th, {}),
+          ("theta_dth", "kxtf,xtc->kfc", Z.view(K, Bz * N, 12, 32), r(Bz * N, 12, 32), {})]
+cat, Wf = r(Bz * N, 24, 32), r(12, 24)
+cases += [("fcmy", "xsc,ts->xtc", cat, Wf, {}), ("fcmy_dx", "xtc,ts->xsc", r(Bz * N, 12, 32), Wf, {})]
+fin, Wfin = r(Bz * N, 12, 32), r(128, 12, 32)
+cases += [("final", "xtc,otc->xo", fin, Wfin, {}), ("final_dx", "xo,otc->xtc", r(Bz * N, 128), Wfin, {}),
+          ("final_dw", "xo,xtc->otc", r(Bz * N, 128), fin, {})]
 SE, Ws = r(Bz * N, D), r(192, D)
 cases += [("sat", "rd,od->ro", SE, Ws, {}), ("sat_dx", "ro,od->rd", r(Bz * N, 192), Ws, {}), ("sat_dw", "rd,ro->od", SE, r(Bz * N, 192), {})]
 for name, spec, A, B, kw in cases:
