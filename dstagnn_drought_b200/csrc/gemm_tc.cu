@@ -146,6 +146,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (128 rows x 8 k) is read from tensor memory,
+// lane = row, column = k (one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -410,20 +433,30 @@ struct Producer {
   }
 };
 
-template <int BN, bool X3, bool AMUL>
+template <int BN, bool X3, bool AMUL, bool ATM_>
 struct TcCfg {
   static constexpr int A_PLANE = TC_BM * 128;
   static constexpr int B_PLANE = BN * 128;
   static constexpr int PLANES = X3 ? 2 : 1;
-  static constexpr int A_PLANES = (X3 || AMUL) ? 2 : 1;   // the Hadamard factor lands in a second A plane
+  // A through tensor memory (3xTF32 without a Hadamard factor): the raw A tile lands in shared memory, the
+  // A producer warps read their row of it, split it in registers and store hi / lo into TMEM columns
+  // (tcgen05.st), and the MMAs take A from TMEM (TS form).  A then needs ONE shared-memory plane and no
+  // tensor-core reads of shared memory: the 3-pass product is bound by shared-memory bandwidth
+  // (operand reads 3 x (A + B) per k-block), so this removes a third of the traffic and buys a 4th stage.
+  static constexpr bool ATM = ATM_;
+  static_assert(!ATM_ || (X3 && !AMUL), "A through tensor memory: 3xTF32 without a Hadamard factor");
+  static constexpr int A_PLANES = ATM ? 1 : ((X3 || AMUL) ? 2 : 1);   // (a Hadamard factor lands in a second A plane)
   static constexpr int B_OFF = A_PLANES * A_PLANE;        // B planes follow the A planes in a stage
   static constexpr int STAGE = A_PLANES * A_PLANE + PLANES * B_PLANE;
   static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 6;    // 64 TMEM columns (hi + lo) per stage
+  static constexpr int STAGES_CAP = STAGES_TM < 6 ? STAGES_TM : 6;
+  static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
   static constexpr int BAR_OFF = STAGES * STAGE;
   static constexpr int EPI_OFF = BAR_OFF + 512;
   static constexpr int SMEM = EPI_OFF + TC_EPI_SMEM + 1024 /*align slack*/;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = ATM ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
+  static constexpr int A_TM = 2 * BN;                     // first TMEM column of the A slots
 };
 
 // The CTA's flat (output tile, k-block) sequence, walked identically by every role.
@@ -463,10 +496,74 @@ struct PosIter {
 // (JOINT) all 12 producer warps wait for both tiles and take equal shares of the A and B chunks.
 // Measured on B200: weight-gradient shapes 7-20 % faster; not used with a Hadamard factor or narrower
 // B tiles, where the coupling of the two groups costs more than the balance gains.
+// A through tensor memory: thread (warp w, lane l) owns row 32 (w % 4) + l of the raw tile and the k half w / 4.
+template <class Cfg>
+__device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_major, uint32_t tmem_slot, int t) {
+  const int lane = t & 31, w = t >> 5;
+  const int r = 32 * (w & 3) + lane, kh = w >> 2;
+  uint32_t hi[16], lo[16];
+  if (!mn_major) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(a_raw + swz(r, 4 * kh + c));
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[4 * c + j] = __float_as_uint(e[j]);
+        lo[4 * c + j] = __float_as_uint(tf32_lo(e[j]));
+      }
+    }
+  } else {
+    // MN-major raw tile: atom (ka, mb) at (ka * 4 + mb) * 512, k-row kr at +128 kr, row quad q at 32-byte unit
+    // (q >> 1) ^ kr, half (q & 1) * 16, element (r & 3) * 4
+    const int mb = r >> 5, q = (r & 31) >> 2, e = r & 3;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = 16 * kh + kk, ka = k >> 2, kr = k & 3;
+      const uint32_t off = (uint32_t)(((ka * (TC_BM / 32) + mb) << 9) + (kr << 7) + (((q >> 1) ^ kr) << 5) + ((q & 1) << 4) + (e << 2));
+      const float v = *reinterpret_cast<const float*>(a_raw + off);
+      hi[kk] = __float_as_uint(v);
+      lo[kk] = __float_as_uint(tf32_lo(v));
+    }
+  }
+  const uint32_t ta = tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + 16 * kh;
+  tmem_st16(ta, hi);
+  tmem_st16(ta + 32, lo);
+  tmem_st_wait();
+  tc_fence_before();
+}
+
 template <class Cfg, int BN, bool X3, bool AMUL, bool IS_A>
 __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uint64_t* rawb, uint32_t ph, bool has_mul,
-                                             int t, int pt, int lane) {
-  constexpr bool JOINT = (BN == 128) && !AMUL && X3;
+                                             int t, int pt, int lane, uint32_t tmem_slot = 0, bool a_mn = false) {
+  if constexpr (Cfg::ATM) {
+    // A warps: row split into tensor memory.  With a 128-row B tile all 12 warps then share B's split
+    // (the 4 B warps alone would be the critical path); narrower B tiles stay with the B warps.
+    constexpr bool SHARE_B = BN == 128;
+    if (IS_A) {
+      if (lane == 0) mbar_wait(rawa, ph, 0);
+      __syncwarp();
+      finish_a_tmem<Cfg>(stage, a_mn, tmem_slot, t);
+      if (!SHARE_B) return;
+    }
+    if (lane == 0) mbar_wait(rawb, ph, 0);
+    __syncwarp();
+    uint8_t* b_hi = stage + Cfg::B_OFF;
+    constexpr int B_CH = BN * 8;
+    constexpr int NTB = SHARE_B ? (TC_A_WARPS + TC_B_WARPS) * 32 : TC_B_WARPS * 32;
+    const int tb = SHARE_B ? pt : t;
+#pragma unroll
+    for (int i = 0; i < (B_CH + NTB - 1) / NTB; ++i) {
+      const int c = tb + i * NTB;
+      if (c < B_CH) {
+        const uint32_t off = (uint32_t)c * 16u;
+        *reinterpret_cast<float4*>(b_hi + Cfg::B_PLANE + off) = tf32_lo4(*reinterpret_cast<const float4*>(b_hi + off));
+      }
+    }
+    fence_proxy_async_smem();
+    return;
+  }
+  constexpr bool JOINT = (BN == 128) && !AMUL && X3 && !Cfg::ATM;
   constexpr int A_CH = TC_BM * 8, B_CH = BN * 8;
   if (lane == 0) {
     if (JOINT || IS_A) mbar_wait(rawa, ph, 0);
@@ -521,14 +618,15 @@ __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uin
 // part in finishing the stages.
 template <class Cfg, int BN, bool X3, bool AMUL, bool IS_A>
 __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* rawa_bar,
-                                              uint64_t* rawb_bar, int t, int pt, int lane) {
+                                              uint64_t* rawb_bar, int t, int pt, int lane, uint32_t tmem_base) {
   const bool has_mul = AMUL && p.g.Amul.ptr != nullptr;
+  const bool a_mn = p.a_mode == MODE_MVEC;
   PosIter pos;
   uint32_t it = 0;
   for (bool ok = pos.init(p); ok; ok = pos.next(p), ++it) {
     const int s = it % Cfg::STAGES;
     finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (it / Cfg::STAGES) & 1,
-                                          has_mul, t, pt, lane);
+                                          has_mul, t, pt, lane, tmem_base + Cfg::A_TM + s * 64, a_mn);
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar + s);
   }
@@ -538,7 +636,8 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
 // group's copies run STAGES-1 k-blocks ahead of the stage being finished.
 template <class Cfg, int BN, int ROWS, int NT, bool X3, bool AMUL, bool IS_A>
 __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                              uint64_t* rawa_bar, uint64_t* rawb_bar, int t, int pt, int lane) {
+                                              uint64_t* rawa_bar, uint64_t* rawb_bar, int t, int pt, int lane,
+                                              uint32_t tmem_base) {
   using P = Producer<ROWS, NT, IS_A && AMUL>;
   constexpr int STAGES = Cfg::STAGES;
   const dstag_gemm_t& g = p.g;
@@ -588,7 +687,7 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
   while (okx) {
     const int s = nx % STAGES;
     finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (nx / STAGES) & 1, has_mul,
-                                          t, pt, lane);
+                                          t, pt, lane, tmem_base + Cfg::A_TM + s * 64, p.a_mode == MODE_MVEC);
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar + s);
     okx = px.next(p);
@@ -597,10 +696,10 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
   }
 }
 
-template <int BN, bool X3, bool AMUL>
+template <int BN, bool X3, bool AMUL, bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p,
                                                                 const __grid_constant__ TcMaps maps) {
-  using Cfg = TcCfg<BN, X3, AMUL>;
+  using Cfg = TcCfg<BN, X3, AMUL, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -639,17 +738,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int pt = threadIdx.x;                          // producer thread index over both groups
     if (warp < TC_A_WARPS) {
       if (!AMUL && p.a_tma)
-        transform_all<Cfg, BN, X3, AMUL, true>(p, smem, full_bar, rawa_bar, rawb_bar, threadIdx.x, pt, lane);
+        transform_all<Cfg, BN, X3, AMUL, true>(p, smem, full_bar, rawa_bar, rawb_bar, threadIdx.x, pt, lane, tmem_base);
       else
         produce_async<Cfg, BN, TC_BM, TC_A_WARPS * 32, X3, AMUL, true>(p, smem, full_bar, empty_bar, rawa_bar, rawb_bar,
-                                                                       threadIdx.x, pt, lane);
+                                                                       threadIdx.x, pt, lane, tmem_base);
     } else {
       if (p.b_tma)
         transform_all<Cfg, BN, X3, AMUL, false>(p, smem, full_bar, rawa_bar, rawb_bar, threadIdx.x - TC_A_WARPS * 32, pt,
-                                                lane);
+                                                lane, tmem_base);
       else
         produce_async<Cfg, BN, BN, TC_B_WARPS * 32, X3, AMUL, false>(p, smem, full_bar, empty_bar, rawa_bar, rawb_bar,
-                                                                     threadIdx.x - TC_A_WARPS * 32, pt, lane);
+                                                                     threadIdx.x - TC_A_WARPS * 32, pt, lane, tmem_base);
     }
   } else if (warp == TC_TMA_WARP) {
     // =============================== TMA issuer ========================================
@@ -696,6 +795,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       // descriptor advance per K step of 8 (16-byte units): +32 B inside the swizzle row (K-major),
       // two 4-k atoms = +1024 B (MN-major)
+      const uint32_t idesc_ts = idesc & ~(1u << 15);     // A from tensor memory is always K-major
       const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;
       const uint64_t b_adv = b_mn ? (uint64_t)((BN / 32) * 1024 >> 4) : 2ull;
       uint32_t it = 0, item = 0;
@@ -722,7 +822,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t aa = a_adv * kk, ba = b_adv * kk;
             const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
-            if (X3) {
+            if constexpr (Cfg::ATM) {
+              const uint32_t ta = tmem_base + Cfg::A_TM + s * 64 + 8 * kk;     // hi columns; lo at +32
+              umma_tf32_ts(d_tmem, ta + 32, b_hi + ba, idesc_ts, first);
+              umma_tf32_ts(d_tmem, ta, b_lo + ba, idesc_ts, 1u);
+              umma_tf32_ts(d_tmem, ta, b_hi + ba, idesc_ts, 1u);
+            } else if (X3) {
               umma_tf32(d_tmem, a_lo + aa, b_hi + ba, idesc, first);
               umma_tf32(d_tmem, a_hi + aa, b_lo + ba, idesc, 1u);
               umma_tf32(d_tmem, a_hi + aa, b_hi + ba, idesc, 1u);
@@ -1079,12 +1184,12 @@ static bool split_cols_to_batch(dstag_gemm_t& g) {
 
 static int g_num_sms = 0;
 
-template <int BN, bool X3, bool AMUL>
+template <int BN, bool X3, bool AMUL, bool ATM>
 static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream) {
-  using Cfg = TcCfg<BN, X3, AMUL>;
+  using Cfg = TcCfg<BN, X3, AMUL, ATM>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3, AMUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3, AMUL, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("dstag_gemm(tc): cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
       return (int)e;
@@ -1092,7 +1197,7 @@ static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream)
     configured = true;
   }
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
-  gemm_tc_kernel<BN, X3, AMUL><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p, maps);
+  gemm_tc_kernel<BN, X3, AMUL, ATM><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p, maps);
   DSTAG_RETURN_LAUNCH("dstag_gemm(tcgen05)");
 }
 
@@ -1137,9 +1242,16 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
               p.nsplit, g->accumulate);
     }
   }
+  // A through tensor memory pays when the A tile is K-major (a row is four 16-byte loads); an MN-major
+  // tile would need 16 scalar loads per thread and stays on the shared-memory operand path
+  static int atm_on = -1;
+  if (atm_on < 0) { const char* e = getenv("DSTAG_TC_ATM"); atm_on = (e && e[0] == '0') ? 0 : 1; }
+  const bool atm = atm_on && x3 && !am && p.a_mode != MODE_MVEC;
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
-  return x3 ? (am ? launch_tc<BN_, true, true>(p, maps, stream) : launch_tc<BN_, true, false>(p, maps, stream)) \
-            : (am ? launch_tc<BN_, false, true>(p, maps, stream) : launch_tc<BN_, false, false>(p, maps, stream))
+  return x3 ? (am ? launch_tc<BN_, true, true, false>(p, maps, stream)                                            \
+                  : (atm ? launch_tc<BN_, true, false, true>(p, maps, stream)                                    \
+                         : launch_tc<BN_, true, false, false>(p, maps, stream)))                                 \
+            : (am ? launch_tc<BN_, false, true, false>(p, maps, stream) : launch_tc<BN_, false, false, false>(p, maps, stream))
   if (bn == 128) DSTAG_TC_DISPATCH(128);
   if (bn == 64) DSTAG_TC_DISPATCH(64);
   DSTAG_TC_DISPATCH(32);
