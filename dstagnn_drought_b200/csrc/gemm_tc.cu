@@ -1245,8 +1245,8 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   // A through tensor memory pays when the A tile is K-major (a row is four 16-byte loads); an MN-major
   // tile would need 16 scalar loads per thread and stays on the shared-memory operand path
   static int atm_on = -1;
-  if (atm_on < 0) { const char* e = getenv("DSTAG_TC_ATM"); atm_on = (e && e[0] == '0') ? 0 : 1; }
-  const bool atm = atm_on && x3 && !am && p.a_mode != MODE_MVEC;
+  if (atm_on < 0) { const char* e = getenv("DSTAG_TC_ATM"); atm_on = e ? atoi(e) : 1; }
+  const bool atm = atm_on && x3 && !am && (p.a_mode != MODE_MVEC || atm_on == 2);
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true, false>(p, maps, stream)                                            \
                   : (atm ? launch_tc<BN_, true, false, true>(p, maps, stream)                                    \
