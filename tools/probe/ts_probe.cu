@@ -1,4 +1,4 @@
-// Hardware probe: does tcgen05.mma (kind::tf32) with the A operand in TMEM expect "lane = row m, column = k"?
+// Hardware probe (build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o ts_probe ts_probe.cu): does tcgen05.mma (kind::tf32) with the A operand in TMEM expect "lane = row m, column = k"?
 // One CTA, M = 128, N = 128, K = 32.  A goes registers -> TMEM (tcgen05.st 32x32b), B sits K-major SWIZZLE_128B
 // in shared memory.  Prints the max error against a CPU product of the tf32-truncated inputs.
 #include <cstdio>
