@@ -2,14 +2,19 @@
 //
 //   C[b,m,n] (+)= alpha * sum_k (A . Amul)[b,m,k] * B[b,k,n]   (+Cadd) (*Cmul) (relu)
 //
-// Persistent, warp-specialised kernel (one CTA per SM, 13 warps):
-//   warps 0-3   A producers   global (any 2-level strided view) -> registers -> [x Amul] ->
-//                             [hi/lo TF32 split] -> swizzled shared-memory operand tile
-//   warps 4-7   B producers   same for the second operand
-//   warps 8-11  epilogue      TMEM -> registers (tcgen05.ld) -> alpha / Cadd / Cmul / relu ->
+// Persistent, warp-specialised kernel (one CTA per SM, 18 warps = 576 threads):
+//   warps 0-7   A producers   cp.async (16-byte, zero-filled at ragged edges) from any 2-level strided view
+//                             straight into the stage's swizzled tile, STAGES-1 k-blocks ahead; then
+//                             EITHER A through tensor memory (K-major A, 3xTF32): each thread splits its
+//                             row of the raw tile in registers and tcgen05.st's hi / lo into TMEM,
+//                             OR in place in shared memory: [x Hadamard factor] -> lo = v - trunc_tf32(v)
+//   warps 8-11  B producers   the same copies for the second operand; split in place in shared memory
+//                             (with a 128-row B tile all 12 producer warps share that split)
+//   warps 12-15 epilogue      TMEM -> registers (tcgen05.ld) -> alpha / Cadd / Cmul / relu ->
 //                             global (store, add or atomic), accumulator double-buffered in TMEM
-//   warp  12    MMA issuer    one thread issues tcgen05.mma.kind::tf32 (128 x BN x 8) from the
-//                             shared-memory descriptors; tcgen05.commit releases the stages
+//   warp  16    MMA issuer    one thread issues tcgen05.mma.kind::tf32 (128 x BN x 8), A from TMEM (TS form)
+//                             or from a shared-memory descriptor; tcgen05.commit releases the stages
+//   warp  17    TMA issuer    cp.async.bulk.tensor.4d for K-major, 16-byte aligned, single-level operands
 //
 // The operands never need a packed / transposed copy in HBM: the producers read the caller's
 // strides (permuted views, unfolded conv windows, padded leading dimensions) and the Hadamard
@@ -23,9 +28,9 @@
 // same fp32 TMEM accumulator.  DSTAG_PREC_TF32 issues the single a_hi*b_hi pass.
 #include <cuda.h>   // CUtensorMap types only; cuTensorMapEncodeTiled is fetched at run time (no libcuda link)
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
-#include <cstdio>
 #include "common.cuh"
 
 namespace dstag {
