@@ -52,6 +52,8 @@ struct TcParams {
   int a_mode, b_mode;      // MODE_* (see Producer)
   int a_tma, b_tma;        // operand tile arrives by TMA (cp.async.bulk.tensor) instead of LDG
   int a_bdim[2], b_bdim[2];  // which of the two batch levels are real tensor-map dimensions
+  int a_rt;                  // output rows per M tile: 128, or fewer when the A tile is a ragged TMA box
+  int a_rag_d1;              // > 0: A rows are (x, t) windows loaded by a rank-3 box (32 k, d1 t, a_rt / d1 x)
 };
 
 struct alignas(64) TcMaps {
@@ -677,7 +679,7 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
       if (IS_A) {
         const float* ab = (const float*)g.A.ptr + axoff64(g.A.batch, pi.batch);
         const float* mb = g.Amul.ptr ? (const float*)g.Amul.ptr + axoff64(g.Amul.batch, pi.batch) : nullptr;
-        pr.begin_item(ab, mb, pi.tm * TC_BM, g.M);
+        pr.begin_item(ab, mb, pi.tm * p.a_rt, g.M);
       } else {
         pr.begin_item((const float*)g.B.ptr + axoff64(g.B.batch, pi.batch), nullptr, pi.tn * ROWS, g.N);
       }
@@ -769,11 +771,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int k0 = pos.kb * TC_BK;
         if (!AMUL && p.a_tma) {
           const int bl = p.a_bdim[1] ? pos.batch % g.A.batch.d1 : 0, bh = p.a_bdim[0] ? pos.batch / g.A.batch.d1 : 0;
-          mbar_expect_tx(rawa_bar + s, Cfg::A_PLANE);
+          mbar_expect_tx(rawa_bar + s, p.a_rt * 128);
           if (a_mn) {
 #pragma unroll
             for (int mb = 0; mb < TC_BM / 32; ++mb)
               tma_load_4d(st + mb * 4096, &maps.a, rawa_bar + s, pos.tm * TC_BM + mb * 32, k0, bl, bh);
+          } else if (p.a_rag_d1) {
+            // ragged tile: whole x's only -- box (32 k, d1 t, a_rt / d1 x) lands as a_rt consecutive tile rows
+            tma_load_4d(st, &maps.a, rawa_bar + s, k0, 0, pos.tm * (p.a_rt / p.a_rag_d1), bl);
           } else {
             tma_load_4d(st, &maps.a, rawa_bar + s, k0, pos.tm * TC_BM, bl, bh);
           }
@@ -873,8 +878,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const int tm = q % p.ntm;
       const int batch = q / p.ntm;
       const uint32_t acc = item & 1;
-      const int m = tm * TC_BM + q4 * 32 + lane;
-      const bool mok = m < g.M;
+      const int m = tm * p.a_rt + q4 * 32 + lane;               // tile rows beyond a_rt are padding of a ragged tile
+      const bool mok = q4 * 32 + lane < p.a_rt && m < g.M;
       float* Cb = (float*)g.C.ptr + axoff64(g.C.batch, batch);
       const float* Cab = (g.Cadd.ptr && ks == 0) ? (const float*)g.Cadd.ptr + axoff64(g.Cadd.batch, batch) : nullptr;
       const float* Cmb = g.Cmul.ptr ? (const float*)g.Cmul.ptr + axoff64(g.Cmul.batch, batch) : nullptr;
@@ -935,11 +940,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = rsub + 4 * i;
-            const int mr = tm * TC_BM + q4 * 32 + rr;
+            const int mr = tm * p.a_rt + q4 * 32 + rr;
             const int ro = __shfl_sync(0xffffffffu, c_ro, rr);
             const int rao = __shfl_sync(0xffffffffu, ca_ro, rr);
             const int rmo = __shfl_sync(0xffffffffu, cm_ro, rr);
-            if (mr < g.M) {
+            if (q4 * 32 + rr < p.a_rt && mr < g.M) {
               const float4 tv = *reinterpret_cast<const float4*>(tbuf + rr * 36 + 4 * q);
               float4 o = make_float4(g.alpha * tv.x, g.alpha * tv.y, g.alpha * tv.z, g.alpha * tv.w);
               if (Cab) {
@@ -971,11 +976,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const int cmo = (Cmb && nok) ? axoff32(g.Cmul.col, n) : 0;
 #pragma unroll 4
           for (int rr = 0; rr < 32; ++rr) {
-            const int mr = tm * TC_BM + q4 * 32 + rr;
+            const int mr = tm * p.a_rt + q4 * 32 + rr;
             const int ro = __shfl_sync(0xffffffffu, c_ro, rr);
             const int rao = __shfl_sync(0xffffffffu, ca_ro, rr);
             const int rmo = __shfl_sync(0xffffffffu, cm_ro, rr);
-            if (mr < g.M && nok) {
+            if (q4 * 32 + rr < p.a_rt && mr < g.M && nok) {
               float o = g.alpha * tbuf[rr * 33 + lane];
               if (Cab) o += __ldg(Cab + rao + cao);
               if (Cmb) o *= __ldg(Cmb + rmo + cmo);
@@ -1187,6 +1192,31 @@ static bool split_cols_to_batch(dstag_gemm_t& g) {
   return true;
 }
 
+// Ragged-tile map for an A operand whose rows are (x, t) windows of a channels-last activation (the GTU
+// convolutions): rows two-level with d1 = windows per node, K contiguous.  A tile takes whole nodes only:
+// a_rt = floor(128 / d1) * d1 rows, box (32 k, d1 t, a_rt / d1 x); the unused tile rows are never stored.
+static bool make_tmap_ragged(CUtensorMap* map, const dstag_gemm_t& g, int* a_rt) {
+  EncodeTiledFn enc = get_encode_tiled();
+  const dstag_operand_t& o = g.A;
+  if (!enc || !o.ptr || g.batch != 1) return false;
+  const dstag_axis_t& r = o.row;
+  const dstag_axis_t& k = o.col;
+  if (r.d1 < 2 || r.d1 > 128 || k.d1 != 1 || k.s0 != 1 || g.M % r.d1 != 0) return false;
+  if (r.s0 <= 0 || r.s1 <= 0 || r.s0 % 4 != 0 || r.s1 % 4 != 0 || (reinterpret_cast<uintptr_t>(o.ptr) & 15) != 0) return false;
+  const int xb = 128 / r.d1;
+  if (xb * r.d1 < 96) return false;                       // more than a quarter of the tile would be padding
+  cuuint64_t dims[4] = {(cuuint64_t)g.K, (cuuint64_t)r.d1, (cuuint64_t)(g.M / r.d1), 1};
+  cuuint64_t strides[3] = {(cuuint64_t)r.s1 * 4, (cuuint64_t)r.s0 * 4, (cuuint64_t)r.s0 * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)r.d1, (cuuint32_t)xb, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return false;
+  *a_rt = xb * r.d1;
+  return true;
+}
+
 static int g_num_sms = 0;
 
 template <int BN, bool X3, bool AMUL, bool ATM>
@@ -1218,7 +1248,28 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   if (!split_rows_to_batch(p.g)) split_cols_to_batch(p.g);
   const dstag_gemm_t* g = &p.g;
   const int bn = g->N > 64 ? 128 : (g->N > 32 ? 64 : 32);
-  p.ntm = (g->M + TC_BM - 1) / TC_BM;
+  p.a_mode = pick_mode(g->A, g->A.col, g->A.row, &g->Amul, &g->Amul.col, &g->Amul.row);
+  p.b_mode = pick_mode(g->B, g->B.row, g->B.col, nullptr, nullptr, nullptr);
+  const bool x3 = g->precision == DSTAG_PREC_TF32X3;
+  const bool am = g->Amul.ptr != nullptr;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
+  p.a_rt = TC_BM;
+  p.a_rag_d1 = 0;
+  p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
+  if (!p.a_tma && !am && p.a_mode == MODE_KVEC) {
+    static int special = -1;
+    if (special < 0) { const char* e = getenv("DSTAG_TC_TMA_SPECIAL"); special = (e && e[0] == '0') ? 0 : 1; }
+    int rt = 0;
+    if (special && make_tmap_ragged(&maps.a, *g, &rt)) {
+      p.a_tma = 1;
+      p.a_rt = rt;
+      p.a_rag_d1 = g->A.row.d1;
+    }
+  }
+  p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
+  p.ntm = (g->M + p.a_rt - 1) / p.a_rt;
   p.ntn = (g->N + bn - 1) / bn;
   p.kblocks = (g->K + TC_BK - 1) / TC_BK;
   int split = g->split_k < 1 ? 1 : g->split_k;
@@ -1228,22 +1279,14 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   const long long items = (long long)g->batch * p.ntm * p.ntn * p.nsplit;
   DSTAG_CHECK_ARG(items < (1ll << 31), "dstag_gemm(tc): too many tiles");
   p.total_items = (int)items;
-  p.a_mode = pick_mode(g->A, g->A.col, g->A.row, &g->Amul, &g->Amul.col, &g->Amul.row);
-  p.b_mode = pick_mode(g->B, g->B.row, g->B.col, nullptr, nullptr, nullptr);
-  const bool x3 = g->precision == DSTAG_PREC_TF32X3;
-  const bool am = g->Amul.ptr != nullptr;
-  TcMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
-  p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
-  p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
   {
     static int trace = -1;
     if (trace < 0) { const char* e = getenv("DSTAG_TC_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
     if (trace) {
       static const char* mn[] = {"KVEC", "MVEC", "ROWG", "KSC"};
       fprintf(stderr, "[dstag_gemm tc] M=%d N=%d K=%d batch=%d bn=%d A=%s%s%s B=%s%s split=%d acc=%d\n", g->M, g->N, g->K,
-              g->batch, bn, mn[p.a_mode], p.a_tma ? "+TMA" : "", am ? "+mul" : "", mn[p.b_mode], p.b_tma ? "+TMA" : "",
+              g->batch, bn, mn[p.a_mode], p.a_tma ? (p.a_rag_d1 ? "+TMA(ragged)" : "+TMA") : "",
+              am ? "+mul" : "", mn[p.b_mode], p.b_tma ? "+TMA" : "",
               p.nsplit, g->accumulate);
     }
   }
