@@ -505,7 +505,7 @@ struct PosIter {
 // B tiles, where the coupling of the two groups costs more than the balance gains.
 // A through tensor memory: thread (warp w, lane l) owns row 32 (w % 4) + l of the raw tile and the k half w / 4.
 template <class Cfg>
-__device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_major, uint32_t tmem_slot, int t) {
+__device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_major, bool plain, uint32_t tmem_slot, int t) {
   const int lane = t & 31, w = t >> 5;
   const int r = 32 * (w & 3) + lane, kh = w >> 2;
   uint32_t hi[16], lo[16];
@@ -527,7 +527,9 @@ __device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_majo
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       const int k = 16 * kh + kk, ka = k >> 2, kr = k & 3;
-      const uint32_t off = (uint32_t)(((ka * (TC_BM / 32) + mb) << 9) + (kr << 7) + (((q >> 1) ^ kr) << 5) + ((q & 1) << 4) + (e << 2));
+      const uint32_t off = plain ? (uint32_t)((mb << 12) + (k << 7) + ((r & 31) << 2))      // TMA boxes: [mb][k][32 rows]
+                                 : (uint32_t)(((ka * (TC_BM / 32) + mb) << 9) + (kr << 7) + (((q >> 1) ^ kr) << 5) +
+                                              ((q & 1) << 4) + (e << 2));
       const float v = *reinterpret_cast<const float*>(a_raw + off);
       hi[kk] = __float_as_uint(v);
       lo[kk] = __float_as_uint(tf32_lo(v));
@@ -542,7 +544,8 @@ __device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_majo
 
 template <class Cfg, int BN, bool X3, bool AMUL, bool IS_A>
 __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uint64_t* rawb, uint32_t ph, bool has_mul,
-                                             int t, int pt, int lane, uint32_t tmem_slot = 0, bool a_mn = false) {
+                                             int t, int pt, int lane, uint32_t tmem_slot = 0, bool a_mn = false,
+                                             bool a_plain = false) {
   if constexpr (Cfg::ATM) {
     // A warps: row split into tensor memory.  With a 128-row B tile all 12 warps then share B's split
     // (the 4 B warps alone would be the critical path); narrower B tiles stay with the B warps.
@@ -550,7 +553,7 @@ __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uin
     if (IS_A) {
       if (lane == 0) mbar_wait(rawa, ph, 0);
       __syncwarp();
-      finish_a_tmem<Cfg>(stage, a_mn, tmem_slot, t);
+      finish_a_tmem<Cfg>(stage, a_mn, a_plain, tmem_slot, t);
       if (!SHARE_B) return;
     }
     if (lane == 0) mbar_wait(rawb, ph, 0);
@@ -633,7 +636,7 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
   for (bool ok = pos.init(p); ok; ok = pos.next(p), ++it) {
     const int s = it % Cfg::STAGES;
     finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (it / Cfg::STAGES) & 1,
-                                          has_mul, t, pt, lane, tmem_base + Cfg::A_TM + s * 64, a_mn);
+                                          has_mul, t, pt, lane, tmem_base + Cfg::A_TM + s * 64, a_mn, a_mn && p.a_tma);
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar + s);
   }
@@ -694,7 +697,7 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
   while (okx) {
     const int s = nx % STAGES;
     finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (nx / STAGES) & 1, has_mul,
-                                          t, pt, lane, tmem_base + Cfg::A_TM + s * 64, p.a_mode == MODE_MVEC);
+                                          t, pt, lane, tmem_base + Cfg::A_TM + s * 64, p.a_mode == MODE_MVEC, false);
     __syncwarp();
     if (lane == 0) mbar_arrive(full_bar + s);
     okx = px.next(p);
@@ -1098,10 +1101,12 @@ static EncodeTiledFn get_encode_tiled() {
 // orientation.  Returns false when the view is not expressible (two-level row / K axis, odd strides).
 static bool make_tmap(CUtensorMap* map, int* bdim, const dstag_operand_t& o, const dstag_axis_t& kax,
                       const dstag_axis_t& rowax, int mode, long long K, long long rows, long long batch,
-                      int box_rows) {
+                      int box_rows, bool plain_mn = false) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc || !o.ptr) return false;
-  if (mode != MODE_KVEC) return false;   // MN-major tiles need 512-byte atoms per (k-atom, row block): LDG path
+  // MN-major tiles for the tensor core need 512-byte atoms per (k-atom, row block), which a tiled copy cannot
+  // produce; an A tile that goes through registers into tensor memory can take plain [k][32 rows] boxes
+  if (mode != MODE_KVEC && !(mode == MODE_MVEC && plain_mn)) return false;
   if (kax.d1 != 1 || rowax.d1 != 1) return false;
   const long long inner_n = mode == MODE_KVEC ? K : rows, outer_n = mode == MODE_KVEC ? rows : K;
   const long long outer_stride = mode == MODE_KVEC ? rowax.s0 : kax.s0;     // elements
@@ -1119,7 +1124,7 @@ static bool make_tmap(CUtensorMap* map, int* bdim, const dstag_operand_t& o, con
                            bdim[0] ? (cuuint64_t)s_hi * 4 : dummy};
   cuuint32_t box[4] = {32u, (cuuint32_t)(mode == MODE_KVEC ? box_rows : 32), 1u, 1u};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  const CUtensorMapSwizzle sw = mode == MODE_KVEC ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUtensorMapSwizzle sw = mode == MODE_KVEC ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(o.ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1258,6 +1263,11 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   p.a_rt = TC_BM;
   p.a_rag_d1 = 0;
   p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
+  static int mn_tma = -1;
+  if (mn_tma < 0) { const char* e = getenv("DSTAG_TC_TMA_MN"); mn_tma = (e && e[0] == '0') ? 0 : 1; }
+  if (!p.a_tma && !am && x3 && mn_tma && p.a_mode == MODE_MVEC &&
+      make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM, true))
+    p.a_tma = 1;                         // MN-major A by TMA: only valid together with A through tensor memory
   if (!p.a_tma && !am && p.a_mode == MODE_KVEC) {
     static int special = -1;
     if (special < 0) { const char* e = getenv("DSTAG_TC_TMA_SPECIAL"); special = (e && e[0] == '0') ? 0 : 1; }
@@ -1294,7 +1304,7 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   // tile would need 16 scalar loads per thread and stays on the shared-memory operand path
   static int atm_on = -1;
   if (atm_on < 0) { const char* e = getenv("DSTAG_TC_ATM"); atm_on = e ? atoi(e) : 1; }
-  const bool atm = atm_on && x3 && !am && (p.a_mode != MODE_MVEC || atm_on == 2);
+  const bool atm = (atm_on && x3 && !am && (p.a_mode != MODE_MVEC || atm_on == 2)) || (p.a_mode == MODE_MVEC && p.a_tma);
 #define DSTAG_TC_DISPATCH(BN_)                                                                     \
   return x3 ? (am ? launch_tc<BN_, true, true, false>(p, maps, stream)                                            \
                   : (atm ? launch_tc<BN_, true, false, true>(p, maps, stream)                                    \
