@@ -996,16 +996,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           __syncwarp();
         } else if (mok) {
-          // (c) column-strided output (e.g. M-contiguous conv layouts): lanes walk rows
+          // (c) column-strided output (rows contiguous in memory: consecutive lanes = consecutive rows, so
+          //     every store instruction still writes whole lines): lanes walk rows, column offsets stepped
+          //     without divisions
+          Walk wc, wa, wm;
+          wc.init(g.C.col, n0, 1);
+          if (Ca) wa.init(g.Cadd.col, n0, 1);
+          if (Cm) wm.init(g.Cmul.col, n0, 1);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
+            const int co = wc.off, cao = Ca ? wa.off : 0, cmo = Cm ? wm.off : 0;
+            wc.next();
+            if (Ca) wa.next();
+            if (Cm) wm.next();
             if (n < g.N) {
               float o = g.alpha * v[j];
-              if (Ca) o += __ldg(Ca + axoff32(g.Cadd.col, n));
-              if (Cm) o *= __ldg(Cm + axoff32(g.Cmul.col, n));
+              if (Ca) o += __ldg(Ca + cao);
+              if (Cm) o *= __ldg(Cm + cmo);
               if (g.relu) o = fmaxf(o, 0.f);
-              float* dst = C + axoff32(g.C.col, n);
+              float* dst = C + co;
               if (g.accumulate == DSTAG_ACC_STORE) *dst = o;
               else if (g.accumulate == DSTAG_ACC_ADD) *dst += o;
               else atomicAdd(dst, o);

@@ -238,6 +238,225 @@ static int launch_sat_rows(const float* qk, const float* biasT, const float* tkT
   DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd(rows)");
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core variant for d_k = 32 and ld <= 1024 (every PEMS / drought graph size).  The K = 32 logit
+// products are far too thin for the tcgen05 engine (one k-block, 883 accumulator columns per row against
+// 512 TMEM columns) but they are what bounds the SIMT variant above (one shared-memory float per 4 FMAs =
+// the shared-memory roofline).  Here a CTA of 8 warps owns 16 output rows j of one (b, k); warp w owns the
+// 8-column tiles {w, w+8, ...} of the complete logit rows as m16n8k8 accumulator fragments (4*NT registers
+// per thread) and computes them as 3xTF32 (hi.hi + hi.lo + lo.hi with truncation splits: fp32-level
+// accuracy).  No shared-memory staging at all: the fragments' K index is permuted (thread tg takes the
+// physical components {4tg..4tg+3, 16+4tg..16+4tg+3}) so both operands are plain float4 loads of whole
+// 128-byte projection rows, and the W_Q rows stay L1-resident across the row groups a CTA walks.
+// Row max / sum: quad shuffles + an 8-way cross-warp reduction through 1 KB of shared memory; the fragment
+// layout gives every quad one full 32-byte sector of P, TP, biasT and tkT per row.
+// ---------------------------------------------------------------------------------------
+constexpr int kSatMmaThreads = 256;
+constexpr int kSatMmaRows = 16;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;                     // the 19 bits the tensor core reads
+  lo = __float_as_uint(v - __uint_as_float(hi));             // exact remainder
+}
+
+constexpr int kSatRing = 4;
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;                                    // 0 source bytes: the slot is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+
+constexpr int kSatRingBytes = (kSatMmaThreads / 32) * kSatRing * 2 * 32 * 16;   // lane-private W_Q slots
+constexpr int kSatRedBytes = 2 * kSatMmaRows * 8 * 4;
+__host__ __device__ constexpr int sat_mma_pitch(int nt) { return 64 * nt + 8; }   // = 8 (mod 32): conflict-free LDS.64
+__host__ __device__ constexpr size_t sat_mma_smem(int nt) {
+  return (size_t)kSatRingBytes + kSatRedBytes + (size_t)kSatMmaRows * sat_mma_pitch(nt) * 4;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kSatMmaThreads, 2)
+sat_softmax_mma_kernel(const float* __restrict__ qk, const float* __restrict__ biasT, const float* __restrict__ tkT,
+                       float* __restrict__ P, float* __restrict__ TP, int N, int K, int ld, float scale) {
+  constexpr int DK = 32;
+  constexpr int PITCH = sat_mma_pitch(NT);
+  extern __shared__ __align__(16) unsigned char sat_smem[];
+  auto qring = reinterpret_cast<float4(*)[kSatRing][2][32]>(sat_smem);
+  auto red = reinterpret_cast<float(*)[kSatMmaRows][8]>(sat_smem + kSatRingBytes);
+  float* rows_s = reinterpret_cast<float*>(sat_smem + kSatRingBytes + kSatRedBytes);   // [16][PITCH]: bias, then T_k
+  const int bk = blockIdx.y, b = bk / K, k = bk - b * K;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const long long nstride = 2LL * K * DK;                         // qk: (B, N, 2, K, dk)
+  const float* qbase = qk + (long long)b * N * nstride + (long long)k * DK + 4 * tg;
+  const float* kbase = qbase + (long long)K * DK;
+  const int j0 = blockIdx.x * kSatMmaRows;
+
+  // The 16 bias rows (and later the 16 T_k rows) of the strip travel to shared memory asynchronously: warp w
+  // copies rows w and w + 8 in 16-byte pieces.  Fetched through registers these loads sat behind their uses
+  // at 16 warps per SM and cost a full L2 round trip each -- 3/4 of the kernel's time in the first version.
+  auto copy_rows = [&](const float* src) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = w + 8 * h;
+      const float* srow = src + ((long long)k * N + min(j0 + r, N - 1)) * ld;
+      float* drow = rows_s + r * PITCH;
+      for (int c = 4 * lane; c < ld; c += 128) cp_async16_zfill(drow + c, srow + c, true);
+    }
+  };
+  copy_rows(biasT);
+  cp_async_commit();
+
+  // A fragments (W_K rows j0+g, j0+g+8), split once
+  uint32_t ah[4][4], al[4][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = j0 + g + 8 * h;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+    if (j < N) {
+      const float* p = kbase + (long long)j * nstride;
+      x = __ldg(reinterpret_cast<const float4*>(p));
+      y = __ldg(reinterpret_cast<const float4*>(p + 16));
+    }
+    const float e[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      split_tf32(e[2 * s], ah[s][h], al[s][h]);
+      split_tf32(e[2 * s + 1], ah[s][2 + h], al[s][2 + h]);
+    }
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+
+  // W_Q fragments: every lane fetches exactly the two 16-byte pieces it consumes itself, kSatRing - 1 column
+  // tiles ahead, with cp.async into lane-private shared-memory slots -- an asynchronous register prefetch that
+  // costs no registers and needs no barrier (cp.async.ca keeps the rows in L1 for the other warps and CTAs).
+  auto issue_q = [&](int t) {
+    const int i = 8 * (t * 8 + w) + g;
+    const bool ok = i < N;
+    const float* p = qbase + (long long)(ok ? i : 0) * nstride;
+    float4* slot = &qring[w][t % kSatRing][0][lane];
+    cp_async16_zfill(slot, p, ok);
+    cp_async16_zfill(slot + 32, p + 16, ok);
+  };
+#pragma unroll
+  for (int t = 0; t < kSatRing - 1; ++t) {
+    if (t < NT) issue_q(t);
+    cp_async_commit();
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    if (t + kSatRing - 1 < NT) issue_q(t + kSatRing - 1);
+    cp_async_commit();
+    cp_async_wait<kSatRing - 1>();                                  // tile t (and the older bias group) landed
+    const float4 qa = qring[w][t % kSatRing][0][lane], qb = qring[w][t % kSatRing][1][lane];
+    const float e[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      uint32_t b0h, b0l, b1h, b1l;
+      split_tf32(e[2 * s], b0h, b0l);
+      split_tf32(e[2 * s + 1], b1h, b1l);
+      mma_tf32_16x8x8(acc[t], al[s], b0h, b1h);                   // small terms first
+      mma_tf32_16x8x8(acc[t], ah[s], b0l, b1l);
+      mma_tf32_16x8x8(acc[t], ah[s], b0h, b1h);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                                  // every warp's share of the bias rows is visible
+
+  // logits = acc * scale + bias, masked beyond N; row max
+  const int cw = 8 * w + 2 * tg;                                    // this thread's column within every 64-column group
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float* brow = rows_s + (g + 8 * h) * PITCH + cw;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int c = cw + 64 * t;
+      const float2 bb = *reinterpret_cast<const float2*>(brow + 64 * t);
+      const float v0 = c < N ? fmaf(acc[t][2 * h], scale, bb.x) : -INFINITY;
+      const float v1 = c + 1 < N ? fmaf(acc[t][2 * h + 1], scale, bb.y) : -INFINITY;
+      acc[t][2 * h] = v0;
+      acc[t][2 * h + 1] = v1;
+      mx = fmaxf(mx, fmaxf(v0, v1));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (tg == 0) red[0][g + 8 * h][w] = mx;
+  }
+  __syncthreads();                                                  // maxima published, bias rows consumed
+  if (TP) copy_rows(tkT);                                           // T_k rows land behind the exponentials
+  cp_async_commit();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 m0 = *reinterpret_cast<const float4*>(&red[0][g + 8 * h][0]);
+    const float4 m1 = *reinterpret_cast<const float4*>(&red[0][g + 8 * h][4]);
+    const float mx = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float e0 = __expf(acc[t][2 * h] - mx), e1 = __expf(acc[t][2 * h + 1] - mx);   // exp(-inf) = 0
+      acc[t][2 * h] = e0;
+      acc[t][2 * h + 1] = e1;
+      sum += e0 + e1;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (tg == 0) red[1][g + 8 * h][w] = sum;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = j0 + g + 8 * h;
+    if (j >= N) continue;
+    const float4 s0 = *reinterpret_cast<const float4*>(&red[1][g + 8 * h][0]);
+    const float4 s1 = *reinterpret_cast<const float4*>(&red[1][g + 8 * h][4]);
+    const float inv = 1.f / (((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w)));
+    float* prow = P + (((long long)b * K + k) * N + j) * ld + cw;
+    float* tprow = TP + (((long long)b * K + k) * N + j) * ld + cw;
+    const float* trow = rows_s + (g + 8 * h) * PITCH + cw;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (cw + 64 * t < ld) {
+        const float2 pv = make_float2(acc[t][2 * h] * inv, acc[t][2 * h + 1] * inv);
+        *reinterpret_cast<float2*>(prow + 64 * t) = pv;
+        if (TP) {
+          const float2 tv = *reinterpret_cast<const float2*>(trow + 64 * t);
+          *reinterpret_cast<float2*>(tprow + 64 * t) = make_float2(pv.x * tv.x, pv.y * tv.y);
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static int launch_sat_mma(const float* qk, const float* biasT, const float* tkT, float* P, float* TP, int B, int N,
+                          int K, int ld, float scale, cudaStream_t stream) {
+  static bool configured = false;                                   // per instantiation
+  const size_t smem = sat_mma_smem(NT);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sat_softmax_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("dstag_sat_softmax_fwd(mma): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const dim3 grid((N + kSatMmaRows - 1) / kSatMmaRows, B * K);
+  sat_softmax_mma_kernel<NT><<<grid, kSatMmaThreads, smem, stream>>>(qk, biasT, tkT, P, TP, N, K, ld, scale);
+  DSTAG_RETURN_LAUNCH("dstag_sat_softmax_fwd(mma)");
+}
+
 }  // namespace dstag
 
 using namespace dstag;
@@ -257,6 +476,22 @@ extern "C" int dstag_sat_softmax_fwd(const float* qk, const float* biasT, const 
   const int nt = (ld + kSatTileI - 1) / kSatTileI;
   const bool rows_ok = nt <= 8 && dk % 4 == 0 && (size_t)dk * (kSatRowsCta + kSatQld) * 4 <= 48 * 1024 &&
                        (reinterpret_cast<uintptr_t>(qk) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+  // DSTAG_SAT_MMA=0 keeps the SIMT variants (A/B measurements)
+  static const int mma_on = [] { const char* e = getenv("DSTAG_SAT_MMA"); return e ? atoi(e) : 1; }();
+  if (mma_on && rows_ok && dk == 32) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt64 = (ld + 63) / 64;
+#define DSTAG_SAT_MMA_CASE(NT_) \
+  case NT_: return launch_sat_mma<NT_>(qk, biasT, tkT, P, TP, B, N, K, ld, scale, st)
+    switch (nt64) {
+      DSTAG_SAT_MMA_CASE(1); DSTAG_SAT_MMA_CASE(2); DSTAG_SAT_MMA_CASE(3); DSTAG_SAT_MMA_CASE(4);
+      DSTAG_SAT_MMA_CASE(5); DSTAG_SAT_MMA_CASE(6); DSTAG_SAT_MMA_CASE(7); DSTAG_SAT_MMA_CASE(8);
+      DSTAG_SAT_MMA_CASE(9); DSTAG_SAT_MMA_CASE(10); DSTAG_SAT_MMA_CASE(11); DSTAG_SAT_MMA_CASE(12);
+      DSTAG_SAT_MMA_CASE(13); DSTAG_SAT_MMA_CASE(14); DSTAG_SAT_MMA_CASE(15);
+      default: DSTAG_SAT_MMA_CASE(16);
+    }
+#undef DSTAG_SAT_MMA_CASE
+  }
   if (rows_ok) {
     cudaStream_t st = (cudaStream_t)stream;
     switch (nt) {

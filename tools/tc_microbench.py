@@ -43,6 +43,9 @@ def main():
         ("cheb_bwd_dx", "bkji,kbje->bie", P[..., :N], Z, {}),
         ("cheb_bwd_dmap", "kbje,bie->bkji", Z, x3, dict(out=dS[..., :N])),
         ("cheb_fwd_amul", "bkji,bie->kbje", P[..., :N], x3, dict(a_mul=("kji", Tk[..., :N]))),
+        # orientation experiment: the row-contiguous operand first (MN-major A by TMA through TMEM, K-major B by TMA)
+        ("cheb_fwd_swap", "bie,bkji->kbje", x3, P[..., :N], dict(noswap=True)),
+        ("qkv_dx_swap", "on,ro->rn", Wqkv, r(B * FT, 3 * H * dk), dict(out=rp(B * FT, N), noswap=True)),
         ("sat_scores", "bjkd,bikd->bkji", qk[:, :, 1], qk[:, :, 0], dict(out=dS[..., :N], alpha=1 / math.sqrt(dk))),
         ("sat_dq", "bkji,bjkd->bikd", dS[..., :N], qk[:, :, 1], {}),
         ("sat_dk", "bkji,bikd->bjkd", dS[..., :N], qk[:, :, 0], {}),
@@ -82,6 +85,7 @@ def main():
         if a.only and not any(o == name or (o.endswith("*") and name.startswith(o[:-1])) for o in a.only.split(",")):
             continue
         kw = dict(kw)
+        noswap = kw.pop("noswap", False)
         out = kw.get("out")
         if out is None:
             out = torch.empty(ct.output_shape(spec, A, Bm), device=dev)
@@ -97,7 +101,12 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            if noswap:
+                saved = ct._prefers_swap
+                ct._prefers_swap = lambda *a, **k: False
             ct.contract_raw(spec, A, Bm, precision=prec, **kw)
+            if noswap:
+                ct._prefers_swap = saved
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
