@@ -327,12 +327,18 @@ ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __r
     for (int i = 0; i < NV; ++i) {
       const int c = 4 * (lane + 32 * i);
       if (c < L) {
-        float o[4];
+        float o[4], dm[4] = {1.f, 1.f, 1.f, 1.f};
+        if (drop_p > 0.f) {
+          const unsigned long long e0 = (unsigned long long)r * L + c;
+          if ((e0 & 3) == 0) {                                     // warp-uniform: one Philox per float4
+            dropout_scale4(e0, seed, drop_p, inv_keep, dm);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o[j] = fmaf((v[i][j] - mu) * rs, gm[i][j], bt[i][j]);
-          if (drop_p > 0.f) o[j] *= dropout_scale((unsigned long long)r * L + c + j, seed, drop_p, inv_keep);
+            for (int j = 0; j < 4; ++j) dm[j] = dropout_scale(e0 + j, seed, drop_p, inv_keep);
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf((v[i][j] - mu) * rs, gm[i][j], bt[i][j]) * dm[j];
         *reinterpret_cast<float4*>(yp + c) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -340,8 +346,11 @@ ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __r
   }
 }
 
+// 128-thread CTAs: the per-lane d gamma / d beta accumulators make this kernel register-heavy (162 registers at
+// NV = 4), and 4-warp CTAs pack 3 per SM (12 warps) where 8-warp CTAs fit once.
+constexpr int kLnBwdThreads = 128;
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kLnBwdThreads, NV <= 4 ? 3 : 2)
 ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ a, long long a_ld,
                    const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dpre,
@@ -385,11 +394,20 @@ ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* _
       }
       const float xv[4] = {x.x, x.y, x.z, x.w};
       const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      float dm[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop_p > 0.f && c < L) {
+        const unsigned long long e0 = (unsigned long long)r * L + c;
+        if ((e0 & 3) == 0) {                                       // warp-uniform: one Philox per float4
+          dropout_scale4(e0, seed, drop_p, inv_keep, dm);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dm[j] = dropout_scale(e0 + j, seed, drop_p, inv_keep);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool ok = c + j < L;
-        float d = ok ? dv[j] : 0.f;
-        if (drop_p > 0.f && ok) d *= dropout_scale((unsigned long long)r * L + c + j, seed, drop_p, inv_keep);
+        const float d = ok ? dv[j] * dm[j] : 0.f;
         const float xn = ok ? (xv[j] - mu) * rs : 0.f;
         const float g = d * gm[i][j];
         xh[i][j] = xn;
@@ -552,12 +570,14 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
                     reinterpret_cast<uintptr_t>(tab)) & 15) == 0 &&
                   a_s0 >= lq && dy_ld >= lq && dpre_ld >= lq && (tab == nullptr || tab_ld >= lq);
   if (al && nv <= 8) {
-    const int blocks = (rows + 7) / 8;
-    const int grid = blocks < kNumSMs * 2 ? blocks : kNumSMs * 2;
+    const int wpc = kLnBwdThreads / 32;
+    const int blocks = (rows + wpc - 1) / wpc;
+    const int resident = kNumSMs * (nv <= 4 ? 3 : 2);
+    const int grid = blocks < resident ? blocks : resident;
     const size_t sm_bytes = (size_t)2 * 128 * nv * sizeof(float);
 #define DSTAG_LN_BWD(NV_)                                                                                        \
   case NV_:                                                                                                      \
-    ln_bwd_warp_kernel<NV_><<<grid, 256, sm_bytes, (cudaStream_t)stream>>>(                                      \
+    ln_bwd_warp_kernel<NV_><<<grid, kLnBwdThreads, sm_bytes, (cudaStream_t)stream>>>(                                      \
         dy, dy_ld, a, a_s0, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed); \
     break
     switch (nv) {
