@@ -198,6 +198,41 @@ def test_spatial_cheb_conv(dev, precision, cfg):
     assert float(gr[1][..., N:].abs().max()) == 0.0 if ld > N else True
 
 
+@pytest.mark.parametrize("cfg", [(1, 1, 1, 32), (2, 15, 3, 32), (2, 16, 1, 32), (3, 17, 2, 32), (2, 64, 3, 32),
+                                 (1, 65, 2, 32), (2, 307, 3, 32), (1, 1021, 2, 32), (1, 1024, 1, 32),
+                                 (2, 50, 2, 16), (1, 1030, 1, 32)])
+@pytest.mark.parametrize("with_tp", [True, False])
+def test_sat_softmax_fwd_kernel(dev, cfg, with_tp):
+    """dstag_sat_softmax_fwd alone through the C ABI: the tensor-core variant (d_k = 32, ld <= 1024) at ragged
+    strip / tile sizes, the SIMT rows kernel (d_k = 16) and the shared-memory strips (ld > 1024); P and
+    T_k (.) P against an fp64 evaluation, zero padding columns, rows of P sum to 1.  Tolerance 2e-6 absolute
+    (probabilities <= 1; 3xTF32 logits with K = 32)."""
+    from dstagnn_drought_b200 import _lib
+    Bz, N, K, dk = cfg
+    ld = (N + 3) // 4 * 4
+    lib = _lib.load()
+    torch.manual_seed(11)
+    qk = torch.randn(Bz, N, 2, K, dk, device=dev)
+    bias = torch.zeros(K, N, ld, device=dev)
+    bias[..., :N] = torch.randn(K, N, N, device=dev)
+    tk = torch.zeros(K, N, ld, device=dev)
+    tk[..., :N] = torch.randn(K, N, N, device=dev)
+    P = torch.full((Bz, K, N, ld), float("nan"), device=dev)
+    TP = torch.full((Bz, K, N, ld), float("nan"), device=dev) if with_tp else None
+    _lib.check(lib.dstag_sat_softmax_fwd(qk.data_ptr(), bias.data_ptr(), tk.data_ptr(), P.data_ptr(),
+                                         TP.data_ptr() if with_tp else None, Bz, N, K, dk, ld, _lib.stream_ptr(P)),
+               "dstag_sat_softmax_fwd")
+    s = torch.einsum("bjkd,bikd->bkji", qk[:, :, 1].double(), qk[:, :, 0].double()) / math.sqrt(dk) + bias[..., :N].double()
+    ref = torch.softmax(s, dim=-1)
+    assert float((P[..., :N].double() - ref).abs().max()) < 2e-6
+    assert float((P[..., :N].double().sum(-1) - 1).abs().max()) < 1e-5
+    assert bool((P[..., N:] == 0).all())
+    if with_tp:
+        want = ref * tk[..., :N].double()
+        assert float((TP[..., :N].double() - want).abs().max()) < 2e-6 * max(1.0, float(tk.abs().max()))
+        assert bool((TP[..., N:] == 0).all())
+
+
 @pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144)])
 def test_gtu_stack(dev, precision, cfg):
     from dstagnn_drought_b200.ops import GtuStack
