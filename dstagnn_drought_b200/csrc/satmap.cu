@@ -5,9 +5,13 @@
 //
 //   P[b, k, j, i] = softmax_i( Qs[b,i,k,:] . Ks[b,j,k,:] / sqrt(dk) + biasT[k, j, i] )
 //
-// A CTA owns a strip of R output nodes j of one (b, k): the R x N logits live in shared memory
-// (never in HBM), the Qs tiles stream through a second buffer, and every row is normalised and
-// written once -- N x N x 4 bytes of HBM traffic per map instead of 3x that for a GEMM + softmax pair.
+// A CTA owns a strip of output nodes j of one (b, k); the logits of the strip never reach HBM and every
+// row is normalised and written once -- N x N x 4 bytes of HBM traffic per map instead of 3x that for a
+// GEMM + softmax pair.  Three variants, chosen by the launcher at the bottom:
+//   sat_softmax_mma_kernel   d_k = 32, ld <= 1024 (every dataset): logits as warp-level tensor-core MMA
+//                            fragments (3xTF32), bias / T_k rows and W_Q pieces by cp.async
+//   sat_softmax_rows_kernel  other d_k, ld <= 1024: a warp keeps 4 complete logit rows in registers (SIMT)
+//   sat_softmax_fwd_kernel   ld > 1024: R x N logits of the strip in shared memory (SIMT)
 #include "common.cuh"
 
 namespace dstag {
