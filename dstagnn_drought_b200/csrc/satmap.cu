@@ -446,15 +446,17 @@ sat_softmax_mma_kernel(const float* __restrict__ qk, const float* __restrict__ b
 template <int NT>
 static int launch_sat_mma(const float* qk, const float* biasT, const float* tkT, float* P, float* TP, int B, int N,
                           int K, int ld, float scale, cudaStream_t stream) {
-  static bool configured = false;                                   // per instantiation
+  static int configured_dev = -1;                                   // per instantiation; the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
   const size_t smem = sat_mma_smem(NT);
-  if (!configured) {
+  if (dev != configured_dev) {
     cudaError_t e = cudaFuncSetAttribute(sat_softmax_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("dstag_sat_softmax_fwd(mma): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured_dev = dev;
   }
   const dim3 grid((N + kSatMmaRows - 1) / kSatMmaRows, B * K);
   sat_softmax_mma_kernel<NT><<<grid, kSatMmaThreads, smem, stream>>>(qk, biasT, tkT, P, TP, N, K, ld, scale);
