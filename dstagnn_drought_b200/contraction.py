@@ -138,6 +138,8 @@ def _k_order(pl: Plan, A, B):
 
 
 _desc_cache = {}
+_swap_cache = {}
+_dims_cache = {}
 
 
 def _layout_key(t):
@@ -293,13 +295,23 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                  relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
                  precision=None, tag: Optional[str] = None) -> torch.Tensor:
     """Enqueue one contraction on the current CUDA stream.  No autograd."""
-    if a_mul is None and _prefers_swap(spec, out, A, B):
-        # C = A.B is symmetric in its operands; put the one that owns the output's innermost index
-        # second, so that index becomes the GEMM's n (contiguous, coalesced epilogue stores)
-        ins, res = spec.replace(" ", "").split("->")
-        sa, sb = ins.split(",")
-        return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
-                            accumulate=accumulate, split_k=split_k, precision=precision, tag=tag)
+    if a_mul is None:
+        # a training step repeats the same ~100 contractions with the same layouts: the orientation decision
+        # and the problem sizes are memoised per (spec, layouts) -- host time matters at the small graph
+        # sizes, where the step is launch bound
+        skey = (spec, A.shape, A.stride(), B.shape, B.stride(), _layout_key(out))
+        swap = _swap_cache.get(skey)
+        if swap is None:
+            swap = _prefers_swap(spec, out, A, B)
+            if len(_swap_cache) < 4096:
+                _swap_cache[skey] = swap
+        if swap:
+            # C = A.B is symmetric in its operands; put the one that owns the output's innermost index
+            # second, so that index becomes the GEMM's n (contiguous, coalesced epilogue stores)
+            ins, res = spec.replace(" ", "").split("->")
+            sa, sb = ins.split(",")
+            return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
+                                accumulate=accumulate, split_k=split_k, precision=precision, tag=tag)
     lib = _lib.load()
     _check(A, "A"), _check(B, "B")
     for opt in (a_mul, c_add, c_mul):
@@ -310,9 +322,15 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             raise ValueError("accumulating contraction needs an explicit out=")
         out = torch.empty(output_shape(spec, A, B), device=A.device, dtype=torch.float32)
     _check(out, "out")
-    pl = plan(spec)
-    size = _sizes(pl, A, B, ((pl.c, out),))
-    M, N, K, nb = _prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size), _prod(pl.batch, size)
+    dkey = (spec, A.shape, B.shape, out.shape)
+    dims = _dims_cache.get(dkey)
+    if dims is None:
+        pl = plan(spec)
+        size = _sizes(pl, A, B, ((pl.c, out),))                    # also validates the shapes against the spec
+        dims = (_prod(pl.m, size), _prod(pl.n, size), _prod(pl.k, size), _prod(pl.batch, size))
+        if len(_dims_cache) < 4096:
+            _dims_cache[dkey] = dims
+    M, N, K, nb = dims
     if split_k is None:
         split_k = 1 if relu else auto_split_k(M, N, K, nb)
     if split_k > 1:

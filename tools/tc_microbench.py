@@ -104,9 +104,11 @@ def main():
             if noswap:
                 saved = ct._prefers_swap
                 ct._prefers_swap = lambda *a, **k: False
+                ct._swap_cache.clear()
             ct.contract_raw(spec, A, Bm, precision=prec, **kw)
             if noswap:
                 ct._prefers_swap = saved
+                ct._swap_cache.clear()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
