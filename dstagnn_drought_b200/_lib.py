@@ -13,10 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_SMEM = -1, -2, -3      # DSTAG_ERR_* of include/dstagnn_b200.h
 
 
 class Axis(C.Structure):
@@ -32,7 +33,8 @@ class Gemm(C.Structure):
                 ("A", Operand), ("B", Operand), ("C", Operand),
                 ("Amul", Operand), ("Cmul", Operand), ("Cadd", Operand),
                 ("alpha", C.c_float), ("relu", C.c_int32), ("accumulate", C.c_int32),
-                ("split_k", C.c_int32), ("precision", C.c_int32), ("pad_", C.c_int32)]
+                ("split_k", C.c_int32), ("precision", C.c_int32), ("pad_", C.c_int32),
+                ("split_stride", C.c_int64)]
 
 
 _F = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
@@ -50,6 +52,7 @@ SIGNATURES = {
                                       _i32, _i32, _f32, _u64, _F]),
     "dstag_layernorm_bwd": (C.c_int, [_F, _i64, _F, _i64, _i64, _i32, _i64, _F, _i32, _i64, _F, _F, _F, _F, _i64,
                                       _F, _F, _i32, _i32, _f32, _u64, _F]),
+    "dstag_sum_slices": (C.c_int, [_F, _i64, _i32, _F, _i64, _i64, _i64, _F]),
     "dstag_colsum": (C.c_int, [_F, _F, _i64, _i64, _i64, _F]),
     "dstag_transpose": (C.c_int, [_F, _i64, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_softmax_fwd": (C.c_int, [_F, _i64, _i32, _i32, _F]),
@@ -114,17 +117,62 @@ class _Profiled:
     @staticmethod
     def _wrap(name, fn):
         def call(*args):
-            if _prof is None:
-                return fn(*args)
-            with prof_range(name):
-                return fn(*args)
+            with on_device(args[-1]):
+                if _prof is None:
+                    return fn(*args)
+                with prof_range(name):
+                    return fn(*args)
         return call
 
 
+class StreamHandle(C.c_void_p):
+    """cudaStream_t as a void* that remembers which device it belongs to."""
+    device_index = -1
+
+
 def stream_ptr(t):
-    """cudaStream_t of torch's current stream on t's device, as a void*."""
+    """cudaStream_t of torch's current stream on t's device, as a void* tagged with the device."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    h = StreamHandle(torch.cuda.current_stream(t.device).cuda_stream)
+    h.device_index = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return h
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(stream):
+    """Kernel launches go to the CURRENT CUDA device; the operands' device must be the current one while
+    an entry point enqueues (a stream handle of device 1 launched on device 0 is an illegal access, or --
+    with peer access enabled -- a silent launch on the wrong GPU).  Returns a no-op guard in the common
+    case (already current) and ``torch.cuda.device(idx)`` otherwise, so models living on ``cuda:k`` work
+    without the caller having to ``torch.cuda.set_device(k)``."""
+    import torch
+    idx = getattr(stream, "device_index", -1)
+    if idx < 0 or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
+
+
+def same_device(*tensors):
+    """Raise unless all (non-None) tensors live on one CUDA device."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"dstagnn_drought_b200: operands on different devices ({dev} and {t.device})")
+    return dev
 
 
 # ---- optional per-kernel CUDA-event profiler (bench.py / profiling only) -----------------------

@@ -17,6 +17,7 @@ hand-written autograd Functions of ``ops.py``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -140,6 +141,24 @@ def _k_order(pl: Plan, A, B):
 _desc_cache = {}
 _swap_cache = {}
 _dims_cache = {}
+_reproducible = os.environ.get("DSTAG_REPRODUCIBLE", "1") != "0"      # A/B switch for measurements
+
+
+def set_reproducible(on: bool):
+    """Module default of ``contract_raw(reproducible=None)``: True (default) = split reductions go through
+    a workspace and a fixed-order sum; False = atomic accumulation (results vary in the last bits from run
+    to run).  The differentiable ``contract`` always runs its FORWARD product reproducibly."""
+    global _reproducible
+    _reproducible = bool(on)
+
+
+def _workspace(n: int, out: torch.Tensor) -> torch.Tensor:
+    """(n, *out.shape) contiguous scratch for the partial results of a two-stage reduction; the slice stride
+    is kept a multiple of 4 floats so that the engine's 16-byte store paths stay available."""
+    numel = out.numel()
+    stride = (numel + 3) // 4 * 4
+    buf = torch.empty(n * stride, device=out.device, dtype=torch.float32)
+    return buf.as_strided((n,) + tuple(out.shape), (stride,) + tuple(torch.empty(out.shape, device="meta").stride()))
 
 
 def _layout_key(t):
@@ -215,22 +234,26 @@ def _build_descriptor(spec: str, A, B, out, a_mul, c_add, c_mul, alpha, relu, ac
     return g
 
 
-def _fold_k_outer_into_batch(g: Gemm) -> bool:
+def _fold_k_outer_into_batch(g: Gemm, dry: bool = False) -> int:
     """A reduction index (b, n) whose inner level is contiguous but of odd length (N = 883 nodes) cannot
     be walked in aligned 32-wide k-blocks.  Such a problem equals a batch over the outer level whose
-    members all accumulate (atomically) into the same output: K' = d1, batch' = K / d1, C batch stride 0.
-    Restores the 16-byte operand load paths for the pre_conv weight gradient.  Rewrites g in place."""
+    members all accumulate into the same output: K' = d1, batch' = K / d1, C batch stride 0 with atomic
+    adds -- or, for a reproducible result, one output slice per member (the caller sets C's batch stride
+    and sums the slices afterwards).  Restores the 16-byte operand load paths for the pre_conv weight
+    gradient.  Rewrites g in place (unless ``dry``); returns the number of members (0 = not applicable)."""
     if g.batch != 1 or g.relu or g.Cadd.ptr or g.Cmul.ptr or g.Amul.ptr:
-        return False
+        return 0
     ka, kb = g.A.col, g.B.row
     d1 = max(ka.d1, kb.d1)
     if d1 < 64 or g.K % d1 or any(ax.d1 not in (1, d1) for ax in (ka, kb)):
-        return False
+        return 0
     if not ((ka.d1 == d1 and ka.s1 == 1) or (kb.d1 == d1 and kb.s1 == 1)):
-        return False
+        return 0
     q = g.K // d1
     if q < 2:
-        return False
+        return 0
+    if dry:
+        return q
 
     def levels(ax):
         return (ax.s0, ax.s1) if ax.d1 == d1 else (ax.s0 * d1, ax.s0)
@@ -241,7 +264,23 @@ def _fold_k_outer_into_batch(g: Gemm) -> bool:
     g.C.batch = Axis(0, 0, 1, 0)
     g.batch, g.K = q, d1
     g.accumulate, g.split_k = ACC_ATOMIC, 1
-    return True
+    return q
+
+
+def even_split(K: int, split: int) -> int:
+    """Largest split count <= ``split`` for which neither engine (k-blocks of 32 on the tensor cores, of 16
+    on the CUDA cores) is left with an empty K slice -- every slice of a two-stage reduction is written."""
+    def eff(bk, s):
+        kb = (K + bk - 1) // bk
+        s = min(s, kb)
+        per = (kb + s - 1) // s
+        return (kb + per - 1) // per
+    split = max(1, split)
+    while True:
+        e = min(eff(32, split), eff(16, split))
+        if e == split:
+            return split
+        split = e
 
 
 def auto_split_k(M: int, N: int, K: int, batch: int) -> int:
@@ -293,8 +332,13 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                  c_add: Optional[Tuple[str, torch.Tensor]] = None,
                  c_mul: Optional[Tuple[str, torch.Tensor]] = None, alpha: float = 1.0,
                  relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
-                 precision=None, tag: Optional[str] = None) -> torch.Tensor:
-    """Enqueue one contraction on the current CUDA stream.  No autograd."""
+                 precision=None, tag: Optional[str] = None, reproducible: Optional[bool] = None) -> torch.Tensor:
+    """Enqueue one contraction on the current CUDA stream.  No autograd.
+
+    ``reproducible``: a reduction that is split over K (or whose outer K level is folded into a batch)
+    writes one partial result per split into a workspace and sums the slices in a fixed order
+    (``dstag_sum_slices``) instead of adding atomically.  Every forward product runs this way
+    (``None`` = the module default, see ``set_reproducible``)."""
     if a_mul is None:
         # a training step repeats the same ~100 contractions with the same layouts: the orientation decision
         # and the problem sizes are memoised per (spec, layouts) -- host time matters at the small graph
@@ -311,12 +355,14 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             ins, res = spec.replace(" ", "").split("->")
             sa, sb = ins.split(",")
             return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
-                                accumulate=accumulate, split_k=split_k, precision=precision, tag=tag)
+                                accumulate=accumulate, split_k=split_k, precision=precision, tag=tag,
+                                reproducible=reproducible)
     lib = _lib.load()
     _check(A, "A"), _check(B, "B")
     for opt in (a_mul, c_add, c_mul):
         if opt is not None:
             _check(opt[1], "epilogue/prologue operand")
+    _lib.same_device(A, B, out, *(opt[1] for opt in (a_mul, c_add, c_mul) if opt is not None))
     if out is None:
         if accumulate != ACC_STORE:
             raise ValueError("accumulating contraction needs an explicit out=")
@@ -333,22 +379,52 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
     M, N, K, nb = dims
     if split_k is None:
         split_k = 1 if relu else auto_split_k(M, N, K, nb)
+    if reproducible is None:
+        reproducible = _reproducible
+    # two-stage (workspace + fixed-order sum) instead of atomics: plain stores into a dense output only
+    two_stage = reproducible and accumulate == ACC_STORE and c_mul is None and is_row_padded(out)
+    ws = None
+    if split_k > 1 and two_stage:
+        split_k = even_split(K, split_k)
     if split_k > 1:
-        if accumulate == ACC_STORE:
-            out.zero_()
-        elif accumulate == ACC_ADD:
-            pass  # existing contents are kept; partial sums are added atomically
-        accumulate = ACC_ATOMIC
-    g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
-    if _fold_k_outer_into_batch(g):
-        if accumulate == ACC_STORE:        # (ACC_ATOMIC here means split-K already zeroed the output)
-            out.zero_()
-    if _lib._prof is None:
-        _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
+        if two_stage:
+            ws = _workspace(split_k, out)
+            g = build_descriptor(spec, A, B, ws[0], a_mul, c_add, c_mul, alpha, relu, ACC_STORE, split_k, precision)
+            g.split_stride = ws.stride(0)
+        else:
+            if accumulate == ACC_STORE:
+                out.zero_()
+            # (ACC_ADD: existing contents are kept; partial sums are added atomically)
+            accumulate = ACC_ATOMIC
+            g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
     else:
-        nbytes = 4 * (A.numel() + B.numel() + out.numel())
-        with _lib.prof_range(tag or ("gemm:" + spec), 2 * M * N * K * nb, nbytes):
-            _lib.check(lib.dstag_gemm(C.byref(g), _lib.stream_ptr(A)), f"dstag_gemm('{spec}')")
+        g = build_descriptor(spec, A, B, out, a_mul, c_add, c_mul, alpha, relu, accumulate, split_k, precision)
+        q = _fold_k_outer_into_batch(g, dry=True)
+        if q:
+            if two_stage:
+                ws = _workspace(q, out)
+                g = build_descriptor(spec, A, B, ws[0], a_mul, c_add, c_mul, alpha, relu, ACC_STORE, 1, precision)
+                _fold_k_outer_into_batch(g)
+                g.accumulate = ACC_STORE
+                g.C.batch = Axis(ws.stride(0), 0, 1, 0)            # one output slice per batch member
+            else:
+                _fold_k_outer_into_batch(g)
+                if accumulate == ACC_STORE:
+                    out.zero_()
+    st = _lib.stream_ptr(A)
+    with _lib.on_device(st):
+        if _lib._prof is None:
+            _lib.check(lib.dstag_gemm(C.byref(g), st), f"dstag_gemm('{spec}')")
+        else:
+            nbytes = 4 * (A.numel() + B.numel() + out.numel())
+            with _lib.prof_range(tag or ("gemm:" + spec), 2 * M * N * K * nb, nbytes):
+                _lib.check(lib.dstag_gemm(C.byref(g), st), f"dstag_gemm('{spec}')")
+        if ws is not None:
+            cols = out.shape[-1] if out.dim() else 1
+            rows = out.numel() // max(cols, 1)
+            ld = out.stride(-2) if out.dim() >= 2 else cols
+            _lib.check(lib.dstag_sum_slices(ws.data_ptr(), ws.stride(0), ws.shape[0], out.data_ptr(), rows, cols, ld, st),
+                       "dstag_sum_slices")
     return out
 
 
@@ -447,7 +523,8 @@ class _Contract(torch.autograd.Function):
             assert not relu
             out = empty_rows(output_shape(spec, A, B), A.device)
         out = contract_raw(spec, A, B, out=out, a_mul=(amul_sub, amul) if amul is not None else None,
-                           c_add=(cadd_sub, cadd) if cadd is not None else None, alpha=alpha, relu=relu)
+                           c_add=(cadd_sub, cadd) if cadd is not None else None, alpha=alpha, relu=relu,
+                           reproducible=True)
         ctx.spec, ctx.cadd_sub, ctx.amul_sub, ctx.alpha, ctx.relu = spec, cadd_sub, amul_sub, alpha, relu
         ctx.has_cadd = cadd is not None
         ctx.save_for_backward(A, B, amul, out if relu else None)

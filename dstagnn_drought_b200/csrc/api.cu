@@ -30,8 +30,11 @@ static int validate(const dstag_gemm_t* g) {
   DSTAG_CHECK_ARG(g->split_k >= 1, "dstag_gemm: split_k must be >= 1");
   DSTAG_CHECK_ARG(g->accumulate >= DSTAG_ACC_STORE && g->accumulate <= DSTAG_ACC_ATOMIC,
                   "dstag_gemm: bad accumulate mode %d", g->accumulate);
-  DSTAG_CHECK_ARG(g->split_k == 1 || (g->accumulate == DSTAG_ACC_ATOMIC && !g->relu),
-                  "dstag_gemm: split_k > 1 needs atomic accumulation and no relu");
+  DSTAG_CHECK_ARG(g->split_k == 1 || (!g->relu && (g->accumulate == DSTAG_ACC_ATOMIC ||
+                                                   (g->accumulate == DSTAG_ACC_STORE && g->split_stride != 0))),
+                  "dstag_gemm: split_k > 1 needs atomic accumulation or per-split slices (split_stride), and no relu");
+  DSTAG_CHECK_ARG(g->split_stride == 0 || (g->accumulate == DSTAG_ACC_STORE && !g->Cmul.ptr),
+                  "dstag_gemm: split_stride needs accumulate == STORE and no Cmul");
   const dstag_axis_t* ax[] = {&g->A.batch, &g->A.row, &g->A.col, &g->B.batch, &g->B.row, &g->B.col,
                               &g->C.batch, &g->C.row, &g->C.col};
   for (const dstag_axis_t* a : ax) DSTAG_CHECK_ARG(a->d1 >= 1, "dstag_gemm: axis d1 must be >= 1");
@@ -42,7 +45,7 @@ static int validate(const dstag_gemm_t* g) {
 
 extern "C" {
 
-int dstag_abi_version(void) { return 8; }
+int dstag_abi_version(void) { return 9; }
 const char* dstag_last_error(void) { return dstag::g_err; }
 int64_t dstag_launch_count(void) { return dstag::g_launches.load(); }
 void dstag_reset_launch_count(void) { dstag::g_launches.store(0); }

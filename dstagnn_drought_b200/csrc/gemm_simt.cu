@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const dstag_gemm_t p) {
   const int per_split = (ktiles + p.split_k - 1) / p.split_k;
   const int kt0 = ks * per_split;
   const int kt1 = min(ktiles, kt0 + per_split);
-  if (kt0 >= kt1 && p.split_k > 1) return;  // empty K slice of an atomic accumulation
+  if (kt0 >= kt1 && p.split_k > 1 && p.split_stride == 0) return;  // empty K slice of an atomic accumulation
+                                                                   // (a slice of a two-stage reduction is written as zeros)
 
   const float* __restrict__ A = (const float*)p.A.ptr + axoff(p.A.batch, batch);
   const float* __restrict__ Bp = (const float*)p.B.ptr + axoff(p.B.batch, batch);
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const dstag_gemm_t p) {
   }
 
   // ---- epilogue ------------------------------------------------------------------------
-  float* __restrict__ C = (float*)p.C.ptr + axoff(p.C.batch, batch);
+  float* __restrict__ C = (float*)p.C.ptr + axoff(p.C.batch, batch) + (long long)ks * p.split_stride;
   const float* __restrict__ Cm =
       p.Cmul.ptr ? (const float*)p.Cmul.ptr + axoff(p.Cmul.batch, batch) : nullptr;
   const float* __restrict__ Ca =

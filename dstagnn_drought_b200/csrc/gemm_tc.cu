@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       return runs && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && o.batch.s0 % 4 == 0 &&
              (o.batch.d1 == 1 || o.batch.s1 % 4 == 0);
     };
-    const bool c_quad = g.accumulate != DSTAG_ACC_ATOMIC && quad(g.C) && (!g.Cadd.ptr || quad(g.Cadd)) &&
+    const bool c_quad = g.accumulate != DSTAG_ACC_ATOMIC && g.split_stride % 4 == 0 && quad(g.C) && (!g.Cadd.ptr || quad(g.Cadd)) &&
                         (!g.Cmul.ptr || quad(g.Cmul));
     uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t acc = item & 1;
       const int m = tm * p.a_rt + q4 * 32 + lane;               // tile rows beyond a_rt are padding of a ragged tile
       const bool mok = q4 * 32 + lane < p.a_rt && m < g.M;
-      float* Cb = (float*)g.C.ptr + axoff64(g.C.batch, batch);
+      float* Cb = (float*)g.C.ptr + axoff64(g.C.batch, batch) + (long long)ks * g.split_stride;
       const float* Cab = (g.Cadd.ptr && ks == 0) ? (const float*)g.Cadd.ptr + axoff64(g.Cadd.batch, batch) : nullptr;
       const float* Cmb = g.Cmul.ptr ? (const float*)g.Cmul.ptr + axoff64(g.Cmul.batch, batch) : nullptr;
       const int c_ro = mok ? axoff32(g.C.row, m) : 0;
@@ -1232,32 +1232,45 @@ static bool make_tmap_ragged(CUtensorMap* map, const dstag_gemm_t& g, int* a_rt)
   return true;
 }
 
-static int g_num_sms = 0;
+// Both the opt-in shared-memory limit of a kernel and the SM count are properties of a DEVICE: a process
+// that drives several GPUs (one replica per device in one process) must set / query them on each.
+constexpr int kMaxDevices = 64;
+static int g_num_sms[kMaxDevices] = {0};
+
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+static int num_sms(int dev) {
+  if (g_num_sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms[dev] = n > 0 ? n : kNumSMs;
+  }
+  return g_num_sms[dev];
+}
 
 template <int BN, bool X3, bool AMUL, bool ATM>
 static int launch_tc(const TcParams& p, const TcMaps& maps, cudaStream_t stream) {
   using Cfg = TcCfg<BN, X3, AMUL, ATM>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};      // per instantiation AND per device
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, X3, AMUL, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("dstag_gemm(tc): cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured[dev] = true;
   }
-  const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
+  const int nsm = num_sms(dev);
+  const int grid = p.total_items < nsm ? p.total_items : nsm;
   gemm_tc_kernel<BN, X3, AMUL, ATM><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(p, maps);
   DSTAG_RETURN_LAUNCH("dstag_gemm(tcgen05)");
 }
 
 int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = kNumSMs;
-  }
   TcParams p;
   p.g = *g_in;
   if (!split_rows_to_batch(p.g)) split_cols_to_batch(p.g);
@@ -1296,6 +1309,9 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   if (split > p.kblocks) split = p.kblocks;
   p.kb_per_split = (p.kblocks + split - 1) / split;
   p.nsplit = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+  DSTAG_CHECK_ARG(g->split_stride == 0 || p.nsplit == g->split_k,
+                  "dstag_gemm(tc): split_k = %d leaves empty K slices (%d k-blocks); the caller of a two-stage "
+                  "reduction must pick a split count that divides the k-blocks evenly", g->split_k, p.kblocks);
   const long long items = (long long)g->batch * p.ntm * p.ntn * p.nsplit;
   DSTAG_CHECK_ARG(items < (1ll << 31), "dstag_gemm(tc): too many tiles");
   p.total_items = (int)items;

@@ -253,6 +253,35 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, const fl
   }
 }
 
+// Fixed-order sum of nslices partial results (the second stage of a reproducible split-K contraction).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+sum_slices_kernel(const float* __restrict__ ws, long long slice_stride, int nslices, float* __restrict__ out,
+                  long long rows, long long cols, long long out_ld) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC) {
+    const long long c4 = cols >> 2, n4 = rows * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const long long r = i / c4, c = (i - r * c4) << 2;
+      const float* src = ws + r * cols + c;
+      float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      for (int s = 1; s < nslices; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * slice_stride));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>(out + r * out_ld + c) = a;
+    }
+  } else {
+    const long long n = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const long long r = i / cols, c = i - r * cols;
+      float a = __ldg(ws + i);
+      for (int s = 1; s < nslices; ++s) a += __ldg(ws + s * slice_stride + i);
+      out[r * out_ld + c] = a;
+    }
+  }
+}
+
 __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                 float* __restrict__ dx, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -595,6 +624,22 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
       dy, dy_ld, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta,
       rows, L, drop_p, seed);
   DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd");
+}
+
+int dstag_sum_slices(const float* ws, int64_t slice_stride, int32_t nslices, float* out, int64_t rows, int64_t cols,
+                     int64_t out_ld, void* stream) {
+  DSTAG_CHECK_ARG(ws && out && nslices > 0 && rows > 0 && cols > 0 && out_ld >= cols && slice_stride >= rows * cols,
+                  "dstag_sum_slices: bad arguments");
+  const bool vec = cols % 4 == 0 && out_ld % 4 == 0 && slice_stride % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long n = vec ? rows * (cols / 4) : rows * cols;
+  long long blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (vec)
+    sum_slices_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ws, slice_stride, nslices, out, rows, cols, out_ld);
+  else
+    sum_slices_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ws, slice_stride, nslices, out, rows, cols, out_ld);
+  DSTAG_RETURN_LAUNCH("dstag_sum_slices");
 }
 
 int dstag_colsum(const float* in, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream) {

@@ -8,7 +8,8 @@
 // A CTA owns a strip of output nodes j of one (b, k); the logits of the strip never reach HBM and every
 // row is normalised and written once -- N x N x 4 bytes of HBM traffic per map instead of 3x that for a
 // GEMM + softmax pair.  Three variants, chosen by the launcher at the bottom:
-//   sat_softmax_mma_kernel   d_k = 32, ld <= 1024 (every dataset): logits as warp-level tensor-core MMA
+//   sat_softmax_mma_kernel   d_k = 32, ld <= 1024 (the PEMS graphs; GAMBIA's N = 2139 takes the strip kernel):
+//                            logits as warp-level tensor-core MMA
 //                            fragments (3xTF32), bias / T_k rows and W_Q pieces by cp.async
 //   sat_softmax_rows_kernel  other d_k, ld <= 1024: a warp keeps 4 complete logit rows in registers (SIMT)
 //   sat_softmax_fwd_kernel   ld > 1024: R x N logits of the strip in shared memory (SIMT)
@@ -118,7 +119,7 @@ sat_softmax_fwd_kernel(const float* __restrict__ qk, const float* __restrict__ b
 
 
 // ---------------------------------------------------------------------------------------
-// Register-resident variant for ld <= 1024 (all PEMS / drought graph sizes): a warp owns 4 output
+// Register-resident variant for ld <= 1024 (all PEMS graph sizes; not the N = 2139 drought graph): a warp owns 4 output
 // rows j and keeps their complete logit rows in registers (4 x 4*NT values per lane, NT column tiles
 // of 128), so the softmax needs no shared-memory round trip at all: 16 FMAs per pair of
 // shared-memory loads in the product loop, row max / sum by warp shuffles, one float4 store per value.
@@ -244,7 +245,7 @@ static int launch_sat_rows(const float* qk, const float* biasT, const float* tkT
 
 
 // ---------------------------------------------------------------------------------------
-// Tensor-core variant for d_k = 32 and ld <= 1024 (every PEMS / drought graph size).  The K = 32 logit
+// Tensor-core variant for d_k = 32 and ld <= 1024 (every PEMS graph size; the drought graph, N = 2139, does not fit).  The K = 32 logit
 // products are far too thin for the tcgen05 engine (one k-block, 883 accumulator columns per row against
 // 512 TMEM columns) but they are what bounds the SIMT variant above (one shared-memory float per 4 FMAs =
 // the shared-memory roofline).  Here a CTA of 8 warps owns 16 output rows j of one (b, k); warp w owns the

@@ -368,18 +368,15 @@ int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const flo
 // =======================================================================================
 // Fused fcmy + tail for the PEMS shape (C = 32 channels = one lane each, T = 12): a warp owns one node.
 // Lane c reads its channel of the concatenated GTU outputs cat[x, s, c] (3T-12 coalesced lines), evaluates
-// the Linear over the concatenated time axis in registers (weights are warp-uniform: `__constant__`
-// FFMA operands, no loads), and the LayerNorm over the 32 channels is a warp-shuffle reduction per time
-// step.  tc never touches HBM; the backward emits d cat and d tc (for the weight gradient) directly.
+// the Linear over the concatenated time axis in registers and the LayerNorm over the 32 channels is a
+// warp-shuffle reduction per time step.  tc never touches HBM; the backward emits d cat and d tc (for the
+// weight gradient) directly.
+// The fcmy weights are staged per CTA in shared memory (288 + 12 floats, read back as warp-uniform
+// float4 broadcasts: one LDS.128 per four FMAs).  They used to live in __constant__ symbols re-uploaded
+// per call, which two streams running different blocks could race on; with per-CTA staging the entry
+// points are re-entrant per stream and need no memcpy nodes when the step is captured in a CUDA graph.
 // =======================================================================================
 namespace dstag {
-
-constexpr int kFusedMaxW = 4096;
-__constant__ float c_wf[kFusedMaxW];   // fcmy weight (T, S) row-major, re-uploaded per call (stream-ordered)
-__constant__ float c_wf2[kFusedMaxW];  // second copy: the backward uses every weight twice (recompute + d cat);
-                                       // with ONE symbol the compiler keeps all T*S weights in registers
-                                       // (and spills) instead of using constant-bank FFMA operands
-__constant__ float c_bf[64];           // fcmy bias (T)
 
 // dropout multipliers of one (node, channel): element e = (x*C + c) * T + t draws word (e & 3) of
 // philox(e >> 2) exactly like dropout_scale(), but one Philox evaluation serves 4 time steps
@@ -399,12 +396,18 @@ __device__ __forceinline__ void row_dropout(float (&ds)[T], long long row, unsig
 
 template <int T>
 __global__ void __launch_bounds__(256)
-tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ g, const float* __restrict__ r,
+tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ wf, const float* __restrict__ bf,
+                      const float* __restrict__ g, const float* __restrict__ r,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                       float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, long long X,
                       float drop_p, unsigned long long seed) {
   constexpr int S = 3 * T - 12, C = 32;
   static_assert(S % 4 == 0 && T % 4 == 0 && T <= 32, "fused tail tiling");
+  __shared__ __align__(16) float s_w[T * S];     // fcmy weight (T, S) row-major
+  __shared__ float s_b[T];
+  for (int i = threadIdx.x; i < T * S; i += blockDim.x) s_w[i] = __ldg(wf + i);
+  if (threadIdx.x < T) s_b[threadIdx.x] = __ldg(bf + threadIdx.x);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float gam = __ldg(gamma + lane), bet = __ldg(beta + lane);
@@ -419,9 +422,15 @@ tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ g
     if (drop_p > 0.f) row_dropout<T>(ds, x * C + lane, seed, drop_p, inv_keep);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      float a = c_bf[t];
+      float a = s_b[t];
 #pragma unroll
-      for (int s = 0; s < S; ++s) a = fmaf(cv[s], c_wf[t * S + s], a);
+      for (int s = 0; s < S; s += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + t * S + s);      // warp-uniform broadcast
+        a = fmaf(cv[s], w4.x, a);
+        a = fmaf(cv[s + 1], w4.y, a);
+        a = fmaf(cv[s + 2], w4.z, a);
+        a = fmaf(cv[s + 3], w4.w, a);
+      }
       a *= ds[t];
       const long long e = (x * T + t) * C + lane;
       if (g) a += __ldg(g + e);
@@ -437,12 +446,23 @@ tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ g
 
 template <int T>
 __global__ void __launch_bounds__(256, 2)
-tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ cat, const float* __restrict__ g,
+tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ cat, const float* __restrict__ wf,
+                      const float* __restrict__ bf, const float* __restrict__ g,
                       const float* __restrict__ r, const float* __restrict__ gamma, const float* __restrict__ mean,
                       const float* __restrict__ rstd, float* __restrict__ dcat, float* __restrict__ dtc_out,
                       float* __restrict__ dg, float* __restrict__ dr, float* __restrict__ dgamma,
                       float* __restrict__ dbeta, long long X, float drop_p, unsigned long long seed) {
   constexpr int S = 3 * T - 12, C = 32, NW = 8;
+  __shared__ __align__(16) float s_w[T * S];     // (T, S): rows for the forward recompute
+  __shared__ __align__(16) float s_wt[S * T];    // (S, T): rows for d cat[s] = sum_t dtc[t] w[t][s]
+  __shared__ float s_b[T];
+  for (int i = threadIdx.x; i < T * S; i += blockDim.x) {
+    const float w = __ldg(wf + i);
+    s_w[i] = w;
+    s_wt[(i % S) * T + i / S] = w;
+  }
+  if (threadIdx.x < T) s_b[threadIdx.x] = __ldg(bf + threadIdx.x);
+  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * NW;
   const float gam = __ldg(gamma + lane);
@@ -460,9 +480,15 @@ tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ 
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       // ---- recompute the forward of this element
-      float a = c_bf[t];
+      float a = s_b[t];
 #pragma unroll
-      for (int s = 0; s < S; ++s) a = fmaf(cv[s], c_wf[t * S + s], a);
+      for (int s = 0; s < S; s += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + t * S + s);
+        a = fmaf(cv[s], w4.x, a);
+        a = fmaf(cv[s + 1], w4.y, a);
+        a = fmaf(cv[s + 2], w4.z, a);
+        a = fmaf(cv[s + 3], w4.w, a);
+      }
       a *= ds[t];
       const long long e = (x * T + t) * C + lane;
       if (g) a += __ldg(g + e);
@@ -489,23 +515,18 @@ tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ 
     for (int s = 0; s < S; ++s) {
       float a = 0.f;
 #pragma unroll
-      for (int t = 0; t < T; ++t) a = fmaf(dtc[t], c_wf2[t * S + s], a);
+      for (int t = 0; t < T; t += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_wt + s * T + t);
+        a = fmaf(dtc[t], w4.x, a);
+        a = fmaf(dtc[t + 1], w4.y, a);
+        a = fmaf(dtc[t + 2], w4.z, a);
+        a = fmaf(dtc[t + 3], w4.w, a);
+      }
       dcat[(x * S + s) * C + lane] = a;
     }
   }
   atomicAdd(dgamma + lane, acc_g);
   atomicAdd(dbeta + lane, acc_be);
-}
-
-static int upload_fcmy(const float* wf, const float* bf, int T, int S, cudaStream_t stream, const char* name) {
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_wf, wf, sizeof(float) * T * S, 0, cudaMemcpyDeviceToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_wf2, wf, sizeof(float) * T * S, 0, cudaMemcpyDeviceToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_bf, bf, sizeof(float) * T, 0, cudaMemcpyDeviceToDevice, stream);
-  if (e != cudaSuccess) {
-    set_error("%s: constant upload failed: %s", name, cudaGetErrorString(e));
-    return (int)e;
-  }
-  return 0;
 }
 
 }  // namespace dstag
@@ -523,12 +544,10 @@ int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, con
     set_error("dstag_tail_fused_fwd: only C = 32, T = 12 is fused (got C=%d T=%d); use the unfused path", C, T);
     return DSTAG_ERR_UNSUPPORTED;
   }
-  int rc = upload_fcmy(wf, bf, T, 3 * T - 12, (cudaStream_t)stream, "dstag_tail_fused_fwd");
-  if (rc) return rc;
   const long long blocks = (X + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
-  tail_fused_fwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(cat, g, r, gamma, beta, eps, out, mean, rstd, X,
-                                                                    drop_p, seed);
+  tail_fused_fwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(cat, wf, bf, g, r, gamma, beta, eps, out, mean,
+                                                                    rstd, X, drop_p, seed);
   DSTAG_RETURN_LAUNCH("dstag_tail_fused_fwd");
 }
 
@@ -544,12 +563,10 @@ int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, c
     set_error("dstag_tail_fused_bwd: only C = 32, T = 12 is fused (got C=%d T=%d)", C, T);
     return DSTAG_ERR_UNSUPPORTED;
   }
-  int rc = upload_fcmy(wf, bf, T, 3 * T - 12, (cudaStream_t)stream, "dstag_tail_fused_bwd");
-  if (rc) return rc;
   const long long blocks = (X + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
-  tail_fused_bwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, cat, g, r, gamma, mean, rstd, dcat, dtc, dg,
-                                                                    dr, dgamma, dbeta, X, drop_p, seed);
+  tail_fused_bwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, cat, wf, bf, g, r, gamma, mean, rstd, dcat,
+                                                                    dtc, dg, dr, dgamma, dbeta, X, drop_p, seed);
   DSTAG_RETURN_LAUNCH("dstag_tail_fused_bwd");
 }
 

@@ -29,18 +29,30 @@ def _p(t: Optional[torch.Tensor]):
 
 
 # ----------------------------------------------------------------------------------------
-# dropout seeds: one fresh 64-bit Philox key per dropout site per forward call, derived
-# from torch's seed so that torch.manual_seed() makes runs reproducible.
+# dropout seeds: one fresh 64-bit Philox key per dropout site per forward call, derived from
+# torch's seed, the data-parallel rank and a call counter.  torch.manual_seed(s) restarts the
+# counter, so two runs that seed the same way draw the same masks; ranks that seed identically
+# (every replica calls manual_seed(1), train_DSTAGNN_my.py:48) still draw DIFFERENT masks.
 # ----------------------------------------------------------------------------------------
 _seed_counter = 0
+_seed_base = None
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def _rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
 def next_seed() -> int:
-    global _seed_counter
+    global _seed_counter, _seed_base
+    base = torch.initial_seed()
+    if base != _seed_base:                 # torch.manual_seed() was called: restart the sequence
+        _seed_base, _seed_counter = base, 0
     _seed_counter += 1
-    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = (base * 0x9E3779B97F4A7C15 + _seed_counter * 0xBF58476D1CE4E5B9 + (_rank() + 1) * 0xD6E8FEB86659FD93) & _M64
     x ^= x >> 31
-    return (x * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (x * 0x94D049BB133111EB) & _M64
 
 
 # ----------------------------------------------------------------------------------------
@@ -242,18 +254,19 @@ class SpatialChebConv(torch.autograd.Function):
         # TP = T_k (.) P is written by the same kernel: the two contractions that need the masked operator
         # (forward, input gradient) then stream one N x N operand instead of two
         TP = torch.empty_like(P)
-        rc = -3 if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
+        rc = _lib.ERR_SMEM if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
             qk.data_ptr(), biasT.data_ptr(), tkT.data_ptr(), P.data_ptr(), TP.data_ptr(), B, N, K, dk, ld, _stream(P))
         Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
-        if rc == -3:      # DSTAG_ERR_SMEM: N too large for the fused row strip -> GEMM + row softmax
+        if rc == _lib.ERR_SMEM:      # N too large for the fused row strip -> GEMM + row softmax
             TP = None
             contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
-                         c_add=("kji", biasT[..., :N]))
+                         c_add=("kji", biasT[..., :N]), reproducible=True)
             _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
-            contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd")
+            contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd",
+                         reproducible=True)
         else:
             _lib.check(rc, "dstag_sat_softmax_fwd")
-            contract_raw("bkji,bie->kbje", TP[..., :N], x3, out=Z, tag="cheb_fwd")
+            contract_raw("bkji,bie->kbje", TP[..., :N], x3, out=Z, tag="cheb_fwd", reproducible=True)
         ctx.save_for_backward(qk, P, tkT, x3, TP)
         return Z
 
@@ -321,7 +334,8 @@ class GtuStack(torch.autograd.Function):
         us, off = [], 0
         for ks, w, b, tp in zip(GtuStack.KS, (w3, w5, w7), (b3, b5, b7), widths):
             wk = w[:, :, 0, :].permute(0, 2, 1).reshape(2 * Cc, ks * Cc).contiguous()      # (o, (d, c))
-            u = contract_raw("xtk,ok->xto", GtuStack._views(g, ks), wk, c_add=("o", b), tag=f"gtu{ks}_fwd")
+            u = contract_raw("xtk,ok->xto", GtuStack._views(g, ks), wk, c_add=("o", b), tag=f"gtu{ks}_fwd",
+                             reproducible=True)
             _lib.check(lib.dstag_gtu_gate_fwd(u.data_ptr(), out.data_ptr(), X, Cc, tp, total, off,
                                               _stream(g)), "dstag_gtu_gate_fwd")
             us.append(u)

@@ -37,7 +37,15 @@ def bucket_of(name: str) -> str:
 
 
 class GradBuckets:
-    """Flat per-block gradient storage + overlapped averaging all-reduce."""
+    """Flat per-block gradient storage + overlapped averaging all-reduce.
+
+    ``p.grad`` of every live parameter is a view into its bucket's flat buffer.  The reference loop
+    calls ``optimizer.zero_grad()`` (train_DSTAGNN_my.py:154), whose default ``set_to_none=True``
+    DETACHES those views; the buckets therefore check the attachment whenever they are about to reduce
+    (and in ``zero()``): a gradient that autograd allocated afresh is copied into its slot and
+    re-attached, a gradient that is still ``None`` leaves a zero slot.  Either calling convention --
+    ``buckets.zero()`` or ``optimizer.zero_grad()`` at the top of the step -- gives the same result.
+    """
 
     def __init__(self, net, process_group=None, overlap: bool = True):
         self.group = process_group
@@ -45,6 +53,7 @@ class GradBuckets:
         self.overlap = overlap and self.world > 1
         self.buckets: Dict[str, torch.Tensor] = {}
         self._members: Dict[str, List[torch.nn.Parameter]] = {}
+        self._views: Dict[str, List[torch.Tensor]] = {}
         self._pending: Dict[str, int] = {}
         self._works = []
         groups: Dict[str, List] = {}
@@ -53,12 +62,16 @@ class GradBuckets:
         for b, items in groups.items():
             n = sum(p.numel() for _, p in items)
             flat = torch.zeros(n, device=items[0][1].device, dtype=items[0][1].dtype)
-            off = 0
+            off, views = 0, []
             for _, p in items:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                v = flat[off:off + p.numel()].view_as(p)
+                p.grad = v
+                views.append(v)
                 off += p.numel()
             self.buckets[b] = flat
             self._members[b] = [p for _, p in items]
+            self._views[b] = views
+            self._pending[b] = len(items)
         if self.overlap:
             for b, ps in self._members.items():
                 for p in ps:
@@ -67,26 +80,49 @@ class GradBuckets:
 
     def _make_hook(self, b):
         def hook(_p):
+            if self._pending[b] <= 0:          # a new step began without zero(): re-arm
+                self._pending[b] = len(self._members[b])
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 self._launch(b)
         return hook
 
+    def _attach(self, b, copy: bool):
+        """Make every ``p.grad`` of bucket b a view of the flat buffer again.  ``copy``: gradients found in
+        foreign storage are copied into their slot first (they were produced by this step's backward);
+        a gradient that is ``None`` gets a zeroed slot."""
+        for p, v in zip(self._members[b], self._views[b]):
+            g = p.grad
+            if g is None:
+                if copy:
+                    v.zero_()
+            elif g.data_ptr() != v.data_ptr() or g.shape != v.shape or not g.is_contiguous():
+                if copy:
+                    v.copy_(g)
+            else:
+                continue
+            p.grad = v
+
     def _launch(self, b):
+        self._attach(b, copy=True)
         flat = self.buckets[b]
         flat.mul_(1.0 / self.world)
         self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero(self):
-        """Start of a step: clear the flat buffers (``.grad`` views stay attached)."""
+        """Start of a step: clear the flat buffers and (re-)attach the ``.grad`` views."""
         for b, flat in self.buckets.items():
             flat.zero_()
+            self._attach(b, copy=False)
             self._pending[b] = len(self._members[b])
         self._works = []
 
     def finish(self):
-        """After ``loss.backward()``: make sure every bucket is averaged across ranks."""
+        """After ``loss.backward()``: make sure every bucket is averaged across ranks (and, also at
+        world size 1, that every gradient lives in its bucket again)."""
         if self.world == 1:
+            for b in self.buckets:
+                self._attach(b, copy=True)
             return
         if not self.overlap:
             for b in self.buckets:
@@ -95,6 +131,7 @@ class GradBuckets:
             for b, n in self._pending.items():
                 if n > 0:          # a parameter got no gradient this step; reduce what there is
                     self._launch(b)
+                    self._pending[b] = 0
         for w in self._works:
             w.wait()
         self._works = []

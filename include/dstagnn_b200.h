@@ -76,10 +76,14 @@ typedef struct {
   dstag_operand_t A, B, C, Amul, Cmul, Cadd;
   float alpha;
   int32_t relu;          /* apply max(.,0) last */
-  int32_t accumulate;    /* DSTAG_ACC_*; ATOMIC required when split_k > 1 or C aliases over batch */
+  int32_t accumulate;    /* DSTAG_ACC_*; with split_k > 1 (or C aliasing over batch) either ATOMIC, or STORE
+                            together with split_stride != 0 */
   int32_t split_k;       /* >= 1 */
   int32_t precision;     /* DSTAG_PREC_* */
   int32_t pad_;
+  int64_t split_stride;  /* 0, or (accumulate == STORE): K-split s writes its partial product to
+                            C + s * split_stride (elements) instead of adding atomically; the caller sums the
+                            split_k slices in a fixed order with dstag_sum_slices -- a reproducible reduction */
 } dstag_gemm_t;
 
 int dstag_gemm(const dstag_gemm_t* g, void* stream);
@@ -108,6 +112,13 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
                         const float* mean, const float* rstd, float* dpre, int64_t dpre_ld, float* dgamma,
                         float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
                         void* stream);
+
+/* out[r * out_ld + c] = sum_{s < nslices} ws[s * slice_stride + r * cols + c]  (s ascending: a fixed-order,
+ * run-to-run reproducible reduction).  Second stage of the split-K / K-outer-fold contractions that must
+ * not use atomics (every forward product: an activation within rounding of a ReLU kink would otherwise
+ * land on either side of it from run to run). */
+int dstag_sum_slices(const float* ws, int64_t slice_stride, int32_t nslices, float* out, int64_t rows, int64_t cols,
+                     int64_t out_ld, void* stream);
 
 /* out[c] (+)= sum_r in[r * ld + c], r < rows, c < cols.  Bias / embedding-table /
  * mask gradients (autograd of model/DSTAGNN_my.py:127,175,180,193,207,221).  `out` must be

@@ -15,8 +15,8 @@ the oracle is pinned against outputs of the reference itself:
 ``tests/golden/make_golden.py`` imports the unmodified reference classes in the
 build container, runs them (fp64 and fp32, eval mode) and commits small
 input/weight/output/gradient fixtures; ``tests/test_oracle_golden.py`` checks
-this file against them, and ``tests/test_oracle_vs_reference.py`` re-runs the
-live comparison whenever ``/root/reference`` is present.
+this file against them (and, whenever ``/root/reference`` is present, against
+a live run of the reference).
 
 Two execution orders are provided for the Chebyshev stage:
   * ``faithful=True``  -- the reference's own order of operations (a Python loop
@@ -65,6 +65,35 @@ def cheb_polynomials(L_tilde: np.ndarray, K: int) -> List[np.ndarray]:
     for k in range(2, K):
         polys.append(2 * L_tilde * polys[k - 1] - polys[k - 2])
     return polys[:max(K, 2)]
+
+
+# ----------------------------------------------------------------------------
+# ReLU with a movable kink for the BACKWARD pass (test instrument)
+# ----------------------------------------------------------------------------
+# The net's three ReLU sites per block (lines 133, 245/247, 252 of model/DSTAGNN_my.py) make the
+# gradients discontinuous in the inputs: a pre-activation within rounding distance of zero is "on" in one
+# correct fp32 implementation and "off" in another.  With KINK_SHIFT = s the forward value is still
+# relu(x) exactly, but the derivative is taken as [x > s * max|x|]: s = -tau treats every unit within tau of
+# the kink as active, s = +tau as inactive.  The difference of the two gradients bounds what flipping those
+# units can do; tests add it to the tolerance at shapes with millions of units, where no input avoids the
+# kinks (tests/test_gpu_parity.py).  KINK_SHIFT = 0 (default) is the plain ReLU of the reference.
+KINK_SHIFT = 0.0
+
+
+class _ShiftedKinkRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift):
+        ctx.save_for_backward(x > shift * x.detach().abs().max())
+        return torch.relu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask, None
+
+
+def _relu(x: Tensor) -> Tensor:
+    return torch.relu(x) if KINK_SHIFT == 0.0 else _ShiftedKinkRelu.apply(x, KINK_SHIFT)
 
 
 # ----------------------------------------------------------------------------
@@ -148,11 +177,11 @@ def cheb_conv_with_sat(p: Params, pre: str, x: Tensor, sat: Tensor, adj_pa: Tens
                 a = cheb[k] * a
                 acc = acc + (a.permute(0, 2, 1) @ sig) @ thetas[k]
             steps.append(acc.unsqueeze(-1))
-        return torch.relu(torch.cat(steps, dim=-1))
+        return _relu(torch.cat(steps, dim=-1))
     bias = torch.stack([adj_pa * m for m in masks])                    # (K,N,N)
     a = torch.softmax(sat + bias, dim=2) * torch.stack(list(cheb))     # (B,K,N,N)
     z = torch.einsum("bkij,bift->bkjft", a, x)
-    return torch.relu(torch.einsum("bkjft,kfc->bjct", z, torch.stack(thetas)))
+    return _relu(torch.einsum("bkjft,kfc->bjct", z, torch.stack(thetas)))
 
 
 def gtu(p: Params, pre: str, name: str, xc: Tensor, C: int) -> Tensor:
@@ -179,13 +208,13 @@ def block_forward(p: Params, idx: int, x: Tensor, res_att, adj_pa: Tensor,
     tc = torch.cat([gtu(p, pre, n, xc, C) for n in ("gtu3", "gtu5", "gtu7")], dim=-1)
     tc = tc @ p[pre + "fcmy.0.weight"].t() + p[pre + "fcmy.0.bias"]        # line 243 (dropout = id)
     if Fin == 1:                                                           # lines 244-251
-        tco = torch.relu(tc)
+        tco = _relu(tc)
         r = F.conv2d(x.permute(0, 2, 1, 3), p[pre + "residual_conv.weight"],
                      p[pre + "residual_conv.bias"])
     else:
-        tco = torch.relu(xc + tc)
+        tco = _relu(xc + tc)
         r = x.permute(0, 2, 1, 3)
-    y = torch.relu(r + tco).permute(0, 3, 2, 1)                            # (B,T,N,C)
+    y = _relu(r + tco).permute(0, 3, 2, 1)                            # (B,T,N,C)
     y = _layer_norm(y, p[pre + "ln.weight"], p[pre + "ln.bias"]).permute(0, 2, 3, 1)
     return y, scores
 

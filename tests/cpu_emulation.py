@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 8
+        return 9
 
     def dstag_last_error(self):
         return self.err
@@ -79,8 +79,24 @@ class FakeLib:
         if g.accumulate == 0:
             assert len(np.unique(off)) == off.size, "store-mode output aliases"
             out[off - lo] = R
+            if g.split_k > 1:
+                # two-stage reduction: one slice per K split.  The emulation puts the whole product into
+                # slice 0 and zeros into the others (their fixed-order sum is the same result).
+                assert g.split_stride != 0, "split_k > 1 with plain stores needs split_stride"
+                for s in range(1, g.split_k):
+                    _arr(g.C.ptr + 4 * (lo + s * g.split_stride), hi - lo + 1)[off - lo] = 0.0
         else:
             np.add.at(out, (off - lo).ravel(), R.ravel().astype(np.float32))
+        return 0
+
+    def dstag_sum_slices(self, ws, slice_stride, nslices, out, rows, cols, out_ld, stream):
+        self.launches += 1
+        acc = np.zeros((rows, cols), np.float32)
+        for s in range(nslices):
+            acc = acc + _arr(ws + 4 * s * slice_stride, rows * cols).reshape(rows, cols)
+        o = _arr(out, (rows - 1) * out_ld + cols)
+        idx = (np.arange(rows, dtype=np.int64) * out_ld)[:, None] + np.arange(cols, dtype=np.int64)[None, :]
+        o[idx] = acc
         return 0
 
     # ---- row kernels ----

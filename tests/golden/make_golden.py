@@ -29,6 +29,10 @@ CASES = {
     "g_n20": dict(N=20, T=12, K=3, H=2, D=16, nb=2, B=2, P=12),
     "g_n33": dict(N=33, T=12, K=3, H=3, D=32, nb=3, B=3, P=12),
     "g_t18": dict(N=24, T=18, K=2, H=2, D=16, nb=2, B=2, P=6),
+    # the one real graph the reference ships (data/PEMS04/stag_001_PEMS04.csv, strg_001_PEMS04.csv; N = 307,
+    # 3 ones per STAG row, 4 non-zeros per STRG row), loaded with the reference's own lib/dataloader.py;
+    # d_model and nb_block are reduced from the conf's 512 / 4 to keep the fixture small
+    "g_pems04_real": dict(N=307, T=12, K=3, H=3, D=64, nb=2, B=2, P=12, real="PEMS04"),
 }
 
 
@@ -53,6 +57,16 @@ def graph(N, seed):
     return tmd, pa
 
 
+def real_graph(name):
+    """STAG / STRG of a dataset shipped with the reference, through the reference's own loaders
+    (lib/dataloader.py:5-15, called at train_DSTAGNN_my.py:71-73; graph = AG => adj_mx = adj_TMD)."""
+    from lib.dataloader import load_PA, load_weighted_adjacency_matrix
+    base = os.path.join(REF, "data", name)
+    tmd = load_weighted_adjacency_matrix(os.path.join(base, f"stag_001_{name}.csv"), None)
+    pa = load_PA(os.path.join(base, f"strg_001_{name}.csv"))
+    return np.float32(tmd), np.float32(pa)
+
+
 def run(net, x, target):
     net.zero_grad(set_to_none=True)
     blocks, atts = [], []
@@ -73,9 +87,13 @@ def run(net, x, target):
 
 def main():
     make_model = import_reference()
+    only = set(sys.argv[1:])
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         N, T, K, H, D, nb, B, P = (c[k] for k in ("N", "T", "K", "H", "D", "nb", "B", "P"))
-        tmd, pa = graph(N, seed=len(name))
+        tmd, pa = real_graph(c["real"]) if "real" in c else graph(N, seed=len(name))
+        assert tmd.shape == (N, N) and pa.shape == (N, N)
         torch.manual_seed(1)
         net = make_model("cpu", 1, nb, 1, K, 32, 32, 1, torch.FloatTensor(tmd), torch.FloatTensor(pa),
                          torch.FloatTensor(tmd), P, T, N, D, 32, 32, H)

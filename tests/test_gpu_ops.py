@@ -170,9 +170,15 @@ def test_temporal_attention(dev, cfg):
         assert rel_err(a.grad, b.grad) < 5e-5
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
 @pytest.mark.parametrize("cfg", [(2, 9, 3, 1), (2, 70, 3, 12), (1, 200, 2, 40), (1, 883, 2, 8), (1, 1100, 1, 4)])
-def test_spatial_cheb_conv(dev, precision, cfg):
+def test_spatial_cheb_conv(dev, precision, cfg, monkeypatch, fused):
+    """fused = the map kernel (logits + bias + softmax + T_k (.) P in one pass); unfused = the branch that large
+    graphs take (N > ~2900: logits GEMM -> row softmax -> Hadamard operand fused into the contraction's
+    load), forced here with DSTAG_SAT_FUSED=0 so that it is covered at sizes an fp64 check affords."""
     from dstagnn_drought_b200.ops import SpatialChebConv, _pad_ld
+    if not fused:
+        monkeypatch.setenv("DSTAG_SAT_FUSED", "0")
     Bz, N, K, FT = cfg
     dk = 32
     ld = _pad_ld(N)

@@ -62,58 +62,110 @@ def test_net_matches_reference_golden(name, precision):
     D.set_precision("tf32x3")
 
 
-@pytest.mark.parametrize("shape", [dict(N=170, T=12, K=3, H=3, D=64, nb=2, B=3),
-                                   dict(N=307, T=12, K=3, H=3, D=128, nb=2, B=2),
-                                   dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2),
-                                   # GAMBIA drought layout (in_channels = 1): T = 144, K = 2, H = 2, d_model = 64
-                                   dict(N=37, T=144, K=2, H=2, D=64, nb=2, B=2)])
-def test_net_matches_oracle_at_config_shapes(shape):
-    """Ragged PEMS08 / PEMS04 node counts and a longer horizon, against the fp64 CPU oracle."""
+# Oracle-only shapes: (shape, data seed, conditioned).
+# conditioned = True: the seed was found offline by tools/find_conditioned_seed.py using ONLY the fp64 oracle
+#   (tests/helpers.conditioned_case: no ReLU pre-activation within ~1e-6 of its kink); the test re-verifies
+#   that before it trusts the seed, and holds every gradient to max(1e-4, 3 x fp32-oracle error).
+# conditioned = False: shapes with so many ReLU units (8 M at PEMS07, 59 M at GAMBIA) that no input avoids the
+#   kinks; the tolerance of a gradient tensor additionally admits twice what flipping the units within
+#   1e-6 * max|pre-activation| of a kink does to it in the fp64 oracle (tests/helpers.kink_slack).  Forward
+#   quantities (predictions, block outputs, attention logits) are continuous and held to 1e-4 everywhere.
+# Nothing is redrawn: the CUDA forward is run-to-run reproducible (no atomics), one run decides.
+ORACLE_CASES = {
+    # ragged PEMS08 / PEMS04 node counts at reduced width, a longer horizon, the GAMBIA layout at small N
+    "n170_d64": (dict(N=170, T=12, K=3, H=3, D=64, nb=2, B=3), 4, True),
+    "n307_d128": (dict(N=307, T=12, K=3, H=3, D=128, nb=2, B=2), 3, True),
+    "n65_t24": (dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2), 3, True),
+    "n37_t144": (dict(N=37, T=144, K=2, H=2, D=64, nb=2, B=2), 6, True),
+    # the BASELINE configurations at their REAL shapes, batch reduced to what the fp64 CPU
+    # oracle finishes in seconds
+    "pems08_full": (dict(N=170, T=12, K=3, H=3, D=512, nb=4, B=2), 11, True),
+    "pems04_full": (dict(N=307, T=12, K=3, H=3, D=512, nb=4, B=2), 39, True),
+    "pems03_full": (dict(N=358, T=12, K=3, H=3, D=512, nb=4, B=2), 4, False),
+    "pems07_full": (dict(N=883, T=12, K=3, H=4, D=512, nb=4, B=2), 4, False),
+    # GAMBIA drought conf (in_channels = 1): N = 2139 > 1024 takes the shared-memory strip map
+    # kernel, the block-per-row LayerNorm / softmax-backward kernels and the unfused tail (T = 144)
+    "gambia_full": (dict(N=2139, T=144, K=2, H=2, D=64, nb=2, B=1), 4, False),
+    # N = 4096: a 16-row logit strip does not fit in shared memory -> logits GEMM + row softmax + Hadamard
+    # operand (the DSTAG_ERR_SMEM branch of ops.SpatialChebConv)
+    "syn4096_nb2": (dict(N=4096, T=12, K=3, H=4, D=512, nb=2, B=1), 11, True),
+}
+COND_THR = 5e-5
+KINK_TAU = 1e-6
+
+
+@pytest.mark.parametrize("case", sorted(ORACLE_CASES))
+def test_net_matches_oracle_at_config_shapes(case):
+    """Whole-net forward + backward against the fp64 CPU oracle: predictions, every block output, every
+    attention-logit tensor < 1e-4; every gradient < max(1e-4, 3 x the error the same algorithm makes in plain
+    fp32 on the CPU) [+ the kink slack at unconditioned shapes].  No retries."""
     from oracle import dstagnn_oracle as O
+    from helpers import _oracle_run, conditioned_case, kink_slack, oracle_fp32_grad_err
+    shape, seed, conditioned = ORACLE_CASES[case]
     dev = torch.device("cuda:0")
     N, T, K, H, Dm, nb, B = (shape[k] for k in ("N", "T", "K", "H", "D", "nb", "B"))
     onet = O.build_oracle(N, T, K, H, Dm, nb, dtype=torch.float64, faithful=False)
+    if conditioned:
+        x, tgt, y_ref, ograds, _ = conditioned_case(onet, B, N, T, seeds=(seed,), thr=COND_THR)
+        slack = {k: 0.0 for k in ograds}
+    else:
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, N, 1, T, generator=g)
+        tgt = torch.randn(B, N, 12, generator=g)
+        y_ref, ograds = _oracle_run(onet, x.double(), tgt.double())
+        slack = kink_slack(onet, x, tgt, ograds, KINK_TAU)
+    fp32_err = oracle_fp32_grad_err(onet, x, tgt, ograds)
+    with torch.no_grad():
+        _, oblocks, oatts = O.net_forward(onet.named(), x.double(), onet.adj_pa, onet.cheb, nb, H, 32,
+                                          faithful=False, return_blocks=True)
     tmd, pa = O.synthetic_graph(N, 0)
     from dstagnn_drought_b200 import make_model
     net = make_model(dev, 1, nb, 1, K, 32, 32, 1, torch.from_numpy(tmd), torch.from_numpy(pa),
                      torch.from_numpy(tmd), 12, T, N, Dm, 32, 32, H)
     net.load_state_dict({k: v.detach().float() for k, v in onet.named().items()})
     net.eval()
-    g = torch.Generator().manual_seed(3)
-    x = torch.randn(B, N, 1, T, generator=g)
-    tgt = torch.randn(B, N, 12, generator=g)
-    y_ref = onet(x.double())
-    torch.nn.SmoothL1Loss()(y_ref, tgt.double()).backward()
-    ograds = {k: v.grad for k, v in onet.named().items()}
-    # yardstick for the ill-conditioned gradients (attention projections: tiny sums of cancelling
-    # terms): the error the SAME algorithm makes in plain fp32 on the CPU, against its fp64 run
-    onet32 = O.build_oracle(N, T, K, H, Dm, nb, dtype=torch.float32, faithful=False)
-    for k, v in onet32.named().items():
-        v.data.copy_(onet.named()[k].data.float())
-    torch.nn.SmoothL1Loss()(onet32(x.float()), tgt.float()).backward()
-    fp32_err = {k: (rel_err(v.grad, ograds[k]) if v.grad is not None else 0.0) for k, v in onet32.named().items()}
-
-    # ReLU kinks: a pre-activation within fp32 rounding of zero can land on either side of it, and the
-    # forward contractions that sum K-outer slices atomically make the side depend on the summation order.
-    # Measured with tools/grad_noise.py at the T = 144 shape: 1 of 340 992 activations (3e-9 against a
-    # maximum of 0.3) flips in ~10 % of the repetitions and moves a handful of gradients by 1e-3 -- the
-    # same jump torch's own fp32 kernels make against an fp64 run.  Such a repetition is drawn again.
-    for attempt in range(3):
-        net.zero_grad(set_to_none=True)
-        y = net(x.to(dev))
-        torch.nn.SmoothL1Loss()(y, tgt.to(dev)).backward()
-        assert rel_err(y.detach(), y_ref.detach()) < TOL_PRED
-        bad = []
-        for k, p in net.named_parameters():
-            if ograds[k] is None:
-                assert p.grad is None, k
-            else:
-                e = rel_err(p.grad, ograds[k])
-                if not e < max(5e-4, 3 * fp32_err[k]):
-                    bad.append(f"{k}: {e:.3e} (fp32 oracle itself: {fp32_err[k]:.3e})")
-        if not bad:
-            break
+    blocks, atts = [], []
+    for b in net.BlockList:
+        b.register_forward_hook(lambda m, i, o: (blocks.append(o[0].detach()), atts.append(o[1].detach()), None)[2])
+    y = net(x.to(dev))
+    torch.nn.SmoothL1Loss()(y, tgt.to(dev)).backward()
+    assert rel_err(y.detach(), y_ref) < TOL_PRED
+    for i in range(nb):
+        assert rel_err(blocks[i], oblocks[i]) < TOL_PRED, f"block {i} output"
+        assert rel_err(atts[i], oatts[i]) < TOL_PRED, f"block {i} logits"
+    bad, worst, strict = [], 0.0, 0
+    for k, p in net.named_parameters():
+        if ograds[k] is None:
+            assert p.grad is None, k
+            continue
+        e = rel_err(p.grad, ograds[k])
+        worst = max(worst, e)
+        tol = max(TOL_GRAD, 3 * fp32_err[k], 2 * slack[k])
+        strict += tol == TOL_GRAD
+        if not e < tol:
+            bad.append(f"{k}: {e:.3e} (fp32 oracle itself: {fp32_err[k]:.3e}, kink slack {slack[k]:.3e})")
+    print(case, "data seed", seed, "pred", rel_err(y.detach(), y_ref), "worst grad", worst,
+          f"; {strict} of {sum(v is not None for v in ograds.values())} gradient tensors held to {TOL_GRAD}")
     assert not bad, "; ".join(bad)
+
+
+def test_forward_is_run_to_run_reproducible():
+    """Every forward reduction has a fixed order (split-K partials go through a workspace and
+    dstag_sum_slices, never atomics): repeated forwards are bit-identical, also at the T = 144 shape whose
+    pre_conv / final_conv products split their reduction."""
+    from oracle import dstagnn_oracle as O
+    from dstagnn_drought_b200 import make_model
+    dev = torch.device("cuda:0")
+    for (N, T, K, H, Dm, nb, B) in ((37, 144, 2, 2, 64, 2, 2), (307, 12, 3, 3, 128, 2, 2)):
+        tmd, pa = O.synthetic_graph(N, 0)
+        torch.manual_seed(1)
+        net = make_model(dev, 1, nb, 1, K, 32, 32, 1, torch.from_numpy(tmd), torch.from_numpy(pa),
+                         torch.from_numpy(tmd), 12, T, N, Dm, 32, 32, H)
+        net.eval()
+        x = torch.randn(B, N, 1, T, generator=torch.Generator().manual_seed(5)).to(dev)
+        with torch.no_grad():
+            ys = [net(x).clone() for _ in range(5)]
+        assert all(torch.equal(ys[0], yy) for yy in ys[1:])
 
 
 def test_train_mode_runs_and_dropout_is_active():

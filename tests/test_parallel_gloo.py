@@ -46,31 +46,40 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, overlap, ret):
+def _worker(rank, world, port, overlap, ret, zero_mode="buckets"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     net = TinyNet()
     buckets = GradBuckets(net, overlap=overlap)
+    opt = torch.optim.SGD([p for p in net.parameters()], lr=0.0)
     g = torch.Generator().manual_seed(11)
     x = torch.randn(8, 6, generator=g)
     y = torch.randn(8, 2, generator=g)
     xs, ys = x.chunk(world)[rank], y.chunk(world)[rank]
-    for _ in range(2):                                   # second step checks zero() re-arms the hooks
-        buckets.zero()
+    for _ in range(3):                                   # later steps check that the hooks are re-armed
+        if zero_mode == "buckets":
+            buckets.zero()
+        else:
+            # the reference loop's own call (train_DSTAGNN_my.py:154): set_to_none=True detaches the views
+            opt.zero_grad(set_to_none=(zero_mode == "none"))
         torch.nn.functional.smooth_l1_loss(net(xs), ys).backward()
         buckets.finish()
+    for b, flat in buckets.buckets.items():              # every live gradient lives in its bucket again
+        for p, v in zip(buckets._members[b], buckets._views[b]):
+            assert p.grad is not None and p.grad.data_ptr() == v.data_ptr()
     if rank == 0:
         ret["grads"] = {k: (p.grad.clone() if p.grad is not None else None) for k, p in net.named_parameters()}
         ret["numel"] = buckets.numel
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False])
-def test_two_rank_average_equals_full_batch(overlap):
+@pytest.mark.parametrize("overlap,zero_mode", [(True, "buckets"), (False, "buckets"), (True, "none"), (False, "none"),
+                                               (True, "zeros")])
+def test_two_rank_average_equals_full_batch(overlap, zero_mode):
     mgr = mp.Manager()
     ret = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, overlap, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, overlap, ret, zero_mode), nprocs=2, join=True)
     net = TinyNet()
     g = torch.Generator().manual_seed(11)
     x = torch.randn(8, 6, generator=g)
