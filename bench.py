@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the DSTAGNN block-stack training step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload pems07|pems04|pems08|gambia|syn4096] [--precision tf32x3|fp32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train|infer]
+                    [--workload pems07|pems04|pems08|pems03|gambia|syn4096] [--precision tf32x3|fp32|tf32]
+                    [--batch B] [--sweep B1,B2,...]
 
 ours:      N ranks (torchrun for N>1), each a full replica with B_local samples; a step is
            zero-grad -> forward -> SmoothL1 -> backward (-> gradient all-reduce) -> Adam.
            `value`  = samples/s with the batch resident in HBM (CUDA events, max over ranks);
            `e2e`    = the same step through the public module API with HOST (pinned) inputs,
                       H2D copies and a D2H read of the loss inside the timed region.
-reference: the reference's algorithm (CPU oracle port, reference op order: the Python loop over
-           time steps and Chebyshev orders) on the box's host cores, rank 0 only.
-One JSON line is printed by rank 0.
+reference: the reference's own CPU path on the box's host cores, rank 0 only: the UNMODIFIED
+           model/DSTAGNN_my.py staged in oracle/_ref by oracle/build_ref.py (`kind: "reference"`), or -- when it is
+           not staged -- the CPU oracle port with the reference's op order (`kind: "port"`).  Batch = the batch of
+           the workload's own configurations/*.conf (12 for PEMS07), reduced only if the host RAM cannot hold the
+           reference's autograd saves (stated in `sample`).
+--mode infer: eval() / no_grad() forward only (BASELINE config 2: PEMS08 batch sweep with --sweep).
+One JSON line is printed by rank 0 (one per batch size with --sweep).
 """
 from __future__ import annotations
 
@@ -30,15 +35,20 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: N, T, K, H, D, nb_block, per-GPU batch, P   
-    "pems07": dict(N=883, T=12, K=3, H=4, D=512, nb=4, B=64, P=12),
-    "pems04": dict(N=307, T=12, K=3, H=3, D=512, nb=4, B=32, P=12),
-    "pems08": dict(N=170, T=12, K=3, H=3, D=512, nb=4, B=64, P=12),
-    "pems03": dict(N=358, T=12, K=3, H=3, D=512, nb=4, B=32, P=12),
-    "gambia": dict(N=2139, T=144, K=2, H=2, D=64, nb=2, B=4, P=12),
-    "syn4096": dict(N=4096, T=12, K=3, H=4, D=512, nb=4, B=16, P=12),
-    "tiny": dict(N=64, T=12, K=3, H=2, D=32, nb=2, B=4, P=12),
+    # conf_B: batch_size of the reference's configurations/<name>_dstagnn.conf (the CPU arms run it)
+    "pems07": dict(N=883, T=12, K=3, H=4, D=512, nb=4, B=64, P=12, conf_B=12),
+    "pems04": dict(N=307, T=12, K=3, H=3, D=512, nb=4, B=32, P=12, conf_B=32),
+    "pems08": dict(N=170, T=12, K=3, H=3, D=512, nb=4, B=64, P=12, conf_B=64),
+    "pems03": dict(N=358, T=12, K=3, H=3, D=512, nb=4, B=32, P=12, conf_B=32),
+    "gambia": dict(N=2139, T=144, K=2, H=2, D=64, nb=2, B=4, P=12, conf_B=4),
+    "syn4096": dict(N=4096, T=12, K=3, H=4, D=512, nb=4, B=16, P=12, conf_B=2),
+    "tiny": dict(N=64, T=12, K=3, H=2, D=32, nb=2, B=4, P=12, conf_B=4),
 }
-METRIC = "train samples/sec (fwd+bwd) PEMS07 shape"
+
+
+def metric_name(args):
+    what = "train samples/sec (fwd+bwd)" if args.mode == "train" else "inference samples/sec (eval, no_grad)"
+    return f"{what} {'PEMS07' if args.workload == 'pems07' else args.workload} shape"
 
 
 def synthetic_graph(N, seed=0, density=0.01):
@@ -105,92 +115,142 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port with the reference's op order, on host cores
+# reference arm / CPU baseline: the reference's own model (oracle/_ref) or the oracle port, on host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_step_factory(w, batch):
-    from oracle import dstagnn_oracle as O
+def reference_batch(w, mode):
+    """The conf's own batch, reduced only when the host cannot hold the reference's autograd saves: its
+    Python loop keeps ~3 (B, N, N) fp32 tensors per (time step, order) and block."""
+    batch = w["conf_B"]
+    if mode != "train":
+        return batch, ""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    per_sample = w["nb"] * w["T"] * w["K"] * 3.2 * w["N"] ** 2 * 4
+    fit = int(0.6 * avail / per_sample)
+    if fit >= batch:
+        return batch, ""
+    fit = max(1, fit)
+    return fit, f" (conf batch {batch} needs ~{batch * per_sample / 2**30:.0f} GiB of autograd saves; host has {avail / 2**30:.0f} GiB free)"
+
+
+def cpu_step_factory(w, batch, mode="train"):
+    """One step of the workload on the host cores.  Returns (step, kind, description)."""
     torch.set_num_threads(os.cpu_count())
-    net = O.build_oracle(w["N"], w["T"], w["K"], w["H"], w["D"], w["nb"], P=w["P"], faithful=True)
-    net.train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-    crit = torch.nn.SmoothL1Loss()
+    from oracle.build_ref import import_reference_make_model
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, w["N"], 1, w["T"], generator=g)
     y = torch.randn(batch, w["N"], w["P"], generator=g)
+    make_ref = None if os.environ.get("DSTAG_BENCH_PORT") == "1" else import_reference_make_model()
+    if make_ref is not None:
+        tmd, pa = synthetic_graph(w["N"], 0)
+        torch.manual_seed(1)
+        # argument order of train_DSTAGNN_my.py:85-104; graph = AG => adj_merge = adj_TMD
+        net = make_ref("cpu", 1, w["nb"], 1, w["K"], 32, 32, 1, torch.FloatTensor(tmd), torch.FloatTensor(pa),
+                       torch.FloatTensor(tmd), w["P"], w["T"], w["N"], w["D"], 32, 32, w["H"])
+        kind, desc = "reference", "unmodified reference model/DSTAGNN_my.py make_model('cpu') (oracle/_ref)"
+    else:
+        from oracle import dstagnn_oracle as O
+        net = O.build_oracle(w["N"], w["T"], w["K"], w["H"], w["D"], w["nb"], P=w["P"], faithful=True)
+        kind, desc = "port", "oracle port of the reference CPU path (model/DSTAGNN_my.py op order)"
+    if mode == "train":
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        crit = torch.nn.SmoothL1Loss()
 
-    def step():
-        opt.zero_grad()
-        loss = crit(net(x), y)
-        loss.backward()
-        opt.step()
-        return float(loss)
-    return step
+        def step():
+            opt.zero_grad()
+            loss = crit(net(x), y)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+    else:
+        net.eval()
+
+        def step():
+            with torch.no_grad():
+                return float(net(x).sum())
+    return step, kind, desc
 
 
-def cpu_baseline(w, budget_s=25.0, max_batch=12):
-    """Bounded sample of the same workload: one warm-up + timed steps at a reduced batch."""
-    step = cpu_step_factory(w, 2)
-    t0 = time.time(); step(); t_probe = time.time() - t0          # also the warm-up
-    per_sample = t_probe / 2
-    batch = int(max(1, min(max_batch, budget_s / 3 / max(per_sample, 1e-6))))
-    step = cpu_step_factory(w, batch)
+def cpu_baseline(w, mode="train"):
+    """Bounded sample of the same workload: the conf's batch, one warm-up + best of 2 timed steps."""
+    batch, note = reference_batch(w, mode)
+    step, kind, desc = cpu_step_factory(w, batch, mode)
     step()
     ts = []
     for _ in range(2):
         t0 = time.time(); step(); ts.append(time.time() - t0)
     best = min(ts)
-    return {"value": batch / best, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle port (reference op order, fp32, torch CPU {torch.get_num_threads()} threads), "
-                      f"train step at batch {batch}, 1 warm-up + best of 2"}
+    return {"value": batch / best, "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{desc}, fp32, torch CPU {torch.get_num_threads()} threads, {mode} step at batch {batch}{note}, "
+                      f"1 warm-up + best of 2"}
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    budget = 150.0
-    step = cpu_step_factory(w, 2)
-    t0 = time.time(); step(); per_sample = (time.time() - t0) / 2
-    batch = int(max(1, min(12, budget / total / max(per_sample, 1e-6))))
-    step = cpu_step_factory(w, batch)
-    for _ in range(args.warmup):
+    batch, note = reference_batch(w, args.mode)
+    if args.batch:
+        batch, note = args.batch, " (--batch override)"
+    step, kind, desc = cpu_step_factory(w, batch, args.mode)
+    # bounded run: the whole --steps / --warmup schedule must end within a few minutes
+    t0 = time.time(); step(); t1 = time.time() - t0
+    budget = 240.0
+    steps, warmup = args.steps, max(0, args.warmup - 1)
+    if t1 * (steps + warmup) > budget:
+        warmup = 0
+        steps = max(2, min(args.steps, int(budget / t1)))
+    for _ in range(warmup):
         step()
     t0 = time.time()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.time() - t0
-    val = batch * args.steps / dt
-    sample = (f"oracle port of the reference CPU path (model/DSTAGNN_my.py op order), fp32, "
-              f"{torch.get_num_threads()} threads, batch {batch} per step")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+    val = batch * steps / dt
+    sample = (f"{desc}, fp32, {torch.get_num_threads()} threads, {args.mode} step at batch {batch}{note}; "
+              f"{steps} timed steps" + ("" if steps == args.steps else f" (of the {args.steps} requested: time bound)"))
+    line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup + 1, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, w, batch),
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
                              "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def needs_l2_flush(args, w):
+    """True when one step's working set may fit the 126 MB L2 (small graphs, inference): the timed steps are
+    then separated by an L2 flush.  PEMS07 / GAMBIA / SYN4096 training moves > 1 GB per step."""
+    return args.mode == "infer" or w["N"] < 800
+
+
 def workload_config(args, w, batch):
+    what = (f"train step (zero_grad+fwd+SmoothL1+bwd{'+allreduce' if args.gpus > 1 else ''}+Adam)"
+            if args.mode == "train" else "inference (eval, no_grad forward)")
     return {"workload": f"{args.workload}: N={w['N']} T={w['T']} K={w['K']} H={w['H']} d_model={w['D']} "
-                        f"nb_block={w['nb']} in_channels=1, train step (zero_grad+fwd+SmoothL1+bwd"
-                        f"{'+allreduce' if args.gpus > 1 else ''}+Adam)",
+                        f"nb_block={w['nb']} in_channels=1, {what}",
             "batch_per_gpu": batch, "global_batch": batch * max(1, args.gpus),
             "parallelism": f"dp{args.gpus}", "graph": "synthetic 1%-dense STAG/STRG, seed 0",
-            "l2_policy": "per-step working set (>1 GB of N x N maps and activations) exceeds the 126 MB L2"}
+            "l2_policy": ("L2 flushed (256 MB fill) between timed steps, outside the per-step CUDA-event pairs"
+                          if needs_l2_flush(args, w) and args.impl == "ours" else
+                          "per-step working set (>1 GB of N x N maps and activations) exceeds the 126 MB L2")}
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def ncu_traffic(w, args):
+def ncu_traffic(w, args, B):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
     capture (profiles/r01_ncu_cheb_final.md); only valid for the configuration it was taken on."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_cheb_traffic.json")
-    if args.workload != "pems07" or args.precision != "tf32x3" or (args.batch or w["B"]) != 64 or not os.path.exists(path):
+    if (args.workload != "pems07" or args.precision != "tf32x3" or B != 64 or args.mode != "train"
+            or not os.path.exists(path)):
         return None
     with open(path) as f:
         return json.load(f)["mean_bytes_per_launch"]
@@ -213,131 +273,162 @@ def run_ours(args, w):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     set_precision(args.precision)
+    train = args.mode == "train"
 
-    B = args.batch or w["B"]
     tmd, pa = synthetic_graph(w["N"], 0)
     torch.manual_seed(1)
     net = make_model(dev, 1, w["nb"], 1, w["K"], 32, 32, 1, torch.from_numpy(tmd), torch.from_numpy(pa),
                      torch.from_numpy(tmd), w["P"], w["T"], w["N"], w["D"], 32, 32, w["H"])
-    net.train()
-    buckets = GradBuckets(net, overlap=True)
-    live = [p for p in net.parameters() if p.grad is not None]
-    opt = torch.optim.Adam(live, lr=1e-4, fused=True)
-    crit = torch.nn.SmoothL1Loss()
-
-    g = torch.Generator().manual_seed(100 + rank)
-    x_host = torch.randn(B, w["N"], 1, w["T"], generator=g).pin_memory()
-    y_host = torch.randn(B, w["N"], w["P"], generator=g).pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    def step(x, y):
-        buckets.zero()
-        loss = crit(net(x), y)
-        loss.backward()
-        buckets.finish()
-        opt.step()
-        return loss
-
-    def step_e2e():
-        x = x_host.to(dev, non_blocking=True)
-        y = y_host.to(dev, non_blocking=True)
-        loss = step(x, y)
-        loss_host.copy_(loss.detach(), non_blocking=True)
+    if train:
+        net.train()
+        buckets = GradBuckets(net, overlap=True)
+        live = [p for p in net.parameters() if p.grad is not None]
+        opt = torch.optim.Adam(live, lr=1e-4, fused=True)
+        crit = torch.nn.SmoothL1Loss()
+    else:
+        net.eval()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    flush = needs_l2_flush(args, w)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+
     def timed(fn, steps):
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        barrier()
-        ms = a.elapsed_time(b)
+        if flush:
+            # small working sets: evict L2 between steps; every step gets its own event pair so that the
+            # flush itself is outside the timed region
+            evs = []
+            for _ in range(steps):
+                flush_buf.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            barrier()
+            ms = a.elapsed_time(b)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
-    barrier()
+    def measure(B, with_cpu):
+        g = torch.Generator().manual_seed(100 + rank)
+        x_host = torch.randn(B, w["N"], 1, w["T"], generator=g).pin_memory()
+        y_host = torch.randn(B, w["N"], w["P"], generator=g).pin_memory()
+        x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+        # the step's result read back by the host: the loss (train) or the predictions (inference)
+        res_host = (torch.zeros((), dtype=torch.float32) if train else torch.zeros(B, w["N"], w["P"])).pin_memory()
 
-    # ---- headline: device-resident inputs ----
-    sampler = ClockSampler(local) if rank == 0 else None
-    _lib.reset_launch_count()
-    ms = timed(lambda: step(x_dev, y_dev), args.steps)
-    launches = _lib.launch_count()
-    # ---- end to end through the module API with host buffers ----
-    ms_e2e = timed(step_e2e, args.steps)
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    final_loss = float(loss_host)
+        if train:
+            def step(x, y):
+                buckets.zero()
+                loss = crit(net(x), y)
+                loss.backward()
+                buckets.finish()
+                opt.step()
+                return loss.detach()
+        else:
+            def step(x, y):
+                with torch.no_grad():
+                    return net(x)
 
-    # ---- per-kernel CUDA-event profile of the same step (separate pass; not the headline) ----
-    _lib.prof_enable(True)
-    prof_steps = min(args.steps, 3)
-    for _ in range(prof_steps):
-        step(x_dev, y_dev)
-    torch.cuda.synchronize()
-    prof = _lib.prof_results()
-    _lib.prof_enable(False)
+        def step_e2e():
+            x = x_host.to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True) if train else None
+            res_host.copy_(step(x, y), non_blocking=True)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        for _ in range(max(args.warmup, 3)):
+            step(x_dev, y_dev)
+        barrier()
 
-    pk = peaks()
-    gemm_ms = sum(v[1] for v in prof.values()) / prof_steps
-    cheb = {t: prof[t] for t in ("cheb_fwd", "cheb_bwd_dx", "cheb_bwd_dmap") if t in prof}
-    # dominant kernel family: the Chebyshev contraction (forward + its two backward products)
-    c_calls = sum(v[0] for v in cheb.values())
-    c_ms = sum(v[1] for v in cheb.values())
-    c_flops = sum(v[2] for v in cheb.values())
-    achieved = c_flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "Chebyshev contraction (cheb_fwd + cheb_bwd_dx + cheb_bwd_dmap)",
-                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                "peak_source": f"{pk['src']} dense bf16 (sustained); fp32-grade 3xTF32 issues 6 bf16-equivalent "
-                               "MMA passes per algorithmic flop, so its ceiling is peak/6",
-                "traffic": ncu_traffic(w, args), "launches_per_step": c_calls / prof_steps,
-                "avg_launch_ms": c_ms / max(c_calls, 1), "share_of_step": (c_ms / prof_steps) / (ms / args.steps),
-                "precision": args.precision}
-    breakdown = {t: {"calls_per_step": v[0] / prof_steps, "ms_per_step": round(v[1] / prof_steps, 4),
-                     "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 2)} for t, v in
-                 sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        # ---- headline: device-resident inputs ----
+        sampler = ClockSampler(local) if rank == 0 else None
+        _lib.reset_launch_count()
+        ms = timed(lambda: step(x_dev, y_dev), args.steps)
+        launches = _lib.launch_count()
+        # ---- end to end through the module API with host buffers ----
+        ms_e2e = timed(step_e2e, args.steps)
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        final = float(res_host) if train else float(res_host.abs().mean())
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(w)
+        # ---- per-kernel CUDA-event profile of the same step (separate pass; not the headline) ----
+        _lib.prof_enable(True)
+        prof_steps = min(args.steps, 3)
+        for _ in range(prof_steps):
+            step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        prof = _lib.prof_results()
+        _lib.prof_enable(False)
+        if rank != 0:
+            return
 
-    n = max(1, args.gpus)
-    h2d = x_host.numel() * 4 + y_host.numel() * 4
-    line = {"metric": METRIC if args.workload == "pems07" else f"train samples/sec (fwd+bwd) {args.workload} shape",
-            "value": B * n * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": n, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, w, B),
-            "e2e": {"value": B * n * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "precision": args.precision, "final_loss": final_loss,
-            "gemm_ms_per_step_profiled": round(gemm_ms, 3)}
-    print(json.dumps(line), flush=True)
-    out_dir = os.path.join(ROOT, "gpurun_out")
-    if os.path.isdir(out_dir):
-        with open(os.path.join(out_dir, f"breakdown_{args.workload}_{args.precision}_n{n}.json"), "w") as f:
-            json.dump({"ms_per_step": ms / args.steps, "breakdown": breakdown}, f, indent=1)
-    if args.verbose:
-        for t, v in breakdown.items():
-            print(f"  {t:45s} {v['calls_per_step']:6.1f} calls {v['ms_per_step']:9.3f} ms  {v['tflops']:8.2f} TF/s",
-                  file=sys.stderr)
+        pk = peaks()
+        gemm_ms = sum(v[1] for v in prof.values()) / prof_steps
+        cheb = {t: prof[t] for t in ("cheb_fwd", "cheb_bwd_dx", "cheb_bwd_dmap") if t in prof}
+        # dominant kernel family: the Chebyshev contraction (forward + its two backward products)
+        c_calls = sum(v[0] for v in cheb.values())
+        c_ms = sum(v[1] for v in cheb.values())
+        c_flops = sum(v[2] for v in cheb.values())
+        achieved = c_flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
+        roofline = {"bound": "tensor",
+                    "kernel": "Chebyshev contraction (" + " + ".join(sorted(cheb)) + ")",
+                    "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                    "peak_source": f"{pk['src']} dense bf16 (sustained); fp32-grade 3xTF32 issues 6 bf16-equivalent "
+                                   "MMA passes per algorithmic flop, so its ceiling is peak/6",
+                    "traffic": ncu_traffic(w, args, B), "launches_per_step": c_calls / prof_steps,
+                    "avg_launch_ms": c_ms / max(c_calls, 1), "share_of_step": (c_ms / prof_steps) / (ms / args.steps),
+                    "precision": args.precision}
+        breakdown = {t: {"calls_per_step": v[0] / prof_steps, "ms_per_step": round(v[1] / prof_steps, 4),
+                         "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 2),
+                         "gbs": round(v[3] / max(v[1], 1e-9) / 1e6, 1)} for t, v in
+                     sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+        cpu = None
+        if world == 1 and with_cpu and not args.no_cpu_baseline:
+            cpu = cpu_baseline(w, args.mode)
+
+        n = max(1, args.gpus)
+        h2d = x_host.numel() * 4 + (y_host.numel() * 4 if train else 0)
+        d2h = res_host.numel() * 4
+        line = {"metric": metric_name(args),
+                "value": B * n * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": n, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, w, B),
+                "e2e": {"value": B * n * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "precision": args.precision, "final_loss" if train else "mean_abs_prediction": final,
+                "kernel_ms_per_step_profiled": round(gemm_ms, 3)}
+        print(json.dumps(line), flush=True)
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, f"breakdown_{args.workload}_{args.mode}_b{B}_{args.precision}_n{n}.json"), "w") as f:
+                json.dump({"ms_per_step": ms / args.steps, "launches_per_step": launches / args.steps,
+                           "breakdown": breakdown}, f, indent=1)
+        if args.verbose:
+            for t, v in breakdown.items():
+                print(f"  {t:45s} {v['calls_per_step']:6.1f} calls {v['ms_per_step']:9.3f} ms  {v['tflops']:8.2f} TF/s "
+                      f"{v['gbs']:8.1f} GB/s", file=sys.stderr)
+
+    batches = [int(b) for b in args.sweep.split(",")] if args.sweep else [args.batch or w["B"]]
+    for i, B in enumerate(batches):
+        measure(B, with_cpu=(i == 0))
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,6 +442,8 @@ def main():
     ap.add_argument("--workload", default="pems07", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--sweep", default="", help="comma-separated per-GPU batch sizes: one JSON line each")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

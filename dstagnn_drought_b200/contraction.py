@@ -138,6 +138,7 @@ def _k_order(pl: Plan, A, B):
     return rev if score(rev) > score(fwd) else fwd
 
 
+_FP32_SPECS = [t for t in os.environ.get("DSTAG_FP32_SPECS", "").split(",") if t]
 _desc_cache = {}
 _swap_cache = {}
 _dims_cache = {}
@@ -150,6 +151,29 @@ def set_reproducible(on: bool):
     to run).  The differentiable ``contract`` always runs its FORWARD product reproducibly."""
     global _reproducible
     _reproducible = bool(on)
+
+
+def rows_view(t: torch.Tensor):
+    """(rows, cols, ld) when ``t`` can be read as a rows x cols matrix with a constant row stride ld >= cols
+    (contiguous tensors, row-padded tensors, one half of a packed [Q | K] buffer, ...), else None."""
+    if t.dim() == 0:
+        return (1, 1, 1)
+    cols, d = 1, t.dim() - 1
+    while d >= 0 and (t.shape[d] == 1 or t.stride(d) == cols):      # trailing contiguous block
+        cols *= t.shape[d]
+        d -= 1
+    if d < 0:
+        return (1, cols, cols)
+    ld, rows = t.stride(d), t.shape[d]
+    if ld < cols:
+        return None
+    expect = ld * t.shape[d]
+    for e in range(d - 1, -1, -1):                                   # the leading dims must collapse into one
+        if t.shape[e] != 1 and t.stride(e) != expect:
+            return None
+        rows *= t.shape[e]
+        expect *= t.shape[e]
+    return (rows, cols, ld)
 
 
 def _workspace(n: int, out: torch.Tensor) -> torch.Tensor:
@@ -357,6 +381,8 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
                                 accumulate=accumulate, split_k=split_k, precision=precision, tag=tag,
                                 reproducible=reproducible)
+    if _FP32_SPECS and precision is None and any(t in spec or (tag and t in tag) for t in _FP32_SPECS):
+        precision = _lib.PREC_FP32          # debugging aid: DSTAG_FP32_SPECS=substring,... forces the exact engine
     lib = _lib.load()
     _check(A, "A"), _check(B, "B")
     for opt in (a_mul, c_add, c_mul):
@@ -382,7 +408,8 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
     if reproducible is None:
         reproducible = _reproducible
     # two-stage (workspace + fixed-order sum) instead of atomics: plain stores into a dense output only
-    two_stage = reproducible and accumulate == ACC_STORE and c_mul is None and is_row_padded(out)
+    rv = rows_view(out) if (reproducible and accumulate == ACC_STORE and c_mul is None) else None
+    two_stage = rv is not None
     ws = None
     if split_k > 1 and two_stage:
         split_k = even_split(K, split_k)
@@ -420,9 +447,7 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             with _lib.prof_range(tag or ("gemm:" + spec), 2 * M * N * K * nb, nbytes):
                 _lib.check(lib.dstag_gemm(C.byref(g), st), f"dstag_gemm('{spec}')")
         if ws is not None:
-            cols = out.shape[-1] if out.dim() else 1
-            rows = out.numel() // max(cols, 1)
-            ld = out.stride(-2) if out.dim() >= 2 else cols
+            rows, cols, ld = rv
             _lib.check(lib.dstag_sum_slices(ws.data_ptr(), ws.stride(0), ws.shape[0], out.data_ptr(), rows, cols, ld, st),
                        "dstag_sum_slices")
     return out

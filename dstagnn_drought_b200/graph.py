@@ -16,7 +16,12 @@ def scaled_Laplacian(W):
 
     lambda_max is the eigenvalue with the largest real part (ARPACK, ``which='LR'``),
     as in the reference; W may be a numpy array or a torch tensor and the result keeps
-    that kind (tensor results are float32 on W's device)."""
+    that kind (tensor results are float32 on W's device).
+
+    The reference hands ARPACK the float32 adjacency and lets it draw a random start vector, so
+    its own lambda_max -- and with it T_1, T_2 -- moves by ~3e-6 (relative) from run to run and from
+    machine to machine.  Here the eigenvalue is computed in float64 from a fixed start vector: one
+    value, inside the reference's own spread, identical on every rank and every box."""
     from scipy.sparse.linalg import eigs
 
     is_tensor = torch.is_tensor(W)
@@ -25,9 +30,9 @@ def scaled_Laplacian(W):
         raise AssertionError("adjacency matrix must be square")
     n = w.shape[0]
     lap = np.diag(w.sum(axis=1)) - w
-    # fixed start vector: every rank / run gets bit-identical polynomials (the reference lets
-    # ARPACK draw a random one; the converged eigenvalue is the same to ~1e-7)
-    lam_max = eigs(lap, k=1, which="LR", v0=np.random.RandomState(0).uniform(-1.0, 1.0, n))[0].real
+    lam_max = eigs(lap.astype(np.float64), k=1, which="LR",
+                   v0=np.random.RandomState(0).uniform(-1.0, 1.0, n))[0].real
+    lam_max = lap.dtype.type(lam_max) if np.issubdtype(lap.dtype, np.floating) else lam_max
     lt = 2.0 * lap / lam_max - np.eye(n)
     if is_tensor:
         return torch.from_numpy(lt).float().to(W.device)

@@ -222,6 +222,9 @@ def sum_over_f(ds: torch.Tensor, B: int, F: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 # spatial attention -> softmax -> Chebyshev contraction
 # ----------------------------------------------------------------------------------------
+_DQK_CHAIN = int(os.environ.get("DSTAG_DQK_CHAIN", "64"))
+
+
 def _pad_ld(n: int) -> int:
     return (n + 31) // 32 * 32      # 128-byte rows: aligned vector / TMA access to the N x N maps
 
@@ -293,8 +296,14 @@ class SpatialChebConv(torch.autograd.Function):
         dSv = dS[..., :N]
         dqk = torch.empty_like(qk)
         alpha = 1.0 / math.sqrt(dk)
-        contract_raw("bkji,bjkd->bikd", dSv, Ks, out=dqk[:, :, 0], alpha=alpha)
-        contract_raw("bkji,bikd->bjkd", dSv, Qs, out=dqk[:, :, 1], alpha=alpha)
+        # The rows of dS sum to zero (softmax backward), so these two products cancel heavily, and the tensor
+        # core's fp32 accumulator TRUNCATES at every k-step: over a chain of N / 8 steps the bias reached
+        # 1.3e-4 of max|grad| on the real PEMS04 graph.  Chains of <= _DQK_CHAIN terms, partial results summed
+        # in fp32 (round to nearest) by dstag_sum_slices, keep the error at the level of a plain fp32 product;
+        # the outputs are small (B x N x K x d_k), so the extra slices cost nothing measurable.
+        sk = max(1, -(-N // _DQK_CHAIN))
+        contract_raw("bkji,bjkd->bikd", dSv, Ks, out=dqk[:, :, 0], alpha=alpha, split_k=sk, reproducible=True)
+        contract_raw("bkji,bikd->bjkd", dSv, Qs, out=dqk[:, :, 1], alpha=alpha, split_k=sk, reproducible=True)
         dbias = None
         if ctx.needs_input_grad[1]:
             dbias = colsum(dS, B, K * N * ld).view(K, N, ld)

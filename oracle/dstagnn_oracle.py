@@ -46,14 +46,21 @@ def scaled_laplacian(W: np.ndarray) -> np.ndarray:
 
     lambda_max is the eigenvalue of largest real part of the (generally
     non-symmetric) Laplacian, obtained in the reference with ARPACK
-    ``eigs(L, k=1, which='LR')`` (lib/utils.py:170).
+    ``eigs(L, k=1, which='LR')`` (lib/utils.py:170) -- there in the precision of W (float32 from the
+    driver, train_DSTAGNN_my.py:76) and from a random start vector, so the reference's own value moves
+    by ~3e-6 between runs.  The oracle computes it in float64 from a fixed start vector (one value,
+    inside that spread, the same on every machine -- the parity tests need reproducible polynomials)
+    and then follows the reference's arithmetic in W's precision.
     """
     from scipy.sparse.linalg import eigs
 
     W = np.asarray(W)
     assert W.shape[0] == W.shape[1]
     lap = np.diag(W.sum(axis=1)) - W
-    lam = eigs(lap, k=1, which="LR")[0].real
+    lam = eigs(lap.astype(np.float64), k=1, which="LR",
+               v0=np.random.RandomState(0).uniform(-1.0, 1.0, W.shape[0]))[0].real
+    if np.issubdtype(lap.dtype, np.floating):
+        lam = lap.dtype.type(lam)
     return (2.0 * lap) / lam - np.identity(W.shape[0])
 
 

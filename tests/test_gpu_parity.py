@@ -76,11 +76,11 @@ ORACLE_CASES = {
     "n170_d64": (dict(N=170, T=12, K=3, H=3, D=64, nb=2, B=3), 4, True),
     "n307_d128": (dict(N=307, T=12, K=3, H=3, D=128, nb=2, B=2), 3, True),
     "n65_t24": (dict(N=65, T=24, K=2, H=2, D=64, nb=2, B=2), 3, True),
-    "n37_t144": (dict(N=37, T=144, K=2, H=2, D=64, nb=2, B=2), 6, True),
+    "n37_t144": (dict(N=37, T=144, K=2, H=2, D=64, nb=2, B=2), 5, True),
     # the BASELINE configurations at their REAL shapes, batch reduced to what the fp64 CPU
     # oracle finishes in seconds
-    "pems08_full": (dict(N=170, T=12, K=3, H=3, D=512, nb=4, B=2), 11, True),
-    "pems04_full": (dict(N=307, T=12, K=3, H=3, D=512, nb=4, B=2), 39, True),
+    "pems08_full": (dict(N=170, T=12, K=3, H=3, D=512, nb=4, B=2), 12, True),
+    "pems04_full": (dict(N=307, T=12, K=3, H=3, D=512, nb=4, B=2), 21, True),
     "pems03_full": (dict(N=358, T=12, K=3, H=3, D=512, nb=4, B=2), 4, False),
     "pems07_full": (dict(N=883, T=12, K=3, H=4, D=512, nb=4, B=2), 4, False),
     # GAMBIA drought conf (in_channels = 1): N = 2139 > 1024 takes the shared-memory strip map
@@ -88,7 +88,7 @@ ORACLE_CASES = {
     "gambia_full": (dict(N=2139, T=144, K=2, H=2, D=64, nb=2, B=1), 4, False),
     # N = 4096: a 16-row logit strip does not fit in shared memory -> logits GEMM + row softmax + Hadamard
     # operand (the DSTAG_ERR_SMEM branch of ops.SpatialChebConv)
-    "syn4096_nb2": (dict(N=4096, T=12, K=3, H=4, D=512, nb=2, B=1), 11, True),
+    "syn4096_nb2": (dict(N=4096, T=12, K=3, H=4, D=512, nb=2, B=1), 4, False),
 }
 COND_THR = 5e-5
 KINK_TAU = 1e-6

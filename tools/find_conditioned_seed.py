@@ -26,7 +26,7 @@ from test_gpu_parity import COND_THR, ORACLE_CASES  # noqa: E402
 
 def main():
     for name in sys.argv[1:] or sorted(ORACLE_CASES):
-        shape, _ = ORACLE_CASES[name]
+        shape = ORACLE_CASES[name][0]
         N, T, K, H, D, nb, B = (shape[k] for k in ("N", "T", "K", "H", "D", "nb", "B"))
         t0 = time.time()
         net = O.build_oracle(N, T, K, H, D, nb, dtype=torch.float64, faithful=False)
