@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -49,9 +49,9 @@ SIGNATURES = {
     "dstag_gemm": (C.c_int, [C.POINTER(Gemm), _F]),
     "dstag_gemm_uses_tensor_cores": (C.c_int, [C.POINTER(Gemm)]),
     "dstag_layernorm_fwd": (C.c_int, [_F, _i64, _i64, _i32, _i64, _F, _i32, _i64, _F, _F, _f32, _F, _i64, _F, _F,
-                                      _i32, _i32, _f32, _u64, _F]),
+                                      _i32, _i32, _f32, _u64, _F, _F]),
     "dstag_layernorm_bwd": (C.c_int, [_F, _i64, _F, _i64, _i64, _i32, _i64, _F, _i32, _i64, _F, _F, _F, _F, _i64,
-                                      _F, _F, _i32, _i32, _f32, _u64, _F]),
+                                      _F, _F, _i32, _i32, _f32, _u64, _F, _F]),
     "dstag_sum_slices": (C.c_int, [_F, _i64, _i32, _F, _i64, _i64, _i64, _F]),
     "dstag_colsum": (C.c_int, [_F, _F, _i64, _i64, _i64, _F]),
     "dstag_transpose": (C.c_int, [_F, _i64, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
@@ -65,13 +65,20 @@ SIGNATURES = {
     "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_outer_sum_supported": (C.c_int, [_i32, _i32, _i32]),
     "dstag_outer_sum": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _F]),
-    "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F]),
+    "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F, _F]),
     "dstag_tail_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i32, _i32, _f32,
-                                 _u64, _F]),
+                                 _u64, _F, _F]),
     "dstag_tail_fused_supported": (C.c_int, [_i32, _i32]),
-    "dstag_tail_fused_fwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F]),
+    "dstag_tail_fused_fwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F,
+                                       _F]),
     "dstag_tail_fused_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i64, _i32, _i32,
-                                       _f32, _u64, _F]),
+                                       _f32, _u64, _F, _F]),
+    "dstag_smooth_l1_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _F]),
+    "dstag_smooth_l1_bwd": (C.c_int, [_F, _F, _F, _F, _i64, _F]),
+    "dstag_adam_step": (C.c_int, [_F, _F, _F, _F, _i64, _f32, _f32, _f32, _f32, _f32, _F, _u64, _F]),
+    "dstag_tick": (C.c_int, [_F, _i32, _F]),
+    "dstag_bias_transpose": (C.c_int, [_F, C.POINTER(C.c_void_p), _i32, _F, _i32, _i32, _F]),
+    "dstag_bias_transpose_bwd": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _F]),
 }
 
 _lib = None

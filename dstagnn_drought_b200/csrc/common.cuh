@@ -94,6 +94,13 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t seed) {
   }
   return make_uint4(c0, c1, c2, c3);
 }
+// Dropout key of a launch: the host-side per-site key, advanced by a DEVICE-resident step counter when one
+// is given.  A training step captured in a CUDA graph replays the same kernel arguments every time; the
+// counter (bumped once per step by dstag_tick, inside the graph) is what makes the masks differ per step.
+__device__ __forceinline__ unsigned long long fold_seed(unsigned long long seed, const unsigned long long* seed_dev) {
+  return seed_dev ? seed + 0x9E3779B97F4A7C15ull * (*seed_dev + 1ull) : seed;
+}
+
 // Inverted-dropout multiplier for element e: 0 with probability p, else 1/(1-p).
 __device__ __forceinline__ float dropout_scale(uint64_t e, uint64_t seed, float p, float inv_keep) {
   const uint4 r = philox4x32(e >> 2, seed);

@@ -16,7 +16,8 @@ ln_fwd_kernel(const float* __restrict__ a, long long a_s0, long long a_s1, int a
               const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, float* __restrict__ y, long long y_ld,
               float* __restrict__ mean, float* __restrict__ rstd, int rows, int L, float drop_p,
-              unsigned long long seed) {
+              unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   extern __shared__ float sm[];
   float* row = sm;        // L floats; slot c is only ever touched by thread (c % blockDim)
   float* red = sm + L;    // 33 floats
@@ -59,7 +60,8 @@ ln_bwd_kernel(const float* __restrict__ dy, long long dy_ld, const float* __rest
               long long tab_ld, const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, float* __restrict__ dpre, long long dpre_ld,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int L, float drop_p,
-              unsigned long long seed) {
+              unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   extern __shared__ float sm[];
   float* xh = sm;            // xhat
   float* gg = sm + L;        // dy * gamma
@@ -309,7 +311,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __restrict__ tab, int tab_mod,
                    long long tab_ld, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ y, long long y_ld, float* __restrict__ mean, float* __restrict__ rstd, int rows,
-                   int L, float drop_p, unsigned long long seed) {
+                   int L, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const float invL = 1.f / (float)L;
@@ -384,7 +387,8 @@ ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* _
                    const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dpre,
                    long long dpre_ld, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int L,
-                   float drop_p, unsigned long long seed) {
+                   float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   extern __shared__ float sm[];          // [2][128 * NV] CTA-level d gamma / d beta accumulators
   constexpr int W = 128 * NV;
   float* sg = sm;
@@ -545,7 +549,8 @@ extern "C" {
 int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
                         const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma, const float* beta,
                         float eps, float* y, int64_t y_ld, float* mean, float* rstd, int32_t rows, int32_t L,
-                        float drop_p, uint64_t seed, void* stream) {
+                        float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(a && gamma && beta && y && mean && rstd, "dstag_layernorm_fwd: null pointer");
   DSTAG_CHECK_ARG(y_ld >= L && (tab == nullptr || tab_ld >= L), "dstag_layernorm_fwd: leading dimension < L");
   DSTAG_CHECK_ARG(rows > 0 && L > 0 && a_div > 0 && (tab == nullptr || tab_mod > 0),
@@ -562,7 +567,7 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
 #define DSTAG_LN_FWD(NV_)                                                                                       \
   case NV_:                                                                                                     \
     ln_fwd_warp_kernel<NV_><<<grid, 256, 0, (cudaStream_t)stream>>>(a, a_s0, tab, tab_mod, tab_ld, gamma, beta, eps, y, \
-                                                                    y_ld, mean, rstd, rows, L, drop_p, seed);    \
+                                                                    y_ld, mean, rstd, rows, L, drop_p, seed, sd); \
     break
     switch (nv) {
       DSTAG_LN_FWD(1); DSTAG_LN_FWD(2); DSTAG_LN_FWD(3); DSTAG_LN_FWD(4);
@@ -576,7 +581,7 @@ int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_di
   if (rc) return rc;
   const int grid = rows < kNumSMs * 8 ? rows : kNumSMs * 8;
   ln_fwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
-      a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, beta, eps, y, y_ld, mean, rstd, rows, L, drop_p, seed);
+      a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, beta, eps, y, y_ld, mean, rstd, rows, L, drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_layernorm_fwd");
 }
 
@@ -584,7 +589,8 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
                         int64_t a_sc, const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma,
                         const float* mean, const float* rstd, float* dpre, int64_t dpre_ld, float* dgamma,
                         float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
-                        void* stream) {
+                        const uint64_t* seed_dev, void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(dy_ld >= L && dpre_ld >= L && (tab == nullptr || tab_ld >= L),
                   "dstag_layernorm_bwd: leading dimension < L");
   DSTAG_CHECK_ARG(dy && a && gamma && mean && rstd && dpre && dgamma && dbeta,
@@ -607,7 +613,7 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
 #define DSTAG_LN_BWD(NV_)                                                                                        \
   case NV_:                                                                                                      \
     ln_bwd_warp_kernel<NV_><<<grid, kLnBwdThreads, sm_bytes, (cudaStream_t)stream>>>(                                      \
-        dy, dy_ld, a, a_s0, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed); \
+        dy, dy_ld, a, a_s0, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed, sd); \
     break
     switch (nv) {
       DSTAG_LN_BWD(1); DSTAG_LN_BWD(2); DSTAG_LN_BWD(3); DSTAG_LN_BWD(4);
@@ -622,7 +628,7 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
   const int grid = rows < kNumSMs * 4 ? rows : kNumSMs * 4;
   ln_bwd_kernel<<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
       dy, dy_ld, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, mean, rstd, dpre, dpre_ld, dgamma, dbeta,
-      rows, L, drop_p, seed);
+      rows, L, drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_layernorm_bwd");
 }
 

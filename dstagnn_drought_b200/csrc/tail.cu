@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256)
 tail_rows_fwd_kernel(const float* __restrict__ tc, const float* __restrict__ g, const float* __restrict__ r,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
-                     int C, int T, float drop_p, unsigned long long seed) {
+                     int C, int T, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -212,7 +213,8 @@ tail_rows_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ t
                      const float* __restrict__ r, const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ dtc, float* __restrict__ dg,
                      float* __restrict__ dr, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
-                     int C, int T, float drop_p, unsigned long long seed) {
+                     int C, int T, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -334,7 +336,8 @@ int dstag_outer_sum(const float* a, const float* b, float* out, float* asum, int
 
 int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
                    const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
-                   int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream) {
+                   int32_t C, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(tc && r && gamma && beta && out && mean && rstd, "dstag_tail_fwd: null pointer");
   DSTAG_CHECK_ARG(X > 0 && C > 0 && T > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_fwd: bad sizes");
   DSTAG_CHECK_ARG(C <= 32 * kTailNC, "dstag_tail_fwd: at most %d channels", 32 * kTailNC);
@@ -342,14 +345,15 @@ int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float*
   const long long blocks = (rows + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   tail_rows_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tc, g, r, gamma, beta, eps, out, mean, rstd, rows, C, T,
-                                                               drop_p, seed);
+                                                               drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_tail_fwd");
 }
 
 int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
                    const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
                    float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
-                   float drop_p, uint64_t seed, void* stream) {
+                   float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(dout && tc && r && gamma && mean && rstd && dtc && dr && dgamma && dbeta,
                   "dstag_tail_bwd: null pointer");
   DSTAG_CHECK_ARG((g == nullptr) == (dg == nullptr), "dstag_tail_bwd: g and dg must both be given or both be null");
@@ -359,7 +363,7 @@ int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const flo
   const long long blocks = (rows + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);
   tail_rows_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, tc, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma,
-                                                               dbeta, rows, C, T, drop_p, seed);
+                                                               dbeta, rows, C, T, drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_tail_bwd");
 }
 
@@ -400,7 +404,8 @@ tail_fused_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ w
                       const float* __restrict__ g, const float* __restrict__ r,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                       float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, long long X,
-                      float drop_p, unsigned long long seed) {
+                      float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   constexpr int S = 3 * T - 12, C = 32;
   static_assert(S % 4 == 0 && T % 4 == 0 && T <= 32, "fused tail tiling");
   __shared__ __align__(16) float s_w[T * S];     // fcmy weight (T, S) row-major
@@ -451,7 +456,9 @@ tail_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ 
                       const float* __restrict__ r, const float* __restrict__ gamma, const float* __restrict__ mean,
                       const float* __restrict__ rstd, float* __restrict__ dcat, float* __restrict__ dtc_out,
                       float* __restrict__ dg, float* __restrict__ dr, float* __restrict__ dgamma,
-                      float* __restrict__ dbeta, long long X, float drop_p, unsigned long long seed) {
+                      float* __restrict__ dbeta, long long X, float drop_p, unsigned long long seed,
+                      const unsigned long long* __restrict__ seed_dev) {
+  seed = fold_seed(seed, seed_dev);
   constexpr int S = 3 * T - 12, C = 32, NW = 8;
   __shared__ __align__(16) float s_w[T * S];     // (T, S): rows for the forward recompute
   __shared__ __align__(16) float s_wt[S * T];    // (S, T): rows for d cat[s] = sum_t dtc[t] w[t][s]
@@ -537,7 +544,9 @@ int dstag_tail_fused_supported(int32_t C, int32_t T) { return (C == 32 && T == 1
 
 int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, const float* g, const float* r,
                          const float* gamma, const float* beta, float eps, float* out, float* mean, float* rstd,
-                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream) {
+                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                         void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(cat && wf && bf && r && gamma && beta && out && mean && rstd, "dstag_tail_fused_fwd: null pointer");
   DSTAG_CHECK_ARG(X > 0 && drop_p >= 0.f && drop_p < 1.f, "dstag_tail_fused_fwd: bad sizes");
   if (!dstag_tail_fused_supported(C, T)) {
@@ -547,14 +556,15 @@ int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, con
   const long long blocks = (X + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   tail_fused_fwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(cat, wf, bf, g, r, gamma, beta, eps, out, mean,
-                                                                    rstd, X, drop_p, seed);
+                                                                    rstd, X, drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_tail_fused_fwd");
 }
 
 int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, const float* bf, const float* g,
                          const float* r, const float* gamma, const float* mean, const float* rstd, float* dcat,
                          float* dtc, float* dg, float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C,
-                         int32_t T, float drop_p, uint64_t seed, void* stream) {
+                         int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   DSTAG_CHECK_ARG(dout && cat && wf && bf && r && gamma && mean && rstd && dcat && dtc && dr && dgamma && dbeta,
                   "dstag_tail_fused_bwd: null pointer");
   DSTAG_CHECK_ARG((g == nullptr) == (dg == nullptr), "dstag_tail_fused_bwd: g and dg must both be given or both be null");
@@ -566,7 +576,7 @@ int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, c
   const long long blocks = (X + 7) / 8;
   const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   tail_fused_bwd_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(dout, cat, wf, bf, g, r, gamma, mean, rstd, dcat,
-                                                                    dtc, dg, dr, dgamma, dbeta, X, drop_p, seed);
+                                                                    dtc, dg, dr, dgamma, dbeta, X, drop_p, seed, sd);
   DSTAG_RETURN_LAUNCH("dstag_tail_fused_bwd");
 }
 

@@ -158,8 +158,7 @@ class DSTAGNN_block(nn.Module):
     # -- helpers ---------------------------------------------------------------------------
     def _bias_T(self) -> torch.Tensor:
         """(adj_pa . mask_k)^T for all k, padded to ld: (K, N, ld).  Batch independent."""
-        m = torch.stack([self.adj_pa * mk for mk in self.cheb_conv_SAt.mask])          # (K, N, N)
-        return F_.pad(m.transpose(1, 2), (0, self.ld - self.N)).contiguous()
+        return ops.BiasT.apply(self.adj_pa, self.ld, *self.cheb_conv_SAt.mask)
 
     def forward(self, x, res_att):
         _require_cuda(x)

@@ -44,6 +44,25 @@ def _rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+# Device-resident step counter per device (set by step.StepCounters): when present, every dropout kernel
+# folds it into its key, so a step captured in a CUDA graph draws fresh masks on every replay.
+_seed_counters = {}
+
+
+def set_seed_counter(device, tensor):
+    """Register (or, with ``None``, remove) the device tensor whose element 0 is the dropout step counter."""
+    idx = torch.device(device).index
+    if tensor is None:
+        _seed_counters.pop(idx, None)
+    else:
+        _seed_counters[idx] = tensor
+
+
+def _seed_dev(t: torch.Tensor):
+    c = _seed_counters.get(t.device.index)
+    return None if c is None else c.data_ptr()
+
+
 def next_seed() -> int:
     global _seed_counter, _seed_base
     base = torch.initial_seed()
@@ -127,7 +146,7 @@ class LayerNormAdd(torch.autograd.Function):
         _lib.check(lib.dstag_layernorm_fwd(a.data_ptr(), lay[0], lay[1], lay[2], lay[3], tab.data_ptr(),
                                            tab_mod, tab.stride(0), gamma.data_ptr(), beta.data_ptr(), 1e-5,
                                            y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(), rows, L,
-                                           float(drop_p), int(seed), _stream(a)), "dstag_layernorm_fwd")
+                                           float(drop_p), int(seed), _seed_dev(a), _stream(a)), "dstag_layernorm_fwd")
         ctx.save_for_backward(a, tab, gamma, mean, rstd)
         ctx.meta = (lay, tab_mod, rows, L, gather, float(drop_p), int(seed))
         return y
@@ -148,7 +167,7 @@ class LayerNormAdd(torch.autograd.Function):
                                            lay[3], tab.data_ptr(), tab_mod, tab.stride(0), gamma.data_ptr(),
                                            mean.data_ptr(), rstd.data_ptr(), dpre.data_ptr(), dpre.stride(0),
                                            dgamma.data_ptr(), dbeta.data_ptr(), rows, L, drop_p, seed,
-                                           _stream(a)), "dstag_layernorm_bwd")
+                                           _seed_dev(a), _stream(a)), "dstag_layernorm_bwd")
         da = dtab = None
         if ctx.needs_input_grad[0]:
             if gather:
@@ -227,6 +246,41 @@ _DQK_CHAIN = int(os.environ.get("DSTAG_DQK_CHAIN", "64"))
 
 def _pad_ld(n: int) -> int:
     return (n + 31) // 32 * 32      # 128-byte rows: aligned vector / TMA access to the N x N maps
+
+
+class BiasT(torch.autograd.Function):
+    """(adj_pa . mask_k)^T for all k, zero-padded to ld: the batch-independent additive term of
+    model/DSTAGNN_my.py:126 in the transposed map layout -- one kernel instead of K multiplies, a stack, a
+    transpose, a pad and a copy.  Backward: dmask_k = adj_pa . dbiasT_k^T."""
+
+    @staticmethod
+    def forward(ctx, adj_pa, ld, *masks):
+        lib = _lib.load()
+        _check(adj_pa, "adj_pa")
+        K, N = len(masks), adj_pa.shape[0]
+        for m in masks:
+            _check(m, "mask")
+            if not m.is_contiguous() or m.shape != adj_pa.shape:
+                raise RuntimeError("mask parameters must be contiguous (N, N) tensors")
+        adj_pa = adj_pa.contiguous()
+        out = torch.empty((K, N, ld), device=adj_pa.device, dtype=torch.float32)
+        ptrs = (C.c_void_p * K)(*[m.data_ptr() for m in masks])
+        _lib.check(lib.dstag_bias_transpose(adj_pa.data_ptr(), ptrs, K, out.data_ptr(), N, ld, _stream(adj_pa)),
+                   "dstag_bias_transpose")
+        ctx.save_for_backward(adj_pa)
+        ctx.meta = (K, N, ld)
+        return out
+
+    @staticmethod
+    def backward(ctx, dbias):
+        lib = _lib.load()
+        (adj_pa,) = ctx.saved_tensors
+        K, N, ld = ctx.meta
+        dbias = dbias.contiguous()
+        dmask = torch.empty((K, N, N), device=adj_pa.device, dtype=torch.float32)
+        _lib.check(lib.dstag_bias_transpose_bwd(adj_pa.data_ptr(), dbias.data_ptr(), dmask.data_ptr(), K, N, ld,
+                                                _stream(adj_pa)), "dstag_bias_transpose_bwd")
+        return (None, None) + tuple(dmask[k] for k in range(K))
 
 
 class SpatialChebConv(torch.autograd.Function):
@@ -402,7 +456,7 @@ class BlockTail(torch.autograd.Function):
         rstd = torch.empty((X, T), device=tc.device, dtype=torch.float32)
         _lib.check(lib.dstag_tail_fwd(tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                       1e-5, out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), X, Cc, T,
-                                      float(drop_p), int(seed), _stream(tc)), "dstag_tail_fwd")
+                                      float(drop_p), int(seed), _seed_dev(tc), _stream(tc)), "dstag_tail_fwd")
         ctx.save_for_backward(tc, g, r, gamma, mean, rstd)
         ctx.meta = (float(drop_p), int(seed))
         return out
@@ -422,7 +476,7 @@ class BlockTail(torch.autograd.Function):
         _lib.check(lib.dstag_tail_bwd(dout.data_ptr(), tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(),
                                       mean.data_ptr(), rstd.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
                                       dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
-                                      _stream(tc)), "dstag_tail_bwd")
+                                      _seed_dev(tc), _stream(tc)), "dstag_tail_bwd")
         return dtc, dg, dr, dgamma, dbeta, None, None
 
 
@@ -451,7 +505,7 @@ class FusedTail(torch.autograd.Function):
         _lib.check(lib.dstag_tail_fused_fwd(cat.data_ptr(), wf.data_ptr(), bf.data_ptr(), _p(g), r.data_ptr(),
                                             gamma.data_ptr(), beta.data_ptr(), 1e-5, out.data_ptr(),
                                             mean.data_ptr(), rstd.data_ptr(), X, Cc, T, float(drop_p), int(seed),
-                                            _stream(r)), "dstag_tail_fused_fwd")
+                                            _seed_dev(r), _stream(r)), "dstag_tail_fused_fwd")
         ctx.save_for_backward(cat, wf, bf, g, r, gamma, mean, rstd)
         ctx.meta = (float(drop_p), int(seed))
         return out
@@ -474,7 +528,7 @@ class FusedTail(torch.autograd.Function):
                                             r.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                             dcat.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
                                             dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
-                                            _stream(r)), "dstag_tail_fused_bwd")
+                                            _seed_dev(r), _stream(r)), "dstag_tail_fused_bwd")
         dwf, dbf = fcmy_param_grads(dtc, cat)
         return dcat, dwf, dbf, dg, dr, dgamma, dbeta, None, None
 

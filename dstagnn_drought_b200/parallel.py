@@ -47,8 +47,9 @@ class GradBuckets:
     ``buckets.zero()`` or ``optimizer.zero_grad()`` at the top of the step -- gives the same result.
     """
 
-    def __init__(self, net, process_group=None, overlap: bool = True):
+    def __init__(self, net, process_group=None, overlap: bool = True, average: bool = True):
         self.group = process_group
+        self.average = average          # False: buckets hold the SUM over ranks (the optimizer scales by 1 / world)
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
         self.buckets: Dict[str, torch.Tensor] = {}
@@ -106,7 +107,8 @@ class GradBuckets:
     def _launch(self, b):
         self._attach(b, copy=True)
         flat = self.buckets[b]
-        flat.mul_(1.0 / self.world)
+        if self.average:
+            flat.mul_(1.0 / self.world)
         self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero(self):

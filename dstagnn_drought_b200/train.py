@@ -33,7 +33,6 @@ from typing import Optional
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 from . import data as D
 from .metrics import predict_and_save_results
@@ -204,12 +203,16 @@ def redirect_to_synthetic(cfg: Config, workdir: str, samples: int, rank: int = 0
 
 
 def fit(cfg: Config, device, out_root: str = "myexperiments", epochs: Optional[int] = None,
-        max_batches: Optional[int] = None, rank: int = 0, world: int = 1, log=print, precision: Optional[str] = None):
-    """The loop of train_DSTAGNN_my.py:132-191.  Returns a summary dict (losses, best epoch, checkpoint path)."""
+        max_batches: Optional[int] = None, rank: int = 0, world: int = 1, log=print, precision: Optional[str] = None,
+        cuda_graph: bool = True):
+    """The loop of train_DSTAGNN_my.py:132-191.  Returns a summary dict (losses, best epoch, checkpoint path).
+
+    The step itself -- zero-grad, forward, SmoothL1, backward, gradient averaging, Adam (lines 154-158) -- is
+    ``step.TrainStep``: every kernel is this library's, and on one GPU the step is captured in a CUDA graph."""
     import torch.distributed as dist
 
     from .contraction import set_precision
-    from .parallel import GradBuckets
+    from .step import TrainStep, smooth_l1_loss
     if precision:
         set_precision(precision)
     seed_torch(1)
@@ -223,9 +226,8 @@ def fit(cfg: Config, device, out_root: str = "myexperiments", epochs: Optional[i
     if rank == 0:
         os.makedirs(path, exist_ok=True)
         log(f"Params path: {path}")
-    criterion = nn.SmoothL1Loss()
-    buckets = GradBuckets(net) if world > 1 else None
-    optimizer = make_optimizer(net, cfg.learning_rate)
+    criterion = smooth_l1_loss
+    train_step = TrainStep(net, cfg.learning_rate, graph=cuda_graph and torch.device(device).type == "cuda")
 
     def mean_loss(loader, limit):
         net.eval()
@@ -253,16 +255,8 @@ def fit(cfg: Config, device, out_root: str = "myexperiments", epochs: Optional[i
         for batch_idx, (x, y) in enumerate(train_loader):
             if max_batches is not None and batch_idx >= max_batches:
                 break
-            if buckets is not None:
-                buckets.zero()
-            else:
-                optimizer.zero_grad(set_to_none=False)
-            loss = criterion(net(x), y)
-            loss.backward()
-            if buckets is not None:
-                buckets.finish()
-            optimizer.step()
-            total += loss.detach()                      # no host sync per batch (the reference's loss.item(), line 160)
+            loss = train_step(x, y)
+            total += loss                               # no host sync per batch (the reference's loss.item(), line 160)
             nb += 1
             if batch_idx % 100 == 0 and rank == 0:
                 log(f"Epoch {epoch} Batch {batch_idx} Loss: {float(loss):.4f}")
@@ -295,15 +289,6 @@ def fit(cfg: Config, device, out_root: str = "myexperiments", epochs: Optional[i
     return summary
 
 
-def make_optimizer(net, lr: float):
-    """Adam over the parameters that receive gradients.  The dead parameters of blocks >= 1 never
-    get a ``.grad`` in the reference either, so Adam skips them there too (train_DSTAGNN_my.py:133)."""
-    from .parallel import live_parameters
-    params = list(live_parameters(net).values())
-    fused = all(p.is_cuda for p in params)
-    return torch.optim.Adam(params, lr=lr, fused=fused)
-
-
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--config", default=None, type=str,
@@ -319,6 +304,7 @@ def main(argv=None):
     ap.add_argument("--max-batches", type=int, default=None, help="limit batches per epoch / evaluation (smoke runs)")
     ap.add_argument("--batch-size", type=int, default=None, help="override the conf's per-GPU batch size")
     ap.add_argument("--precision", default=None, choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run every step eagerly (default: captured on 1 GPU)")
     args = ap.parse_args(argv)
 
     import torch.distributed as dist
@@ -348,7 +334,8 @@ def main(argv=None):
         redirect_to_synthetic(cfg, args.workdir, args.synthetic_samples, rank)
         if world > 1:
             dist.barrier()
-    summary = fit(cfg, device, args.out, args.epochs, args.max_batches, rank, world, precision=args.precision)
+    summary = fit(cfg, device, args.out, args.epochs, args.max_batches, rank, world, precision=args.precision,
+                  cuda_graph=not args.no_cuda_graph)
     if world > 1:
         dist.destroy_process_group()
     return summary

@@ -92,7 +92,9 @@ int dstag_gemm_uses_tensor_cores(const dstag_gemm_t* g);
 
 /* ------------------------------------------------------------------------------------
  * Row LayerNorm with fused pre-add:  y[r,:] = LN(a[r,:] + tab[r % tab_mod,:]) * gamma + beta
- * followed by optional inverted dropout (Philox, keyed by seed; p == 0 disables).
+ * followed by optional inverted dropout (Philox, keyed by seed; p == 0 disables).  seed_dev (nullable, all
+ * dropout entry points): a device-resident step counter folded into the key, so that a step captured in a CUDA
+ * graph draws fresh masks on every replay (dstag_tick advances it inside the graph).
  *   a is gathered as a[(r / a_div) * a_s0 + (r % a_div) * a_s1 + c * a_sc].
  * Replaces Embedding.forward (model/DSTAGNN_my.py:172-182: pos_embed + LayerNorm, both
  * 'T' and 'S' types, tab = the embedding table), the residual LayerNorm of
@@ -104,14 +106,14 @@ int dstag_gemm_uses_tensor_cores(const dstag_gemm_t* g);
 int dstag_layernorm_fwd(const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div, int64_t a_sc,
                         const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma, const float* beta,
                         float eps, float* y, int64_t y_ld, float* mean, float* rstd, int32_t rows, int32_t L,
-                        float drop_p, uint64_t seed, void* stream);
+                        float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* dpre[r,:] = d(loss)/d(a + tab) (contiguous rows x L); dgamma/dbeta are ACCUMULATED
  * (atomicAdd) into caller-zeroed buffers. */
 int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t a_s0, int64_t a_s1, int32_t a_div,
                         int64_t a_sc, const float* tab, int32_t tab_mod, int64_t tab_ld, const float* gamma,
                         const float* mean, const float* rstd, float* dpre, int64_t dpre_ld, float* dgamma,
                         float* dbeta, int32_t rows, int32_t L, float drop_p, uint64_t seed,
-                        void* stream);
+                        const uint64_t* seed_dev, void* stream);
 
 /* out[r * out_ld + c] = sum_{s < nslices} ws[s * slice_stride + r * cols + c]  (s ascending: a fixed-order,
  * run-to-run reproducible reduction).  Second stage of the split-K / K-outer-fold contractions that must
@@ -209,12 +211,12 @@ int dstag_outer_sum(const float* a, const float* b, float* out, float* asum, int
  * Dropout element index = (x*C + c)*T + t (the reference's (B,N,C,T) order). */
 int dstag_tail_fwd(const float* tc, const float* g, const float* r, const float* gamma,
                    const float* beta, float eps, float* out, float* mean, float* rstd, int64_t X,
-                   int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
+                   int32_t C, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* dtc, dr, dg (when g != NULL): (X, T, C); accumulates dgamma / dbeta (caller-zeroed). */
 int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const float* r,
                    const float* gamma, const float* mean, const float* rstd, float* dtc, float* dg,
                    float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C, int32_t T,
-                   float drop_p, uint64_t seed, void* stream);
+                   float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 
 /* fcmy (Linear over the concatenated time axis, line 243) fused with the tail, for C = 32, T = 12:
  *   tc[x, t, c] = bf[t] + sum_s wf[t, s] * cat[x, s, c]   evaluated in registers, then the tail above.
@@ -222,13 +224,47 @@ int dstag_tail_bwd(const float* dout, const float* tc, const float* g, const flo
 int dstag_tail_fused_supported(int32_t C, int32_t T);
 int dstag_tail_fused_fwd(const float* cat, const float* wf, const float* bf, const float* g, const float* r,
                          const float* gamma, const float* beta, float eps, float* out, float* mean, float* rstd,
-                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, void* stream);
+                         int64_t X, int32_t C, int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                         void* stream);
 /* Backward: dcat (X, S, C), dtc (X, T, C) (feeds dstag_outer_sum for the fcmy weight / bias gradients),
  * dr, dg (when g != NULL) (X, T, C); accumulates dgamma / dbeta. */
 int dstag_tail_fused_bwd(const float* dout, const float* cat, const float* wf, const float* bf, const float* g,
                          const float* r, const float* gamma, const float* mean, const float* rstd, float* dcat,
                          float* dtc, float* dg, float* dr, float* dgamma, float* dbeta, int64_t X, int32_t C,
-                         int32_t T, float drop_p, uint64_t seed, void* stream);
+                         int32_t T, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * The step either side of the block stack.
+ *
+ * SmoothL1Loss (beta = 1, reduction = mean; train_DSTAGNN_my.py:132,156):
+ *   loss = mean(0.5 d^2 if |d| < 1 else |d| - 0.5), d = pred - target, n elements.
+ *   workspace: 1025 floats of caller-owned scratch, ZEROED ONCE when allocated (partial sums + a
+ *   self-resetting arrival counter); the partials are added in index order: reproducible.
+ * Backward: dpred = gout * clamp(d, -1, 1) / n with gout a DEVICE scalar (nullable = 1).
+ * ---------------------------------------------------------------------------------- */
+int dstag_smooth_l1_fwd(const float* pred, const float* target, float* loss, float* workspace, int64_t n,
+                        void* stream);
+int dstag_smooth_l1_bwd(const float* pred, const float* target, const float* gout, float* dpred, int64_t n,
+                        void* stream);
+
+/* Adam on one flat fp32 buffer (torch.optim.Adam with the reference's defaults, train_DSTAGNN_my.py:133,158:
+ * betas given by the caller, no weight decay, no amsgrad):
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * with g = grad_scale * g (1/world_size after a summing all-reduce).  The step count t (1-based) is read from
+ * the device counter step_dev when given (CUDA-graph replays), else step_host.  16-byte aligned buffers. */
+int dstag_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float grad_scale, const uint64_t* step_dev, uint64_t step_host, void* stream);
+
+/* counters[i] += 1 for i < n (n <= 32): the device-resident step counters (dropout key, Adam step). */
+int dstag_tick(uint64_t* counters, int32_t n, void* stream);
+
+/* biasT[k, j, i] = adj_pa[i, j] * mask_k[i, j] for i < N, 0 for N <= i < ld: the batch-independent additive
+ * term of model/DSTAGNN_my.py:126 in the transposed, padded map layout.  masks: HOST array of K (<= 8) device
+ * pointers to the (N, N) mask parameters.  Backward: dmask[k, i, j] = adj_pa[i, j] * dbiasT[k, j, i]. */
+int dstag_bias_transpose(const float* adj_pa, const float* const* masks, int32_t K, float* biasT, int32_t N,
+                         int32_t ld, void* stream);
+int dstag_bias_transpose_bwd(const float* adj_pa, const float* dbiasT, float* dmask, int32_t K, int32_t N, int32_t ld,
+                             void* stream);
 
 #ifdef __cplusplus
 }

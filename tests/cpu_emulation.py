@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 9
+        return 10
 
     def dstag_last_error(self):
         return self.err
@@ -110,7 +110,7 @@ class FakeLib:
         return pre
 
     def dstag_layernorm_fwd(self, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, beta, eps, y, y_ld,
-                            mean, rstd, rows, L, drop_p, seed, stream):
+                            mean, rstd, rows, L, drop_p, seed, seed_dev, stream):
         assert drop_p == 0.0, "emulation has no dropout"
         self.launches += 1
         pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, rows, L)
@@ -123,7 +123,7 @@ class FakeLib:
         return 0
 
     def dstag_layernorm_bwd(self, dy, dy_ld, a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, gamma, mean, rstd,
-                            dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed, stream):
+                            dpre, dpre_ld, dgamma, dbeta, rows, L, drop_p, seed, seed_dev, stream):
         assert drop_p == 0.0
         self.launches += 1
         pre = self._ln_pre(a, a_s0, a_s1, a_div, a_sc, tab, tab_mod, tab_ld, rows, L)
@@ -263,7 +263,7 @@ class FakeLib:
         return 0
 
     # ---- tail: every tensor (X, T, C) channels-last ----
-    def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, stream):
+    def dstag_tail_fwd(self, tc, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed, seed_dev, stream):
         assert drop_p == 0.0
         self.launches += 1
         n = X * Cc * T
@@ -279,7 +279,7 @@ class FakeLib:
         return 0
 
     def dstag_tail_bwd(self, dout, tc, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma, dbeta, X, Cc, T, drop_p,
-                       seed, stream):
+                       seed, seed_dev, stream):
         assert drop_p == 0.0
         self.launches += 1
         n = X * Cc * T
@@ -314,29 +314,87 @@ class FakeLib:
         return W, np.ascontiguousarray((tc + _arr(bf, T)[None, :, None]).astype(np.float32))
 
     def dstag_tail_fused_fwd(self, cat, wf, bf, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p, seed,
-                             stream):
+                             seed_dev, stream):
         _, self._tc = self._fcmy(cat, wf, bf, X, Cc, T)
         return self.dstag_tail_fwd(self._tc.ctypes.data, g, r, gamma, beta, eps, out, mean, rstd, X, Cc, T, drop_p,
-                                   seed, stream)
+                                   seed, seed_dev, stream)
 
     def dstag_tail_fused_bwd(self, dout, cat, wf, bf, g, r, gamma, mean, rstd, dcat, dtc, dg, dr, dgamma, dbeta, X,
-                             Cc, T, drop_p, seed, stream):
+                             Cc, T, drop_p, seed, seed_dev, stream):
         S = 3 * T - 12
         W, tc = self._fcmy(cat, wf, bf, X, Cc, T)
         rc = self.dstag_tail_bwd(dout, tc.ctypes.data, g, r, gamma, mean, rstd, dtc, dg, dr, dgamma, dbeta, X, Cc, T,
-                                 drop_p, seed, stream)
+                                 drop_p, seed, seed_dev, stream)
         _arr(dcat, X * S * Cc).reshape(X, S, Cc)[:] = np.einsum(
             "xtc,ts->xsc", _arr(dtc, X * Cc * T).reshape(X, T, Cc).astype(np.float64), W)
         return rc
 
 
+def _emu_optim(cls):
+    """The step either side of the block stack (csrc/optim.cu)."""
+    def dstag_smooth_l1_fwd(self, pred, target, loss, workspace, n, stream):
+        self.launches += 1
+        d = np.abs(_arr(pred, n).astype(np.float64) - _arr(target, n))
+        _arr(loss, 1)[0] = np.mean(np.where(d < 1, 0.5 * d * d, d - 0.5))
+        return 0
+
+    def dstag_smooth_l1_bwd(self, pred, target, gout, dpred, n, stream):
+        self.launches += 1
+        d = _arr(pred, n).astype(np.float64) - _arr(target, n)
+        g = _arr(gout, 1)[0] if gout else 1.0
+        _arr(dpred, n)[:] = g * np.clip(d, -1, 1) / n
+        return 0
+
+    def dstag_adam_step(self, p, g, m, v, n, lr, b1, b2, eps, gscale, step_dev, step_host, stream):
+        self.launches += 1
+        t = float(np.ctypeslib.as_array((C.c_int64 * 1).from_address(int(step_dev)))[0]) if step_dev else float(step_host)
+        P, G, M_, V = _arr(p, n), _arr(g, n).astype(np.float64) * gscale, _arr(m, n), _arr(v, n)
+        mm = b1 * M_.astype(np.float64) + (1 - b1) * G
+        vv = b2 * V.astype(np.float64) + (1 - b2) * G * G
+        M_[:], V[:] = mm, vv
+        P[:] = P - (lr / (1 - b1 ** t)) * mm / (np.sqrt(vv) / math.sqrt(1 - b2 ** t) + eps)
+        return 0
+
+    def dstag_tick(self, counters, n, stream):
+        self.launches += 1
+        np.ctypeslib.as_array((C.c_int64 * int(n)).from_address(int(counters)))[:] += 1
+        return 0
+
+    def dstag_bias_transpose(self, adj_pa, masks, K, biasT, N, ld, stream):
+        self.launches += 1
+        pa = _arr(adj_pa, N * N).reshape(N, N)
+        out = _arr(biasT, K * N * ld).reshape(K, N, ld)
+        out[:] = 0
+        for k in range(K):
+            out[k, :, :N] = (pa * _arr(masks[k], N * N).reshape(N, N)).T
+        return 0
+
+    def dstag_bias_transpose_bwd(self, adj_pa, dbiasT, dmask, K, N, ld, stream):
+        self.launches += 1
+        pa = _arr(adj_pa, N * N).reshape(N, N)
+        d = _arr(dbiasT, K * N * ld).reshape(K, N, ld)
+        out = _arr(dmask, K * N * N).reshape(K, N, N)
+        for k in range(K):
+            out[k] = pa * d[k, :, :N].T
+        return 0
+
+    for f in (dstag_smooth_l1_fwd, dstag_smooth_l1_bwd, dstag_adam_step, dstag_tick, dstag_bias_transpose,
+              dstag_bias_transpose_bwd):
+        setattr(cls, f.__name__, f)
+    return cls
+
+
+FakeLib = _emu_optim(FakeLib)
+
+
 def install(monkeypatch):
     """Route the package's ctypes calls to the emulation (CPU tensors)."""
-    from dstagnn_drought_b200 import _lib, contraction, modules, ops
+    from dstagnn_drought_b200 import _lib, contraction, modules, ops, step
     fake = FakeLib()
     monkeypatch.setattr(modules, "_require_cuda", lambda x: None)
     monkeypatch.setattr(_lib, "load", lambda: fake)
     monkeypatch.setattr(_lib, "stream_ptr", lambda t: None)
     monkeypatch.setattr(contraction, "_check", lambda t, name: None)
     monkeypatch.setattr(ops, "_check", lambda t, name: None)
+    monkeypatch.setattr(step, "_check", lambda t, name: None)
     return fake
