@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -79,6 +79,13 @@ SIGNATURES = {
     "dstag_tick": (C.c_int, [_F, _i32, _F]),
     "dstag_bias_transpose": (C.c_int, [_F, C.POINTER(C.c_void_p), _i32, _F, _i32, _i32, _F]),
     "dstag_bias_transpose_bwd": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _F]),
+    "dstag_edge_probs": (C.c_int, [_F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_spmm_expand": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_spmm_reduce": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_edge_dots": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_scale_keys": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _i32, _F]),
+    "dstag_dqk_combine": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _f32, _F]),
+    "dstag_dbias_sparse": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _i32, _F]),
 }
 
 _lib = None

@@ -30,6 +30,7 @@ import torch.nn.functional as F_
 from . import ops
 from .contraction import contract, padded_ld
 from .graph import cheb_polynomial, scaled_Laplacian
+from .sparse import EdgeLists, SparseChebConv, choose_path
 
 
 class Embedding(nn.Module):
@@ -153,6 +154,15 @@ class DSTAGNN_block(nn.Module):
         self.register_buffer("adj_pa", pa.clone(), persistent=False)
         self.register_buffer("cheb_T", tk, persistent=False)        # T_k^T, (K, N, ld)
         self.ld = ld
+        # The polynomials of this model are element-wise powers of the Laplacian: as sparse as the graph.  A
+        # block whose T_k are sparse walks their edges instead of contracting N x N maps (sparse.py).
+        polys = [_as_float_tensor(t).numpy() for t in cheb_polynomials]
+        self.cheb_path = choose_path(polys, d_k)
+        self._edge_names = []
+        if self.cheb_path == "sparse":
+            for name, t in EdgeLists(polys, pa.numpy()).tensors.items():
+                self.register_buffer("edges_" + name, t, persistent=False)
+                self._edge_names.append(name)
         self.to(DEVICE)
 
     # -- helpers ---------------------------------------------------------------------------
@@ -202,7 +212,11 @@ class DSTAGNN_block(nn.Module):
         # 5+6. spatial attention maps and the Chebyshev contraction                  (lines 235-236)
         w_sat = torch.cat([self.SAt.W_Q.weight, self.SAt.W_K.weight], dim=0)           # (2*K*dk, D)
         qk = contract("rd,od->ro", se, w_sat).view(B, N, 2, K, dk)
-        zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)             # (K, B, N, (t,f))
+        if self.cheb_path == "sparse" and (T * Fin) % 4 == 0:      # (the edge kernels move rows as float4)
+            edges = {n: getattr(self, "edges_" + n) for n in self._edge_names}
+            zc = SparseChebConv.apply(qk, self._bias_T(), self.cheb_T, x3, edges)       # (K, B, N, (t,f))
+        else:
+            zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)
         theta = torch.stack(list(self.cheb_conv_SAt.Theta))                             # (K, F, C)
         g = contract("kxtf,kfc->xtc", zc.view(K, B * N, T, Fin), theta, relu=True)      # (B*N, T, C)
         # 7. gated temporal convolutions                                             (lines 237-242)

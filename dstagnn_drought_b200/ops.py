@@ -283,6 +283,31 @@ class BiasT(torch.autograd.Function):
         return (None, None) + tuple(dmask[k] for k in range(K))
 
 
+def spatial_maps(qk, biasT, tkT=None):
+    """Softmax maps of the spatial attention in the transposed, padded layout (SMultiHeadAttention scores,
+    lines 62-66 and 19, + bias + the dim=1 softmax of line 127):
+        P[b, k, j, i] = softmax_i( Qs[b,i,k,:] . Ks[b,j,k,:] / sqrt(dk) + biasT[k, j, i] ),  pad columns = 0.
+    With ``tkT`` the fused kernel also writes TP = tkT (.) P and (P, TP) is returned (TP is None when the graph
+    is too large for the fused kernel's row strip and the GEMM + row-softmax pair ran instead); without it, P."""
+    lib = _lib.load()
+    qk = qk.contiguous()
+    B, N, _, K, dk = qk.shape
+    biasT = biasT.contiguous()
+    ld = biasT.shape[-1]
+    P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
+    TP = torch.empty_like(P) if tkT is not None else None
+    rc = _lib.ERR_SMEM if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
+        qk.data_ptr(), biasT.data_ptr(), _p(tkT), P.data_ptr(), _p(TP), B, N, K, dk, ld, _stream(P))
+    if rc == _lib.ERR_SMEM:      # N too large for the fused row strip -> logits GEMM + row softmax
+        TP = None
+        contract_raw("bjkd,bikd->bkji", qk[:, :, 1], qk[:, :, 0], out=P[..., :N], alpha=1.0 / math.sqrt(dk),
+                     c_add=("kji", biasT[..., :N]), reproducible=True)
+        _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+    else:
+        _lib.check(rc, "dstag_sat_softmax_fwd")
+    return (P, TP) if tkT is not None else P
+
+
 class SpatialChebConv(torch.autograd.Function):
     """SMultiHeadAttention scores (lines 62-66, 19) + the attention-masked Chebyshev product
     of cheb_conv_withSAt (lines 126-130), per Chebyshev order k:
@@ -298,31 +323,20 @@ class SpatialChebConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qk, biasT, tkT, x3):
-        lib = _lib.load()
         for t, n in ((qk, "qk"), (biasT, "biasT"), (tkT, "tkT"), (x3, "x")):
             _check(t, n)
         qk, x3 = qk.contiguous(), x3.contiguous()
         B, N, _, K, dk = qk.shape
-        ld = biasT.shape[-1]
         FT = x3.shape[-1]
-        Qs, Ks = qk[:, :, 0], qk[:, :, 1]                      # (B,N,K,dk) views
-        P = torch.empty((B, K, N, ld), device=qk.device, dtype=torch.float32)
-        biasT, tkT = biasT.contiguous(), tkT.contiguous()
+        tkT = tkT.contiguous()
         # TP = T_k (.) P is written by the same kernel: the two contractions that need the masked operator
         # (forward, input gradient) then stream one N x N operand instead of two
-        TP = torch.empty_like(P)
-        rc = _lib.ERR_SMEM if os.environ.get("DSTAG_SAT_FUSED") == "0" else lib.dstag_sat_softmax_fwd(
-            qk.data_ptr(), biasT.data_ptr(), tkT.data_ptr(), P.data_ptr(), TP.data_ptr(), B, N, K, dk, ld, _stream(P))
+        P, TP = spatial_maps(qk, biasT, tkT)
         Z = torch.empty((K, B, N, FT), device=qk.device, dtype=torch.float32)
-        if rc == _lib.ERR_SMEM:      # N too large for the fused row strip -> GEMM + row softmax
-            TP = None
-            contract_raw("bjkd,bikd->bkji", Ks, Qs, out=P[..., :N], alpha=1.0 / math.sqrt(dk),
-                         c_add=("kji", biasT[..., :N]), reproducible=True)
-            _lib.check(lib.dstag_softmax_fwd(P.data_ptr(), B * K * N, N, ld, _stream(P)), "dstag_softmax_fwd")
+        if TP is None:      # N too large for the fused row strip: Hadamard factor fused into the operand load
             contract_raw("bkji,bie->kbje", P[..., :N], x3, out=Z, a_mul=("kji", tkT[..., :N]), tag="cheb_fwd",
                          reproducible=True)
         else:
-            _lib.check(rc, "dstag_sat_softmax_fwd")
             contract_raw("bkji,bie->kbje", TP[..., :N], x3, out=Z, tag="cheb_fwd", reproducible=True)
         ctx.save_for_backward(qk, P, tkT, x3, TP)
         return Z

@@ -36,6 +36,9 @@ def bucket_of(name: str) -> str:
     return ".".join(parts[:2]) if parts[0] == "BlockList" else "head"
 
 
+ALIGN = 32      # floats: members of a flat bucket start on 128-byte boundaries
+
+
 class GradBuckets:
     """Flat per-block gradient storage + overlapped averaging all-reduce.
 
@@ -55,29 +58,35 @@ class GradBuckets:
         self.buckets: Dict[str, torch.Tensor] = {}
         self._members: Dict[str, List[torch.nn.Parameter]] = {}
         self._views: Dict[str, List[torch.Tensor]] = {}
+        self._offsets: Dict[str, List[int]] = {}
         self._pending: Dict[str, int] = {}
         self._works = []
         groups: Dict[str, List] = {}
         for name, p in live_parameters(net).items():
             groups.setdefault(bucket_of(name), []).append((name, p))
         for b, items in groups.items():
-            n = sum(p.numel() for _, p in items)
-            flat = torch.zeros(n, device=items[0][1].device, dtype=items[0][1].dtype)
-            off, views = 0, []
+            # every member starts on a 128-byte boundary: kernels that read parameters / write gradients through
+            # these views (and the flat Adam that mirrors the layout) keep their 16-byte vector paths
+            offs, n = [], 0
             for _, p in items:
+                offs.append(n)
+                n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            flat = torch.zeros(n, device=items[0][1].device, dtype=items[0][1].dtype)
+            views = []
+            for (_, p), off in zip(items, offs):
                 v = flat[off:off + p.numel()].view_as(p)
                 p.grad = v
                 views.append(v)
-                off += p.numel()
             self.buckets[b] = flat
             self._members[b] = [p for _, p in items]
             self._views[b] = views
+            self._offsets[b] = offs
             self._pending[b] = len(items)
         if self.overlap:
             for b, ps in self._members.items():
                 for p in ps:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
-        self.numel = sum(f.numel() for f in self.buckets.values())
+        self.numel = sum(p.numel() for ps in self._members.values() for p in ps)      # without the alignment padding
 
     def _make_hook(self, b):
         def hook(_p):

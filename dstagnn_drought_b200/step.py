@@ -113,14 +113,12 @@ class FlatAdam:
         self.m: Dict[str, torch.Tensor] = {}
         self.v: Dict[str, torch.Tensor] = {}
         for b, members in buckets._members.items():
-            flat = torch.empty_like(buckets.buckets[b])
-            off = 0
+            flat = torch.zeros_like(buckets.buckets[b])     # same (128-byte aligned) member offsets as the gradients
             with torch.no_grad():
-                for p in members:
+                for p, off in zip(members, buckets._offsets[b]):
                     view = flat[off:off + p.numel()].view_as(p)
                     view.copy_(p.data)
                     p.data = view                          # the parameter now lives inside the flat buffer
-                    off += p.numel()
             self.flat_p[b] = flat
             self.m[b] = torch.zeros_like(flat)
             self.v[b] = torch.zeros_like(flat)

@@ -266,6 +266,47 @@ int dstag_bias_transpose(const float* adj_pa, const float* const* masks, int32_t
 int dstag_bias_transpose_bwd(const float* adj_pa, const float* dbiasT, float* dmask, int32_t K, int32_t N, int32_t ld,
                              void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sparse Chebyshev path of cheb_conv_withSAt (model/DSTAGNN_my.py:117-133) -- csrc/sparse.cu.
+ *
+ * The polynomials T_k of this model are element-wise (Hadamard) powers of the scaled Laplacian
+ * (lib/utils.py:198-203): T_0 = I and every T_k carries the adjacency's sparsity pattern (~1 % with the STAG
+ * graphs), so the operator T_k (.) softmax(S_k) and the surviving part of its gradient live on the graph's
+ * EDGES.  Edge e of order k joins output node j to input node i with weight tval[e] = T_k[i, j]; the
+ * E edges are stored as a CSR over rows r = k * N + j (rowptr (K N + 1), col = i, erow = r) and as the
+ * transposed CSR over rows k * N + i (t_rowptr, t_col = j, t_eid = index of the same edge in the row CSR).
+ * All index arrays are int32 device pointers; a, h are (B, E); r is (B, K, N); row length L % 4 == 0.
+ *
+ *   dstag_edge_probs   a[b,e] = tval[e] * P[b,k,j,i]                                  (line 128 on the edges)
+ *   dstag_spmm_expand  dst[k,b,n,:] = sum_{e in row (k,n)} a[b,eid?eid[e]:e] * src[b,col[e],:]   Z_k = A_k^T X (l.130)
+ *   dstag_spmm_reduce  dst[b,n,:] = sum_k sum_{e in row (k,n)} a[b,..] * src[k,b,col[e],:]      dX = sum_k A_k dZ_k
+ *   dstag_edge_dots    h[b,e] = a[b,e] * <dZ[k,b,j,:], X[b,col[e],:]>, r[b,k,j] = sum_{e in row} h[b,e]
+ *   dstag_scale_keys   rK[b,j,k,:] = r[b,k,j] * Ks[b,j,k,:]          qk (B,N,2,K,dk) packed [Qs | Ks], rK (B,N,K,dk)
+ *   dstag_dqk_combine  dqk[b,n,0,k,:] = alpha (sum_{e in col (k,n)} h[b,e] Ks[b,j_e,k,:] - W[b,n,k,:])
+ *                      dqk[b,n,1,k,:] = alpha (sum_{e in row (k,n)} h[b,e] Qs[b,i_e,k,:] - r[b,k,n] O[b,n,k,:])
+ *                      with O = P Qs and W = P^T (r Ks) from dstag_gemm: the softmax backward
+ *                      dS = h (on edges) - r P is never materialised
+ *   dstag_dbias_sparse dbiasT[k, pa_j[p], pa_i[p]] = sum_b (h[b, pa_eid[k,p]] if >= 0) - r[b,k,j] P[b,k,j,i]
+ *                      over the npa non-zeros of adj_pa (the only entries the mask gradient keeps)
+ * ---------------------------------------------------------------------------------- */
+int dstag_edge_probs(const float* P, const int32_t* erow, const int32_t* col, const float* tval, float* a, int32_t B,
+                     int32_t K, int32_t N, int32_t ld, int32_t E, void* stream);
+int dstag_spmm_expand(const float* src, const float* a, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                      float* dst, int32_t B, int32_t K, int32_t N, int32_t L, int32_t E, void* stream);
+int dstag_spmm_reduce(const float* src, const float* a, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                      float* dst, int32_t B, int32_t K, int32_t N, int32_t L, int32_t E, void* stream);
+int dstag_edge_dots(const float* dZ, const float* X, const float* a, const int32_t* rowptr, const int32_t* col, float* h,
+                    float* r, int32_t B, int32_t K, int32_t N, int32_t L, int32_t E, void* stream);
+int dstag_scale_keys(const float* qk, const float* r, float* rK, int32_t B, int32_t N, int32_t K, int32_t dk,
+                     void* stream);
+int dstag_dqk_combine(const float* qk, const float* h, const float* r, const float* O, const float* W,
+                      const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                      const int32_t* t_eid, float* dqk, int32_t B, int32_t N, int32_t K, int32_t dk, int32_t E,
+                      float alpha, void* stream);
+int dstag_dbias_sparse(const float* P, const float* h, const float* r, const int32_t* pa_j, const int32_t* pa_i,
+                       const int32_t* pa_eid, float* dbiasT, int32_t B, int32_t K, int32_t N, int32_t ld, int32_t E,
+                       int32_t npa, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

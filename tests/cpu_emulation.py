@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 10
+        return 11
 
     def dstag_last_error(self):
         return self.err
@@ -387,9 +387,121 @@ def _emu_optim(cls):
 FakeLib = _emu_optim(FakeLib)
 
 
+def _iarr(ptr, n):
+    return np.ctypeslib.as_array((C.c_int32 * int(n)).from_address(int(ptr)))
+
+
+def _emu_sparse(cls):
+    """Sparse Chebyshev path (csrc/sparse.cu), edge by edge in numpy."""
+    def dstag_edge_probs(self, P, erow, col, tval, a, B, K, N, ld, E, stream):
+        self.launches += 1
+        Pm = _arr(P, B * K * N * ld).reshape(B, K * N, ld)
+        a_ = _arr(a, B * E).reshape(B, E)
+        a_[:] = _arr(tval, E)[None, :] * Pm[:, _iarr(erow, E), _iarr(col, E)]
+        return 0
+
+    def _rows(rowptr, KN):
+        rp = _iarr(rowptr, KN + 1)
+        return np.repeat(np.arange(KN), np.diff(rp))              # row id of every CSR slot
+
+    def dstag_spmm_expand(self, src, a, rowptr, col, eid, dst, B, K, N, L, E, stream):
+        self.launches += 1
+        slot_row = _rows(rowptr, K * N)
+        c = _iarr(col, E)
+        ids = _iarr(eid, E) if eid else np.arange(E)
+        S = _arr(src, B * N * L).reshape(B, N, L).astype(np.float64)
+        A = _arr(a, B * E).reshape(B, E).astype(np.float64)
+        out = np.zeros((B, K * N, L))
+        for b in range(B):
+            np.add.at(out[b], slot_row, A[b, ids][:, None] * S[b, c])
+        _arr(dst, K * B * N * L).reshape(K, B, N, L)[:] = out.reshape(B, K, N, L).transpose(1, 0, 2, 3)
+        return 0
+
+    def dstag_spmm_reduce(self, src, a, rowptr, col, eid, dst, B, K, N, L, E, stream):
+        self.launches += 1
+        slot_row = _rows(rowptr, K * N)
+        c = _iarr(col, E)
+        ids = _iarr(eid, E) if eid else np.arange(E)
+        S = _arr(src, K * B * N * L).reshape(K, B, N, L).astype(np.float64)
+        A = _arr(a, B * E).reshape(B, E).astype(np.float64)
+        out = np.zeros((B, N, L))
+        k_of, n_of = slot_row // N, slot_row % N
+        for b in range(B):
+            np.add.at(out[b], n_of, A[b, ids][:, None] * S[k_of, b, c])
+        _arr(dst, B * N * L).reshape(B, N, L)[:] = out
+        return 0
+
+    def dstag_edge_dots(self, dZ, X, a, rowptr, col, h, r, B, K, N, L, E, stream):
+        self.launches += 1
+        slot_row = _rows(rowptr, K * N)
+        c = _iarr(col, E)
+        D = _arr(dZ, K * B * N * L).reshape(K, B, N, L).astype(np.float64)
+        Xm = _arr(X, B * N * L).reshape(B, N, L).astype(np.float64)
+        A = _arr(a, B * E).reshape(B, E).astype(np.float64)
+        k_of, j_of = slot_row // N, slot_row % N
+        H = np.zeros((B, E))
+        R = np.zeros((B, K * N))
+        for b in range(B):
+            H[b] = A[b] * np.einsum("el,el->e", D[k_of, b, j_of], Xm[b, c])
+            np.add.at(R[b], slot_row, H[b])
+        _arr(h, B * E).reshape(B, E)[:] = H
+        _arr(r, B * K * N).reshape(B, K * N)[:] = R
+        return 0
+
+    def dstag_scale_keys(self, qk, r, rK, B, N, K, dk, stream):
+        self.launches += 1
+        Q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk)
+        R = _arr(r, B * K * N).reshape(B, K, N)
+        _arr(rK, B * N * K * dk).reshape(B, N, K, dk)[:] = R.transpose(0, 2, 1)[..., None] * Q[:, :, 1]
+        return 0
+
+    def dstag_dqk_combine(self, qk, h, r, O, W, rowptr, col, t_rowptr, t_col, t_eid, dqk, B, N, K, dk, E, alpha, stream):
+        self.launches += 1
+        Q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk).astype(np.float64)
+        H = _arr(h, B * E).reshape(B, E).astype(np.float64)
+        R = _arr(r, B * K * N).reshape(B, K, N).astype(np.float64)
+        Om = _arr(O, B * N * K * dk).reshape(B, N, K, dk).astype(np.float64)
+        Wm = _arr(W, B * N * K * dk).reshape(B, N, K, dk).astype(np.float64)
+        row = _rows(rowptr, K * N); c = _iarr(col, E)
+        trow = _rows(t_rowptr, K * N); tc = _iarr(t_col, E); te = _iarr(t_eid, E)
+        out = _arr(dqk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk)
+        for b in range(B):
+            dq = np.zeros((K * N, dk)); dk_ = np.zeros((K * N, dk))
+            np.add.at(dq, trow, H[b, te][:, None] * Q[b, tc, 1, trow // N])
+            np.add.at(dk_, row, H[b][:, None] * Q[b, c, 0, row // N])
+            dq = dq.reshape(K, N, dk).transpose(1, 0, 2) - Wm[b]
+            dk_ = dk_.reshape(K, N, dk).transpose(1, 0, 2) - R[b].T[..., None] * Om[b]
+            out[b, :, 0] = alpha * dq
+            out[b, :, 1] = alpha * dk_
+        return 0
+
+    def dstag_dbias_sparse(self, P, h, r, pa_j, pa_i, pa_eid, dbiasT, B, K, N, ld, E, npa, stream):
+        self.launches += 1
+        Pm = _arr(P, B * K * N * ld).reshape(B, K, N, ld).astype(np.float64)
+        H = _arr(h, B * E).reshape(B, E).astype(np.float64)
+        R = _arr(r, B * K * N).reshape(B, K, N).astype(np.float64)
+        pj, pi = _iarr(pa_j, npa), _iarr(pa_i, npa)
+        pe = _iarr(pa_eid, K * npa).reshape(K, npa)
+        out = _arr(dbiasT, K * N * ld).reshape(K, N, ld)
+        for k in range(K):
+            v = -(R[:, k, pj] * Pm[:, k, pj, pi]).sum(0)
+            hit = pe[k] >= 0
+            v[hit] += H[:, pe[k][hit]].sum(0)
+            out[k, pj, pi] = v
+        return 0
+
+    for f in (dstag_edge_probs, dstag_spmm_expand, dstag_spmm_reduce, dstag_edge_dots, dstag_scale_keys,
+              dstag_dqk_combine, dstag_dbias_sparse):
+        setattr(cls, f.__name__, f)
+    return cls
+
+
+FakeLib = _emu_sparse(FakeLib)
+
+
 def install(monkeypatch):
     """Route the package's ctypes calls to the emulation (CPU tensors)."""
-    from dstagnn_drought_b200 import _lib, contraction, modules, ops, step
+    from dstagnn_drought_b200 import _lib, contraction, modules, ops, sparse, step
     fake = FakeLib()
     monkeypatch.setattr(modules, "_require_cuda", lambda x: None)
     monkeypatch.setattr(_lib, "load", lambda: fake)
@@ -397,4 +509,5 @@ def install(monkeypatch):
     monkeypatch.setattr(contraction, "_check", lambda t, name: None)
     monkeypatch.setattr(ops, "_check", lambda t, name: None)
     monkeypatch.setattr(step, "_check", lambda t, name: None)
+    monkeypatch.setattr(sparse, "_check", lambda t, name: None)
     return fake

@@ -239,6 +239,47 @@ def test_sat_softmax_fwd_kernel(dev, cfg, with_tp):
         assert bool((TP[..., N:] == 0).all())
 
 
+@pytest.mark.parametrize("cfg", [(2, 9, 3, 4), (2, 70, 3, 12), (3, 200, 2, 384), (1, 883, 3, 8), (1, 1100, 1, 640)])
+def test_sparse_cheb_conv_matches_dense_formula(dev, precision, cfg):
+    """sparse.SparseChebConv (edge lists: csrc/sparse.cu) against an fp64 evaluation of the dense formula of
+    model/DSTAGNN_my.py:126-130, forward and every gradient, on sparse T_k (identity + ~3 % random edges) and a
+    sparse adj_pa; ragged N, row lengths 4 ... 640 (registers-cached and streamed edge dots)."""
+    from dstagnn_drought_b200.ops import _pad_ld
+    from dstagnn_drought_b200.sparse import EdgeLists, SparseChebConv
+    Bz, N, K, FT = cfg
+    dk = 32
+    ld = _pad_ld(N)
+    g = torch.Generator().manual_seed(5)
+    polys = [torch.eye(N)] + [torch.randn(N, N, generator=g) * (torch.rand(N, N, generator=g) < 0.03) + torch.eye(N)
+                              for _ in range(K - 1)]
+    pa = (torch.rand(N, N, generator=g) < 0.04).float()
+    edges = {n: t.to(dev) for n, t in EdgeLists([p.numpy() for p in polys], pa.numpy()).tensors.items()}
+    tk = torch.zeros(K, N, ld)
+    for k in range(K):
+        tk[k, :, :N] = polys[k].t()
+    tk = tk.to(dev)
+    qk = torch.randn(Bz, N, 2, K, dk, generator=g).to(dev)
+    bias = torch.zeros(K, N, ld)
+    bias[..., :N] = torch.randn(K, N, N, generator=g) * pa.t()            # (adj_pa . mask)^T: non-zero on adj_pa only
+    bias = bias.to(dev)
+    x3 = torch.randn(Bz, N, FT, generator=g).to(dev)
+    dZ = torch.randn(K, Bz, N, FT, generator=g).to(dev)
+
+    def ref_fn(qk_, bias_, x_):
+        s = torch.einsum("bjkd,bikd->bkji", qk_[:, :, 1], qk_[:, :, 0]) / math.sqrt(dk) + bias_[..., :N]
+        a = torch.softmax(s, dim=-1) * tk[..., :N].to(s.dtype)
+        return torch.einsum("bkji,bie->kbje", a, x_)
+
+    out, gr = _grads(lambda a, b, c: SparseChebConv.apply(a, b, tk, c, edges), [qk, bias, x3], dZ)
+    ref, rr = _grads(ref_fn, [qk.double(), bias.double(), x3.double()], dZ.double())
+    assert rel_err(out, ref) < TOL
+    assert rel_err(gr[0], rr[0]) < 5e-5 and rel_err(gr[2], rr[2]) < 5e-5
+    # d bias: the mask gradient keeps the adj_pa entries only (dmask = adj_pa . dbias^T) -- compare there
+    keep = pa.t().to(dev)
+    assert rel_err(gr[1][..., :N] * keep, rr[1][..., :N] * keep.double()) < 5e-5
+    assert float((gr[1][..., :N] * (1 - keep)).abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144)])
 def test_gtu_stack(dev, precision, cfg):
     from dstagnn_drought_b200.ops import GtuStack

@@ -24,10 +24,14 @@ def _build(cfg, d, dev):
                       cfg["N"], cfg["D"], 32, 32, cfg["H"])
 
 
+@pytest.mark.parametrize("path", ["dense", "sparse"])
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_net_matches_reference_golden(name, precision):
+def test_net_matches_reference_golden(name, precision, path, monkeypatch):
+    """Both Chebyshev paths -- the dense tensor-core contraction of the N x N maps and the edge-list path that
+    sparse graphs take by default -- against the reference's own outputs and gradients."""
     import dstagnn_drought_b200 as D
+    monkeypatch.setenv("DSTAG_CHEB", path)
     D.set_precision(precision)
     dev = torch.device("cuda:0")
     d, cfg, w, g, cheb = load_golden(name)
@@ -58,7 +62,7 @@ def test_net_matches_reference_golden(name, precision):
         e = rel_err(p.grad, g[k])
         worst[k] = e
         assert e < max(TOL_GRAD, 3 * ref_err[k]), f"{k}: {e:.3e} (reference fp32 itself: {ref_err[k]:.3e})"
-    print(name, precision, "pred", rel_err(y.detach(), d["y64"]), "worst grad", max(worst.values()))
+    print(name, precision, path, "pred", rel_err(y.detach(), d["y64"]), "worst grad", max(worst.values()))
     D.set_precision("tf32x3")
 
 
@@ -94,11 +98,19 @@ COND_THR = 5e-5
 KINK_TAU = 1e-6
 
 
-@pytest.mark.parametrize("case", sorted(ORACLE_CASES))
-def test_net_matches_oracle_at_config_shapes(case):
+# every case on the path its graph selects (the 1 %-dense synthetic graphs take the edge lists), plus the dense
+# tensor-core contraction forced at the shapes that exercise its variants (TMA-fed maps at N = 883 / 307, the
+# shared-memory strip map kernel at N = 2139, the GEMM + row softmax + Hadamard-operand branch at N = 4096)
+CASE_PATHS = [(c, "auto") for c in sorted(ORACLE_CASES)] + [(c, "dense") for c in
+                                                             ("n307_d128", "pems07_full", "gambia_full", "syn4096_nb2")]
+
+
+@pytest.mark.parametrize("case,path", CASE_PATHS)
+def test_net_matches_oracle_at_config_shapes(case, path, monkeypatch):
     """Whole-net forward + backward against the fp64 CPU oracle: predictions, every block output, every
     attention-logit tensor < 1e-4; every gradient < max(1e-4, 3 x the error the same algorithm makes in plain
     fp32 on the CPU) [+ the kink slack at unconditioned shapes].  No retries."""
+    monkeypatch.setenv("DSTAG_CHEB", path)
     from oracle import dstagnn_oracle as O
     from helpers import _oracle_run, conditioned_case, kink_slack, oracle_fp32_grad_err
     shape, seed, conditioned = ORACLE_CASES[case]
@@ -124,6 +136,7 @@ def test_net_matches_oracle_at_config_shapes(case):
                      torch.from_numpy(tmd), 12, T, N, Dm, 32, 32, H)
     net.load_state_dict({k: v.detach().float() for k, v in onet.named().items()})
     net.eval()
+    assert all(b.cheb_path == ("sparse" if path == "auto" else path) for b in net.BlockList)
     blocks, atts = [], []
     for b in net.BlockList:
         b.register_forward_hook(lambda m, i, o: (blocks.append(o[0].detach()), atts.append(o[1].detach()), None)[2])
@@ -144,7 +157,7 @@ def test_net_matches_oracle_at_config_shapes(case):
         strict += tol == TOL_GRAD
         if not e < tol:
             bad.append(f"{k}: {e:.3e} (fp32 oracle itself: {fp32_err[k]:.3e}, kink slack {slack[k]:.3e})")
-    print(case, "data seed", seed, "pred", rel_err(y.detach(), y_ref), "worst grad", worst,
+    print(case, path, "data seed", seed, "pred", rel_err(y.detach(), y_ref), "worst grad", worst,
           f"; {strict} of {sum(v is not None for v in ograds.values())} gradient tensors held to {TOL_GRAD}")
     assert not bad, "; ".join(bad)
 

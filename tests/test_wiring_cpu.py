@@ -10,8 +10,11 @@ from dstagnn_drought_b200 import make_model
 from helpers import GOLDEN, load_golden, rel_err
 
 
+@pytest.mark.parametrize("path", ["dense", "sparse"])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_block_stack_wiring_matches_reference(name, monkeypatch):
+def test_block_stack_wiring_matches_reference(name, path, monkeypatch):
+    """Both Chebyshev paths (dense N x N contraction / edge lists) against the reference fixtures."""
+    monkeypatch.setenv("DSTAG_CHEB", path)
     fake = cpu_emulation.install(monkeypatch)
     d, cfg, w, g, cheb = load_golden(name)
     net = make_model("cpu", 1, cfg["nb"], 1, cfg["K"], 32, 32, 1, torch.from_numpy(d["adj_tmd"]),
@@ -19,6 +22,7 @@ def test_block_stack_wiring_matches_reference(name, monkeypatch):
                      cfg["N"], cfg["D"], 32, 32, cfg["H"])
     net.load_state_dict(w)
     net.eval()
+    assert all(b.cheb_path == path for b in net.BlockList)
     blocks, atts = [], []
 
     def grab(_m, _i, o):
