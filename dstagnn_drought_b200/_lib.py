@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -33,7 +33,7 @@ class Gemm(C.Structure):
                 ("A", Operand), ("B", Operand), ("C", Operand),
                 ("Amul", Operand), ("Cmul", Operand), ("Cadd", Operand),
                 ("alpha", C.c_float), ("relu", C.c_int32), ("accumulate", C.c_int32),
-                ("split_k", C.c_int32), ("precision", C.c_int32), ("pad_", C.c_int32),
+                ("split_k", C.c_int32), ("precision", C.c_int32), ("chain", C.c_int32),
                 ("split_stride", C.c_int64)]
 
 
@@ -84,7 +84,9 @@ SIGNATURES = {
     "dstag_spmm_reduce": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_edge_dots": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_scale_keys": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _i32, _F]),
-    "dstag_dqk_combine": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _f32, _F]),
+    "dstag_center_queries": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _i32, _F]),
+    "dstag_dqk_combine": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _f32,
+                                    _F]),
     "dstag_dbias_sparse": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _i32, _F]),
 }
 

@@ -356,13 +356,17 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                  c_add: Optional[Tuple[str, torch.Tensor]] = None,
                  c_mul: Optional[Tuple[str, torch.Tensor]] = None, alpha: float = 1.0,
                  relu: bool = False, accumulate: int = ACC_STORE, split_k: Optional[int] = None,
-                 precision=None, tag: Optional[str] = None, reproducible: Optional[bool] = None) -> torch.Tensor:
+                 precision=None, tag: Optional[str] = None, reproducible: Optional[bool] = None,
+                 chain: int = 0) -> torch.Tensor:
     """Enqueue one contraction on the current CUDA stream.  No autograd.
 
     ``reproducible``: a reduction that is split over K (or whose outer K level is folded into a batch)
     writes one partial result per split into a workspace and sums the slices in a fixed order
     (``dstag_sum_slices``) instead of adding atomically.  Every forward product runs this way
-    (``None`` = the module default, see ``set_reproducible``)."""
+    (``None`` = the module default, see ``set_reproducible``).
+
+    ``chain``: longest accumulation chain (in k) the tensor-core engine may run in its truncating fp32
+    accumulator before folding the partial result into registers (0 = unlimited; honoured for N <= 32)."""
     if a_mul is None:
         # a training step repeats the same ~100 contractions with the same layouts: the orientation decision
         # and the problem sizes are memoised per (spec, layouts) -- host time matters at the small graph
@@ -380,7 +384,7 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
             sa, sb = ins.split(",")
             return contract_raw(f"{sb},{sa}->{res}", B, A, out=out, c_add=c_add, c_mul=c_mul, alpha=alpha, relu=relu,
                                 accumulate=accumulate, split_k=split_k, precision=precision, tag=tag,
-                                reproducible=reproducible)
+                                reproducible=reproducible, chain=chain)
     if _FP32_SPECS and precision is None and any(t in spec or (tag and t in tag) for t in _FP32_SPECS):
         precision = _lib.PREC_FP32          # debugging aid: DSTAG_FP32_SPECS=substring,... forces the exact engine
     lib = _lib.load()
@@ -438,6 +442,7 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
                 _fold_k_outer_into_batch(g)
                 if accumulate == ACC_STORE:
                     out.zero_()
+    g.chain = int(chain)
     st = _lib.stream_ptr(A)
     with _lib.on_device(st):
         if _lib._prof is None:

@@ -52,6 +52,7 @@ struct TcParams {
   int a_mode, b_mode;      // MODE_* (see Producer)
   int a_tma, b_tma;        // operand tile arrives by TMA (cp.async.bulk.tensor) instead of LDG
   int a_bdim[2], b_bdim[2];  // which of the two batch levels are real tensor-map dimensions
+  int chunk_kb;              // > 0: accumulate at most this many k-blocks per TMEM pass (see "short chains")
   int a_rt;                  // output rows per M tile: 128, or fewer when the A tile is a ragged TMA box
   int a_rag_d1;              // > 0: A rows are (x, t) windows loaded by a rank-3 box (32 k, d1 t, a_rt / d1 x)
 };
@@ -811,16 +812,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t idesc_ts = idesc & ~(1u << 15);     // A from tensor memory is always K-major
       const uint64_t a_adv = a_mn ? (uint64_t)((TC_BM / 32) * 1024 >> 4) : 2ull;
       const uint64_t b_adv = b_mn ? (uint64_t)((BN / 32) * 1024 >> 4) : 2ull;
-      uint32_t it = 0, item = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
+      // Short chains: the tensor core's fp32 accumulator TRUNCATES at every k-step, a bias that grows with
+      // the chain and shows up in products whose result is much smaller than its terms.  With chunk_kb > 0 a
+      // tile is accumulated in passes of chunk_kb k-blocks that alternate between the two TMEM accumulators;
+      // the epilogue warps add the passes in registers (round to nearest).  `pass` counts accumulator passes
+      // the same way in both roles; without chunking a pass is a whole tile.
+      uint32_t it = 0, pass = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
         const int ks = w % p.nsplit;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        const uint32_t acc = item & 1;
-        mbar_wait(tempty_bar + acc, ((item >> 1) & 1) ^ 1, 0);
+        const int chunk = p.chunk_kb > 0 ? p.chunk_kb : kb1 - kb0;
+        for (int c0 = kb0; c0 < kb1; c0 += chunk, ++pass) {
+        const int c1 = min(kb1, c0 + chunk);
+        const uint32_t acc = pass & 1;
+        mbar_wait(tempty_bar + acc, ((pass >> 1) & 1) ^ 1, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = c0; kb < c1; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(full_bar + s, ph, 0);
@@ -834,7 +843,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t aa = a_adv * kk, ba = b_adv * kk;
-            const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
+            const uint32_t first = (kb == c0 && kk == 0) ? 0u : 1u;
             if constexpr (Cfg::ATM) {
               const uint32_t ta = tmem_base + Cfg::A_TM + s * 64 + 8 * kk;     // hi columns; lo at +32
               umma_tf32_ts(d_tmem, ta + 32, b_hi + ba, idesc_ts, first);
@@ -850,7 +859,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           umma_commit(empty_bar + s);          // stage reusable once these MMAs have read it
         }
-        umma_commit(tfull_bar + acc);          // accumulator complete -> epilogue
+        umma_commit(tfull_bar + acc);          // accumulator pass complete -> epilogue
+        }
       }
     }
   } else {
@@ -873,14 +883,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     };
     const bool c_quad = g.accumulate != DSTAG_ACC_ATOMIC && g.split_stride % 4 == 0 && quad(g.C) && (!g.Cadd.ptr || quad(g.Cadd)) &&
                         (!g.Cmul.ptr || quad(g.Cmul));
-    uint32_t item = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item) {
+    uint32_t pass = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
       int q = w;
       const int ks = q % p.nsplit; q /= p.nsplit;
       const int tn = q % p.ntn; q /= p.ntn;
       const int tm = q % p.ntm;
       const int batch = q / p.ntm;
-      const uint32_t acc = item & 1;
+      const int kb0e = ks * p.kb_per_split, kb1e = min(p.kblocks, kb0e + p.kb_per_split);
+      const int npass = p.chunk_kb > 0 ? (kb1e - kb0e + p.chunk_kb - 1) / p.chunk_kb : 1;
       const int m = tm * p.a_rt + q4 * 32 + lane;               // tile rows beyond a_rt are padding of a ragged tile
       const bool mok = q4 * 32 + lane < p.a_rt && m < g.M;
       float* Cb = (float*)g.C.ptr + axoff64(g.C.batch, batch) + (long long)ks * g.split_stride;
@@ -892,13 +903,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       float* C = Cb + c_ro;
       const float* Ca = Cab ? Cab + ca_ro : nullptr;
       const float* Cm = Cmb ? Cmb + cm_ro : nullptr;
-      if (lane == 0) mbar_wait(tfull_bar + acc, (item >> 1) & 1, 1000);
+      // all passes but the last (short-chain mode, BN == 32 only): fold them into registers and hand the
+      // accumulator back at once
+      // (partial sums parked in this warp's 32 x 32 shared-memory tile, pitch 33: the store paths below need
+      //  the registers, and the kernel is capped at 96 per thread)
+      if constexpr (BN == 32) {
+        for (int ps = 0; ps + 1 < npass; ++ps, ++pass) {
+          const uint32_t a0 = pass & 1;
+          if (lane == 0) mbar_wait(tfull_bar + a0, (pass >> 1) & 1, 200);
+          __syncwarp();
+          tc_fence_after();
+          float t[32];
+          tmem_ld32(tmem_base + a0 * BN + ((uint32_t)(q4 * 32) << 16), t);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + a0);          // the accumulator is free again: MMAs go on
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = ps == 0 ? t[j] : tbuf[lane * 33 + j] + t[j];
+        }
+      }
+      const uint32_t acc = pass & 1;
+      if (lane == 0) mbar_wait(tfull_bar + acc, (pass >> 1) & 1, 1000);
       __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         float v[32];
         tmem_ld32(tmem_base + acc * BN + cc * 32 + ((uint32_t)(q4 * 32) << 16), v);
+        if constexpr (BN == 32) {
+          if (npass > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += tbuf[lane * 33 + j];
+            __syncwarp();                                        // tbuf is reused by the transposing store paths
+          }
+        }
         const int n0 = tn * BN + cc * 32;
         if (n0 >= g.N) continue;                       // warp-uniform
         const bool full = n0 + 32 <= g.N;
@@ -1026,6 +1064,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + acc);
+      ++pass;
     }
   }
 
@@ -1302,6 +1341,8 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
     }
   }
   p.b_tma = make_tmap(&maps.b, p.b_bdim, g->B, g->B.row, g->B.col, p.b_mode, g->K, g->N, g->batch, bn) ? 1 : 0;
+  // short accumulation chains: only with a 32-column tile (the partial sums live in 32 registers per thread)
+  p.chunk_kb = (g->chain > 0 && bn == 32) ? (g->chain + TC_BK - 1) / TC_BK : 0;
   p.ntm = (g->M + p.a_rt - 1) / p.a_rt;
   p.ntn = (g->N + bn - 1) / bn;
   p.kblocks = (g->K + TC_BK - 1) / TC_BK;

@@ -366,12 +366,10 @@ class SpatialChebConv(torch.autograd.Function):
         alpha = 1.0 / math.sqrt(dk)
         # The rows of dS sum to zero (softmax backward), so these two products cancel heavily, and the tensor
         # core's fp32 accumulator TRUNCATES at every k-step: over a chain of N / 8 steps the bias reached
-        # 1.3e-4 of max|grad| on the real PEMS04 graph.  Chains of <= _DQK_CHAIN terms, partial results summed
-        # in fp32 (round to nearest) by dstag_sum_slices, keep the error at the level of a plain fp32 product;
-        # the outputs are small (B x N x K x d_k), so the extra slices cost nothing measurable.
-        sk = max(1, -(-N // _DQK_CHAIN))
-        contract_raw("bkji,bjkd->bikd", dSv, Ks, out=dqk[:, :, 0], alpha=alpha, split_k=sk, reproducible=True)
-        contract_raw("bkji,bikd->bjkd", dSv, Qs, out=dqk[:, :, 1], alpha=alpha, split_k=sk, reproducible=True)
+        # 1.3e-4 of max|grad| on the real PEMS04 graph.  The engine folds the accumulator into registers every
+        # _DQK_CHAIN terms (round to nearest), which keeps the error at the level of a plain fp32 product.
+        contract_raw("bkji,bjkd->bikd", dSv, Ks, out=dqk[:, :, 0], alpha=alpha, chain=_DQK_CHAIN)
+        contract_raw("bkji,bikd->bjkd", dSv, Qs, out=dqk[:, :, 1], alpha=alpha, chain=_DQK_CHAIN)
         dbias = None
         if ctx.needs_input_grad[1]:
             dbias = colsum(dS, B, K * N * ld).view(K, N, ld)

@@ -23,6 +23,7 @@ from . import _lib
 from .contraction import _check, contract_raw
 
 SPARSE_MAX_DENSITY = 0.05
+SHORT_CHAIN = int(os.environ.get("DSTAG_SHORT_CHAIN", "64"))
 
 
 def choose_path(cheb_polynomials: Sequence, d_k: int) -> str:
@@ -30,7 +31,7 @@ def choose_path(cheb_polynomials: Sequence, d_k: int) -> str:
     mode = os.environ.get("DSTAG_CHEB", "auto").lower()
     if mode not in ("auto", "dense", "sparse"):
         raise ValueError(f"DSTAG_CHEB must be auto, dense or sparse (got {mode!r})")
-    if d_k > 32:
+    if d_k > 32 or len(cheb_polynomials) * d_k > 128:
         return "dense"                               # dstag_dqk_combine keeps one lane per d_k component
     if mode != "auto":
         return mode
@@ -146,12 +147,18 @@ class SparseChebConv(torch.autograd.Function):
                                        g["col"].data_ptr(), h.data_ptr(), r.data_ptr(), B, K, N, L, E, st), "dstag_edge_dots")
         rK = torch.empty((B, N, K, dk), device=dev, dtype=torch.float32)
         _lib.check(lib.dstag_scale_keys(qk.data_ptr(), r.data_ptr(), rK.data_ptr(), B, N, K, dk, st), "dstag_scale_keys")
+        Qc = torch.empty((B, N, K, dk), device=dev, dtype=torch.float32)
+        qsum = torch.empty((B, K * dk), device=dev, dtype=torch.float32)
+        _lib.check(lib.dstag_center_queries(qk.data_ptr(), qsum.data_ptr(), Qc.data_ptr(), B, N, K, dk, st),
+                   "dstag_center_queries")
         Pv = P[..., :N]
         # the only dense work of the backward: two N x N x d_k products with the (non-negative) softmax maps
-        O = contract_raw("bkji,bikd->bjkd", Pv, qk[:, :, 0], tag="sat_PQ")            # (B, N, K, dk)
-        W = contract_raw("bkji,bjkd->bikd", Pv, rK, tag="sat_PtrK")                   # (B, N, K, dk)
+        # (accumulated in chains of 64 terms: the tensor core's accumulator truncates, and the bias of a chain
+        #  of N terms reached 1e-3 of the projection-bias gradients at N = 4096)
+        O = contract_raw("bkji,bikd->bjkd", Pv, Qc, tag="sat_PQ", chain=SHORT_CHAIN)     # (B, N, K, dk)
+        W = contract_raw("bkji,bjkd->bikd", Pv, rK, tag="sat_PtrK", chain=SHORT_CHAIN)   # (B, N, K, dk)
         dqk = torch.empty_like(qk)
-        _lib.check(lib.dstag_dqk_combine(qk.data_ptr(), h.data_ptr(), r.data_ptr(), O.data_ptr(), W.data_ptr(),
+        _lib.check(lib.dstag_dqk_combine(qk.data_ptr(), Qc.data_ptr(), h.data_ptr(), r.data_ptr(), O.data_ptr(), W.data_ptr(),
                                          g["rowptr"].data_ptr(), g["col"].data_ptr(), g["t_rowptr"].data_ptr(),
                                          g["t_col"].data_ptr(), g["t_eid"].data_ptr(), dqk.data_ptr(), B, N, K, dk, E,
                                          1.0 / math.sqrt(dk), st), "dstag_dqk_combine")

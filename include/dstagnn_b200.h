@@ -80,7 +80,10 @@ typedef struct {
                             together with split_stride != 0 */
   int32_t split_k;       /* >= 1 */
   int32_t precision;     /* DSTAG_PREC_* */
-  int32_t pad_;
+  int32_t chain;         /* 0, or the longest accumulation chain (in k) the tensor-core engine may run in its
+                            fp32 accumulator before folding the partial result into registers: the accumulator
+                            truncates at every k-step, a bias that matters for products whose result is far
+                            smaller than its terms.  Honoured for N <= 32 (tile of 32 columns). */
   int64_t split_stride;  /* 0, or (accumulate == STORE): K-split s writes its partial product to
                             C + s * split_stride (elements) instead of adding atomically; the caller sums the
                             split_k slices in a fixed order with dstag_sum_slices -- a reproducible reduction */
@@ -282,9 +285,11 @@ int dstag_bias_transpose_bwd(const float* adj_pa, const float* dbiasT, float* dm
  *   dstag_spmm_reduce  dst[b,n,:] = sum_k sum_{e in row (k,n)} a[b,..] * src[k,b,col[e],:]      dX = sum_k A_k dZ_k
  *   dstag_edge_dots    h[b,e] = a[b,e] * <dZ[k,b,j,:], X[b,col[e],:]>, r[b,k,j] = sum_{e in row} h[b,e]
  *   dstag_scale_keys   rK[b,j,k,:] = r[b,k,j] * Ks[b,j,k,:]          qk (B,N,2,K,dk) packed [Qs | Ks], rK (B,N,K,dk)
+ *   dstag_center_queries Qc[b,n,k,:] = Qs[b,n,k,:] - mean_n Qs[b,n,k,:]  (rows of dS sum to zero: a vector common
+ *                      to all queries drops out of the key gradient; removing it first avoids its cancellation)
  *   dstag_dqk_combine  dqk[b,n,0,k,:] = alpha (sum_{e in col (k,n)} h[b,e] Ks[b,j_e,k,:] - W[b,n,k,:])
- *                      dqk[b,n,1,k,:] = alpha (sum_{e in row (k,n)} h[b,e] Qs[b,i_e,k,:] - r[b,k,n] O[b,n,k,:])
- *                      with O = P Qs and W = P^T (r Ks) from dstag_gemm: the softmax backward
+ *                      dqk[b,n,1,k,:] = alpha (sum_{e in row (k,n)} h[b,e] Qc[b,i_e,k,:] - r[b,k,n] O[b,n,k,:])
+ *                      with O = P Qc and W = P^T (r Ks) from dstag_gemm: the softmax backward
  *                      dS = h (on edges) - r P is never materialised
  *   dstag_dbias_sparse dbiasT[k, pa_j[p], pa_i[p]] = sum_b (h[b, pa_eid[k,p]] if >= 0) - r[b,k,j] P[b,k,j,i]
  *                      over the npa non-zeros of adj_pa (the only entries the mask gradient keeps)
@@ -299,7 +304,9 @@ int dstag_edge_dots(const float* dZ, const float* X, const float* a, const int32
                     float* r, int32_t B, int32_t K, int32_t N, int32_t L, int32_t E, void* stream);
 int dstag_scale_keys(const float* qk, const float* r, float* rK, int32_t B, int32_t N, int32_t K, int32_t dk,
                      void* stream);
-int dstag_dqk_combine(const float* qk, const float* h, const float* r, const float* O, const float* W,
+int dstag_center_queries(const float* qk, float* sums /* (B, K dk) scratch */, float* Qc, int32_t B, int32_t N,
+                         int32_t K, int32_t dk, void* stream);
+int dstag_dqk_combine(const float* qk, const float* Qc, const float* h, const float* r, const float* O, const float* W,
                       const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
                       const int32_t* t_eid, float* dqk, int32_t B, int32_t N, int32_t K, int32_t dk, int32_t E,
                       float alpha, void* stream);

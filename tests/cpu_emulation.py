@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 11
+        return 12
 
     def dstag_last_error(self):
         return self.err
@@ -455,9 +455,17 @@ def _emu_sparse(cls):
         _arr(rK, B * N * K * dk).reshape(B, N, K, dk)[:] = R.transpose(0, 2, 1)[..., None] * Q[:, :, 1]
         return 0
 
-    def dstag_dqk_combine(self, qk, h, r, O, W, rowptr, col, t_rowptr, t_col, t_eid, dqk, B, N, K, dk, E, alpha, stream):
+    def dstag_center_queries(self, qk, sums, Qc, B, N, K, dk, stream):
+        self.launches += 1
+        Q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk)[:, :, 0].astype(np.float64)
+        _arr(Qc, B * N * K * dk).reshape(B, N, K, dk)[:] = Q - Q.mean(axis=1, keepdims=True)
+        return 0
+
+    def dstag_dqk_combine(self, qk, Qc, h, r, O, W, rowptr, col, t_rowptr, t_col, t_eid, dqk, B, N, K, dk, E, alpha,
+                          stream):
         self.launches += 1
         Q = _arr(qk, B * N * 2 * K * dk).reshape(B, N, 2, K, dk).astype(np.float64)
+        Qcm = _arr(Qc, B * N * K * dk).reshape(B, N, K, dk).astype(np.float64)
         H = _arr(h, B * E).reshape(B, E).astype(np.float64)
         R = _arr(r, B * K * N).reshape(B, K, N).astype(np.float64)
         Om = _arr(O, B * N * K * dk).reshape(B, N, K, dk).astype(np.float64)
@@ -468,7 +476,7 @@ def _emu_sparse(cls):
         for b in range(B):
             dq = np.zeros((K * N, dk)); dk_ = np.zeros((K * N, dk))
             np.add.at(dq, trow, H[b, te][:, None] * Q[b, tc, 1, trow // N])
-            np.add.at(dk_, row, H[b][:, None] * Q[b, c, 0, row // N])
+            np.add.at(dk_, row, H[b][:, None] * Qcm[b, c, row // N])
             dq = dq.reshape(K, N, dk).transpose(1, 0, 2) - Wm[b]
             dk_ = dk_.reshape(K, N, dk).transpose(1, 0, 2) - R[b].T[..., None] * Om[b]
             out[b, :, 0] = alpha * dq
@@ -491,7 +499,7 @@ def _emu_sparse(cls):
         return 0
 
     for f in (dstag_edge_probs, dstag_spmm_expand, dstag_spmm_reduce, dstag_edge_dots, dstag_scale_keys,
-              dstag_dqk_combine, dstag_dbias_sparse):
+              dstag_center_queries, dstag_dqk_combine, dstag_dbias_sparse):
         setattr(cls, f.__name__, f)
     return cls
 
