@@ -136,7 +136,8 @@ class _Profiled:
             with on_device(args[-1]):
                 if _prof is None:
                     return fn(*args)
-                with prof_range(name):
+                from .profile_bytes import algo_bytes
+                with prof_range(name, 0, algo_bytes(name, args)):
                     return fn(*args)
         return call
 
