@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 12
+ABI_VERSION = 14
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -35,6 +35,11 @@ class Gemm(C.Structure):
                 ("alpha", C.c_float), ("relu", C.c_int32), ("accumulate", C.c_int32),
                 ("split_k", C.c_int32), ("precision", C.c_int32), ("chain", C.c_int32),
                 ("split_stride", C.c_int64)]
+
+
+class Copy(C.Structure):     # dstag_copy_t
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int32 * 4), ("src_stride", C.c_int64 * 4),
+                ("dst_stride", C.c_int64 * 4)]
 
 
 _F = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
@@ -76,6 +81,8 @@ SIGNATURES = {
     "dstag_smooth_l1_fwd": (C.c_int, [_F, _F, _F, _F, _i64, _F]),
     "dstag_smooth_l1_bwd": (C.c_int, [_F, _F, _F, _F, _i64, _F]),
     "dstag_adam_step": (C.c_int, [_F, _F, _F, _F, _i64, _f32, _f32, _f32, _f32, _f32, _F, _u64, _F]),
+    "dstag_gather_flat": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(_i64), C.POINTER(_i64), _i32, _F, _F]),
+    "dstag_multi_copy": (C.c_int, [C.POINTER(Copy), _i32, _F]),
     "dstag_tick": (C.c_int, [_F, _i32, _F]),
     "dstag_bias_transpose": (C.c_int, [_F, C.POINTER(C.c_void_p), _i32, _F, _i32, _i32, _F]),
     "dstag_bias_transpose_bwd": (C.c_int, [_F, _F, _F, _i32, _i32, _i32, _F]),

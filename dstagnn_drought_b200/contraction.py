@@ -459,13 +459,72 @@ def contract_raw(spec: str, A: torch.Tensor, B: torch.Tensor, *, out: Optional[t
 
 
 # ----------------------------------------------------------------------------------------
+# zero-initialised scratch (accumulation targets of the backward kernels)
+# ----------------------------------------------------------------------------------------
+class ZeroArena:
+    """One buffer per device, cleared ONCE per training step, from which the backward takes its zero-initialised
+    accumulators (bias / LayerNorm / table gradients that kernels add into): ~80 separate fill kernels per step
+    become one.  ``step.TrainStep`` resets it at the top of every step; when no arena is armed (plain autograd use
+    of the modules) ``zeros`` is ``torch.zeros``.  Slices are handed out in order and never reused within a step."""
+
+    ALIGN = 32                       # floats: every slice starts on a 128-byte boundary
+
+    def __init__(self, device, numel: int):
+        self.buf = torch.zeros(numel, device=device, dtype=torch.float32)
+        self.used = 0
+        self.peak_demand = 0
+
+    def reset(self):
+        if self.used:
+            self.buf[:self.used].zero_()
+        self.used = 0
+        self.peak_demand = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= d
+        need = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.peak_demand += need
+        if self.used + need > self.buf.numel():
+            return None
+        out = self.buf[self.used:self.used + n].view(shape)
+        self.used += need
+        return out
+
+
+_arenas = {}
+
+
+def arm_zero_arena(device, numel: int) -> ZeroArena:
+    a = _arenas[torch.device(device).index] = ZeroArena(device, numel)
+    return a
+
+
+def disarm_zero_arena(device):
+    _arenas.pop(torch.device(device).index, None)
+
+
+def zeros(shape, device) -> torch.Tensor:
+    """fp32 zeros of ``shape``: a slice of the step's arena when one is armed on ``device``, else ``torch.zeros``."""
+    if not isinstance(shape, (tuple, list)):
+        shape = (shape,)
+    a = _arenas.get(torch.device(device).index)
+    if a is not None:
+        t = a.take(tuple(shape))
+        if t is not None:
+            return t
+    return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------
 # small helpers shared with ops.py
 # ----------------------------------------------------------------------------------------
 def colsum(t2d: torch.Tensor, rows: int, cols: int, ld: Optional[int] = None) -> torch.Tensor:
     """sum over rows of a (rows, cols) matrix with leading dimension ld -> (cols,)."""
     lib = _lib.load()
     _check(t2d, "colsum input")
-    out = torch.zeros(cols, device=t2d.device, dtype=torch.float32)
+    out = zeros((cols,), t2d.device)
     _lib.check(lib.dstag_colsum(t2d.data_ptr(), out.data_ptr(), rows, cols, cols if ld is None else ld,
                                 _lib.stream_ptr(t2d)), "dstag_colsum")
     return out

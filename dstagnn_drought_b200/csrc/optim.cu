@@ -3,6 +3,8 @@
 // (train_DSTAGNN_my.py:133,158), the device-resident step counters that make a captured step replayable,
 // and the batch-independent (adj_pa . mask_k)^T bias of cheb_conv_withSAt (model/DSTAGNN_my.py:126).
 // All of them are single-pass streaming kernels: HBM-bound by construction.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace dstag {
@@ -97,6 +99,59 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// flat[off[t] + i] = src[t][i]: the step's parameter gradients (separate tensors, wherever autograd left them)
+// collected into the flat bucket that the all-reduce and the flat Adam consume -- one launch per <= 64 tensors
+// instead of one accumulation kernel per parameter.
+struct GatherArgs {
+  const float* src[64];
+  long long off[64];
+  long long size[64];
+};
+__global__ void __launch_bounds__(256)
+gather_flat_kernel(GatherArgs g, float* __restrict__ flat) {
+  const int t = blockIdx.y;
+  const float* __restrict__ s = g.src[t];
+  float* __restrict__ d = flat + g.off[t];
+  const long long n = g.size[t];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    const long long n4 = n >> 2;
+    for (long long i = i0; i < n4; i += stride) reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
+    for (long long i = (n4 << 2) + i0; i < n; i += stride) d[i] = __ldg(s + i);
+  } else {
+    for (long long i = i0; i < n; i += stride) d[i] = __ldg(s + i);
+  }
+}
+
+// Up to 16 strided copies of <= 4-D fp32 blocks in ONE launch (signed element strides: a flipped axis is a
+// negative stride): the per-step re-layouts of small parameter tensors -- [W_Q | W_K | W_V] packed into
+// 16-byte-aligned rows, the stacked Theta_k, the (o, (d, c)) conv matrices of the GTUs and their flipped
+// transposes, and the matching gradient un-packs -- that used to be ~25 torch cat / pad / flip / copy kernels
+// per block.  blockIdx.y = copy, blockIdx.x strides over its elements (innermost index fastest).
+struct CopyDesc {
+  const float* src;
+  float* dst;
+  int n[4];
+  long long ss[4], ds[4];
+};
+struct MultiCopyArgs { CopyDesc d[16]; };
+__global__ void __launch_bounds__(256)
+multi_copy_kernel(MultiCopyArgs a) {
+  const CopyDesc& c = a.d[blockIdx.y];
+  const long long total = (long long)c.n[0] * c.n[1] * c.n[2] * c.n[3];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    long long q = i;
+    const int i3 = (int)(q % c.n[3]); q /= c.n[3];
+    const int i2 = (int)(q % c.n[2]); q /= c.n[2];
+    const int i1 = (int)(q % c.n[1]);
+    const int i0 = (int)(q / c.n[1]);
+    c.dst[i0 * c.ds[0] + i1 * c.ds[1] + i2 * c.ds[2] + i3 * c.ds[3]] =
+        __ldg(c.src + i0 * c.ss[0] + i1 * c.ss[1] + i2 * c.ss[2] + i3 * c.ss[3]);
+  }
+}
+
 __global__ void tick_kernel(unsigned long long* counters, int n) {
   if ((int)threadIdx.x < n) counters[threadIdx.x] += 1ull;
 }
@@ -184,6 +239,60 @@ int dstag_adam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
       p, g, m, v, n, lr, beta1, beta2, eps, grad_scale, reinterpret_cast<const unsigned long long*>(step_dev),
       (unsigned long long)step_host);
   DSTAG_RETURN_LAUNCH("dstag_adam_step");
+}
+
+int dstag_gather_flat(const float* const* srcs, const int64_t* offsets, const int64_t* sizes, int32_t n, float* flat,
+                      void* stream) {
+  DSTAG_CHECK_ARG(srcs && offsets && sizes && flat && n > 0, "dstag_gather_flat: bad arguments");
+  for (int base = 0; base < n; base += 64) {
+    GatherArgs g;
+    const int m = n - base < 64 ? n - base : 64;
+    long long biggest = 0;
+    for (int t = 0; t < 64; ++t) {
+      const bool on = t < m;
+      g.src[t] = on ? srcs[base + t] : nullptr;
+      g.off[t] = on ? offsets[base + t] : 0;
+      g.size[t] = on ? sizes[base + t] : 0;
+      DSTAG_CHECK_ARG(!on || (g.src[t] && g.size[t] >= 0 && g.off[t] >= 0), "dstag_gather_flat: bad entry %d", base + t);
+      if (g.size[t] > biggest) biggest = g.size[t];
+    }
+    long long bx = (biggest / 4 + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    gather_flat_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(g, flat);
+    DSTAG_CHECK_LAUNCH("dstag_gather_flat");
+  }
+  return 0;
+}
+
+int dstag_multi_copy(const dstag_copy_t* copies, int32_t n, void* stream) {
+  DSTAG_CHECK_ARG(copies && n > 0, "dstag_multi_copy: bad arguments");
+  for (int base = 0; base < n; base += 16) {
+    MultiCopyArgs a;
+    memset(&a, 0, sizeof(a));
+    const int m = n - base < 16 ? n - base : 16;
+    long long biggest = 0;
+    for (int t = 0; t < m; ++t) {
+      const dstag_copy_t& c = copies[base + t];
+      DSTAG_CHECK_ARG(c.src && c.dst, "dstag_multi_copy: null pointer in copy %d", base + t);
+      a.d[t].src = (const float*)c.src;
+      a.d[t].dst = (float*)c.dst;
+      long long tot = 1;
+      for (int k = 0; k < 4; ++k) {
+        DSTAG_CHECK_ARG(c.n[k] >= 1, "dstag_multi_copy: extents must be >= 1");
+        a.d[t].n[k] = c.n[k];
+        a.d[t].ss[k] = c.src_stride[k];
+        a.d[t].ds[k] = c.dst_stride[k];
+        tot *= c.n[k];
+      }
+      if (tot > biggest) biggest = tot;
+    }
+    long long bx = (biggest + 255) / 256;
+    if (bx > 128) bx = 128;
+    multi_copy_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(a);
+    DSTAG_CHECK_LAUNCH("dstag_multi_copy");
+  }
+  return 0;
 }
 
 int dstag_tick(uint64_t* counters, int32_t n, void* stream) {

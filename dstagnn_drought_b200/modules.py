@@ -60,11 +60,8 @@ class MultiHeadAttention(nn.Module):
     def forward(self, e2d, res_att, B, Fe, T):
         """e2d: (B*F*T, N) rows (b,f,t).  Returns (LN(fc(ctx) + e), logits (B,F,H,T,T))."""
         H, dk = self.n_heads, self.d_k
-        w_qkv = torch.cat([self.W_Q.weight, self.W_K.weight, self.W_V.weight], dim=0)     # (3*H*dk, N)
-        N = w_qkv.shape[1]
-        if padded_ld(N) != N:
-            # rows over the node axis are kept 16-byte aligned (vector / TMA operand loads for odd N)
-            w_qkv = F_.pad(w_qkv, (0, padded_ld(N) - N))[:, :N]
+        # (3*H*dk, N) packed projections; rows over the node axis 16-byte aligned (vector / TMA loads for odd N)
+        w_qkv = ops.PackRows.apply(self.W_Q.weight, self.W_K.weight, self.W_V.weight)
         qkv = contract("rn,on->ro", e2d, w_qkv)                                           # (B,F,T,3,H,dk)
         ctx, logits = ops.TemporalAttention.apply(qkv, res_att, B, Fe, H, T, dk)
         fc = contract("rk,nk->rn", ctx.view(B * Fe * T, H * dk), self.fc.weight, pad_rows=True)
@@ -203,21 +200,21 @@ class DSTAGNN_block(nn.Module):
         # 2. temporal attention                                                      (line 231)
         o2d, logits = self.TAt(e2d, res_att, B, Fin, T)
         # 3. pre_conv: per-node Linear over (t, f)                                   (line 232)
-        w_pre = self.pre_conv.weight[:, :, 0, :]                                       # (D, T, F) view
+        w_pre = self.pre_conv.weight.view(D, T, Fin)                                   # (D, T, 1, F) -> (D, T, F)
         z = contract("bftn,dtf->bnd", o2d.view(B, Fin, T, N), w_pre, c_add=("d", self.pre_conv.bias))
         # 4. spatial embedding + dropout                                             (lines 233-234)
         p_drop = self.dropout.p if train else 0.0
         se = ops.LayerNormAdd.apply(z.view(B * N, D), self.EmbedS.pos_embed.weight, self.EmbedS.norm.weight,
                                     self.EmbedS.norm.bias, False, p_drop, ops.next_seed() if train else 0)
         # 5+6. spatial attention maps and the Chebyshev contraction                  (lines 235-236)
-        w_sat = torch.cat([self.SAt.W_Q.weight, self.SAt.W_K.weight], dim=0)           # (2*K*dk, D)
+        w_sat = ops.PackRows.apply(self.SAt.W_Q.weight, self.SAt.W_K.weight)           # (2*K*dk, D)
         qk = contract("rd,od->ro", se, w_sat).view(B, N, 2, K, dk)
         if self.cheb_path == "sparse" and (T * Fin) % 4 == 0:      # (the edge kernels move rows as float4)
             edges = {n: getattr(self, "edges_" + n) for n in self._edge_names}
             zc = SparseChebConv.apply(qk, self._bias_T(), self.cheb_T, x3, edges)       # (K, B, N, (t,f))
         else:
             zc = ops.SpatialChebConv.apply(qk, self._bias_T(), self.cheb_T, x3)
-        theta = torch.stack(list(self.cheb_conv_SAt.Theta))                             # (K, F, C)
+        theta = ops.PackRows.apply(*self.cheb_conv_SAt.Theta).view(K, Fin, C)           # (K, F, C)
         g = contract("kxtf,kfc->xtc", zc.view(K, B * N, T, Fin), theta, relu=True)      # (B*N, T, C)
         # 7. gated temporal convolutions                                             (lines 237-242)
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
@@ -267,18 +264,15 @@ class DSTAGNN_submodule(nn.Module):
         """x: (B, N, F, T) -> (B, N, num_for_predict)   (model/DSTAGNN_my.py:271-280)."""
         B, N = x.shape[0], x.shape[1]
         res_att = 0
-        h = None
         T = self.BlockList[0].T
-        for i, block in enumerate(self.BlockList):
+        outs = []
+        for block in self.BlockList:
             x, res_att = block(x, res_att)
             C = x.shape[2]
-            # final_conv is a per-node Linear over (t_cat, c); summing one slice per block
-            # avoids materialising the concatenation of line 277.
-            w_i = self.final_conv.weight[:, i * T:(i + 1) * T, 0, :]                    # (128, T, C) view
-            part = contract("xtc,otc->xo", x.permute(0, 1, 3, 2).reshape(B * N, T, C), w_i,
-                            c_add=("o", self.final_conv.bias) if i == 0 else None)
-            h = part if h is None else h + part
-        y = contract("xo,po->xp", h, self.final_fc.weight, c_add=("p", self.final_fc.bias))
+            outs.append(x.permute(0, 1, 3, 2).reshape(B * N, T, C))       # the block's own channels-last buffer
+        # final_conv (a per-node Linear over the concatenated (t, c), never concatenated) + final_fc
+        y = ops.Head.apply(self.final_conv.weight, self.final_conv.bias, self.final_fc.weight, self.final_fc.bias,
+                           *outs)
         return y.view(B, N, -1)
 
 

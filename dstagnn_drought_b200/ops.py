@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import ACC_ADD, ACC_ATOMIC, ACC_STORE
-from .contraction import _check, colsum, contract_raw, dense_rows, empty_rows
+from .contraction import _check, colsum, contract_raw, dense_rows, empty_rows, zeros
 
 _VP = C.c_void_p
 
@@ -72,6 +72,68 @@ def next_seed() -> int:
     x = (base * 0x9E3779B97F4A7C15 + _seed_counter * 0xBF58476D1CE4E5B9 + (_rank() + 1) * 0xD6E8FEB86659FD93) & _M64
     x ^= x >> 31
     return (x * 0x94D049BB133111EB) & _M64
+
+
+# ----------------------------------------------------------------------------------------
+# small strided re-layouts, many per launch
+# ----------------------------------------------------------------------------------------
+def multi_copy(pairs):
+    """One launch for a list of strided fp32 copies.  Each entry is ``(dst, src)`` with two tensors of the same
+    shape (<= 4-D, any strides) or ``(dst, (src_ptr, src_strides))`` with an explicit source (element strides, may
+    be negative -- a flipped axis -- which a torch view cannot express)."""
+    lib = _lib.load()
+    n = len(pairs)
+    arr = (_lib.Copy * n)()
+    for c, (dst, src) in zip(arr, pairs):
+        shape = tuple(dst.shape)
+        if len(shape) > 4:
+            raise ValueError("multi_copy handles at most 4 dimensions")
+        pad = 4 - len(shape)
+        if isinstance(src, tuple):
+            sptr, sstr = src
+        else:
+            if tuple(src.shape) != shape:
+                raise ValueError(f"multi_copy: shapes differ: {tuple(src.shape)} vs {shape}")
+            _check(src, "multi_copy source")
+            sptr, sstr = src.data_ptr(), src.stride()
+        c.src, c.dst = sptr, dst.data_ptr()
+        for k in range(4):
+            c.n[k] = 1 if k < pad else shape[k - pad]
+            c.src_stride[k] = 0 if k < pad else sstr[k - pad]
+            c.dst_stride[k] = 0 if k < pad else dst.stride(k - pad)
+    _lib.check(lib.dstag_multi_copy(arr, n, _stream(pairs[0][0])), "dstag_multi_copy")
+
+
+class PackRows(torch.autograd.Function):
+    """``torch.cat(ws, dim=0)`` of 2-D parameters into one matrix whose rows are padded to 16 bytes (the engine's
+    vector / TMA operand loads), and its gradient un-packed into contiguous per-parameter tensors -- one launch
+    each way.  Packs [W_Q | W_K | W_V] (lines 92-94), [SAt.W_Q | SAt.W_K] (lines 62-63) and the K Theta_k
+    (line 112)."""
+
+    @staticmethod
+    def forward(ctx, *ws):
+        rows = [w.shape[0] for w in ws]
+        cols = ws[0].shape[1]
+        for w in ws:
+            _check(w, "PackRows input")
+        out = empty_rows((sum(rows), cols), ws[0].device)
+        pairs, r0 = [], 0
+        for w, r in zip(ws, rows):
+            pairs.append((out[r0:r0 + r], w))
+            r0 += r
+        multi_copy(pairs)
+        ctx.rows, ctx.cols = rows, cols
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = [torch.empty((r, ctx.cols), device=dout.device, dtype=torch.float32) for r in ctx.rows]
+        pairs, r0 = [], 0
+        for g, r in zip(grads, ctx.rows):
+            pairs.append((g, dout[r0:r0 + r]))
+            r0 += r
+        multi_copy(pairs)
+        return tuple(grads)
 
 
 # ----------------------------------------------------------------------------------------
@@ -161,8 +223,8 @@ class LayerNormAdd(torch.autograd.Function):
         dense = ctx.needs_input_grad[1] and tab_mod != rows
         dpre = torch.empty((rows, L), device=a.device, dtype=torch.float32) if dense else empty_rows((rows, L),
                                                                                                      a.device)
-        dgamma = torch.zeros(L, device=a.device, dtype=torch.float32)
-        dbeta = torch.zeros(L, device=a.device, dtype=torch.float32)
+        dgamma = zeros((L,), a.device)
+        dbeta = zeros((L,), a.device)
         _lib.check(lib.dstag_layernorm_bwd(dy.data_ptr(), dy.stride(0), a.data_ptr(), lay[0], lay[1], lay[2],
                                            lay[3], tab.data_ptr(), tab_mod, tab.stride(0), gamma.data_ptr(),
                                            mean.data_ptr(), rstd.data_ptr(), dpre.data_ptr(), dpre.stride(0),
@@ -406,9 +468,12 @@ class GtuStack(torch.autograd.Function):
         widths = [T - ks + 1 for ks in GtuStack.KS]
         total = sum(widths)
         out = torch.empty((X, total, Cc), device=g.device, dtype=torch.float32)
+        # conv kernels (2C, C, 1, ks) -> K-contiguous GEMM operands (o, (d, c)): all three in one launch
+        wks = [torch.empty((2 * Cc, ks, Cc), device=g.device, dtype=torch.float32) for ks in GtuStack.KS]
+        multi_copy([(wk, w[:, :, 0, :].permute(0, 2, 1)) for wk, w in zip(wks, (w3, w5, w7))])
         us, off = [], 0
-        for ks, w, b, tp in zip(GtuStack.KS, (w3, w5, w7), (b3, b5, b7), widths):
-            wk = w[:, :, 0, :].permute(0, 2, 1).reshape(2 * Cc, ks * Cc).contiguous()      # (o, (d, c))
+        for ks, wk3d, b, tp in zip(GtuStack.KS, wks, (b3, b5, b7), widths):
+            wk = wk3d.view(2 * Cc, ks * Cc)
             u = contract_raw("xtk,ok->xto", GtuStack._views(g, ks), wk, c_add=("o", b), tag=f"gtu{ks}_fwd",
                              reproducible=True)
             _lib.check(lib.dstag_gtu_gate_fwd(u.data_ptr(), out.data_ptr(), X, Cc, tp, total, off,
@@ -426,25 +491,35 @@ class GtuStack(torch.autograd.Function):
         dout = dout.contiguous()
         total = dout.shape[1]
         dg = torch.empty_like(g) if ctx.needs_input_grad[0] else None
+        wflips = None
+        if dg is not None:
+            # flipped, transposed kernels (c, (d', o)) = w[o, c, 0, ks-1-d'] for the input-gradient correlation:
+            # the flip is a negative source stride, all three matrices in one launch
+            wflips = [torch.empty((Cc, ks, 2 * Cc), device=g.device, dtype=torch.float32) for ks in GtuStack.KS]
+            multi_copy([(wf, (w.data_ptr() + 4 * (ks - 1), (ks, -1, Cc * ks)))
+                        for wf, w, ks in zip(wflips, (w3, w5, w7), GtuStack.KS)])
+        dwks = []
         grads, off, first = [], 0, True
-        for ks, w, u in zip(GtuStack.KS, (w3, w5, w7), (u3, u5, u7)):
+        for i, (ks, w, u) in enumerate(zip(GtuStack.KS, (w3, w5, w7), (u3, u5, u7))):
             tp, pad = T - ks + 1, ks - 1
             tpad = tp + 2 * pad
             dup = torch.empty((X, tpad, 2 * Cc), device=g.device, dtype=torch.float32)
-            db = torch.zeros(2 * Cc, device=g.device, dtype=torch.float32)           # bias gradient, fused
+            db = zeros((2 * Cc,), g.device)                                          # bias gradient, fused
             _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), db.data_ptr(), X, Cc,
                                               tp, pad, total, off, _stream(g)), "dstag_gtu_gate_bwd")
             du = dup[:, pad:pad + tp, :]                                             # valid rows (view)
             dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
-            dw = dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1).reshape(w.shape)
+            dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)
+            dwks.append((dw[:, :, 0, :], dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1)))     # (o, c, d) <- (o, d, c)
             if dg is not None:
-                wflip = w[:, :, 0, :].flip(-1).permute(1, 2, 0).reshape(Cc, ks * 2 * Cc).contiguous()
+                wflip = wflips[i].view(Cc, ks * 2 * Cc)
                 dview = dup.as_strided((X, T, ks * 2 * Cc), (tpad * 2 * Cc, 2 * Cc, 1))
                 contract_raw("xtk,ck->xtc", dview, wflip, out=dg, accumulate=ACC_STORE if first else ACC_ADD,
                              split_k=1, tag=f"gtu{ks}_dx")
                 first = False
             grads += [dw, db]
             off += tp
+        multi_copy(dwks)
         return (dg, *grads)
 
 
@@ -483,8 +558,8 @@ class BlockTail(torch.autograd.Function):
         dtc = torch.empty_like(tc)
         dr = torch.empty_like(tc)
         dg = torch.empty_like(g) if g is not None else None
-        dgamma = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
-        dbeta = torch.zeros(Cc, device=tc.device, dtype=torch.float32)
+        dgamma = zeros((Cc,), tc.device)
+        dbeta = zeros((Cc,), tc.device)
         _lib.check(lib.dstag_tail_bwd(dout.data_ptr(), tc.data_ptr(), _p(g), r.data_ptr(), gamma.data_ptr(),
                                       mean.data_ptr(), rstd.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
                                       dgamma.data_ptr(), dbeta.data_ptr(), X, Cc, T, drop_p, seed,
@@ -534,8 +609,8 @@ class FusedTail(torch.autograd.Function):
         dtc = torch.empty_like(r)
         dr = torch.empty_like(r)
         dg = torch.empty_like(g) if g is not None else None
-        dgamma = torch.zeros(Cc, device=r.device, dtype=torch.float32)
-        dbeta = torch.zeros(Cc, device=r.device, dtype=torch.float32)
+        dgamma = zeros((Cc,), r.device)
+        dbeta = zeros((Cc,), r.device)
         _lib.check(lib.dstag_tail_fused_bwd(dout.data_ptr(), cat.data_ptr(), wf.data_ptr(), bf.data_ptr(), _p(g),
                                             r.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                             dcat.data_ptr(), dtc.data_ptr(), _p(dg), dr.data_ptr(),
@@ -552,11 +627,57 @@ def fcmy_param_grads(dtc: torch.Tensor, cat: torch.Tensor):
     X, T, Cc = dtc.shape
     S = cat.shape[1]
     if lib.dstag_outer_sum_supported(T, S, Cc):
-        dwf = torch.zeros((T, S), device=dtc.device, dtype=torch.float32)
-        dbf = torch.zeros(T, device=dtc.device, dtype=torch.float32)
+        dwf = zeros((T, S), dtc.device)
+        dbf = zeros((T,), dtc.device)
         _lib.check(lib.dstag_outer_sum(dtc.data_ptr(), cat.data_ptr(), dwf.data_ptr(), dbf.data_ptr(), X, T, S, Cc,
                                        _stream(dtc)), "dstag_outer_sum")
         return dwf, dbf
     dwf = contract_raw("xtc,xsc->ts", dtc, cat, tag="fcmy_dw")
     dbf = colsum(dtc, X, T * Cc).view(T, Cc).sum(1)
     return dwf, dbf
+
+
+# ----------------------------------------------------------------------------------------
+# network head: final_conv over the concatenated block outputs + final_fc
+# ----------------------------------------------------------------------------------------
+class Head(torch.autograd.Function):
+    """``final_conv`` + ``final_fc`` of DSTAGNN_submodule.forward (model/DSTAGNN_my.py:277-280).  final_conv is a
+    per-node Linear over (t_cat, c) of the concatenated block outputs; the concatenation is never
+    built: block i contributes ``x_i . W[:, iT:(i+1)T]`` to one accumulator, and in the backward every block's
+    slice of dW is written in place -- no per-block partial weight gradients to add up.
+    xs: nb tensors (X, T, C) channels-last; w_conv (128, nb*T, 1, C); w_fc (P, 128) -> (X, P)."""
+
+    @staticmethod
+    def forward(ctx, w_conv, b_conv, w_fc, b_fc, *xs):
+        for t in (w_conv, b_conv, w_fc, b_fc) + xs:
+            _check(t, "head operand")
+        X, T, Cc = xs[0].shape
+        O = w_conv.shape[0]
+        wv = w_conv.view(O, len(xs) * T, Cc)
+        h = torch.empty((X, O), device=xs[0].device, dtype=torch.float32)
+        for i, x in enumerate(xs):
+            contract_raw("xtc,otc->xo", x, wv[:, i * T:(i + 1) * T], out=h,
+                         c_add=("o", b_conv) if i == 0 else None, accumulate=ACC_STORE if i == 0 else ACC_ADD,
+                         split_k=1)
+        y = contract_raw("xo,po->xp", h, w_fc, c_add=("p", b_fc), reproducible=True)
+        ctx.save_for_backward(w_conv, w_fc, h, *xs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        w_conv, w_fc, h, *xs = ctx.saved_tensors
+        X, T, Cc = xs[0].shape
+        O = w_conv.shape[0]
+        dy = dy.contiguous()
+        wv = w_conv.view(O, len(xs) * T, Cc)
+        dh = contract_raw("xp,po->xo", dy, w_fc)
+        dw_fc = contract_raw("xp,xo->po", dy, h)
+        db_fc = colsum(dy, X, dy.shape[1])
+        db_conv = colsum(dh, X, O)
+        dw_conv = torch.empty(w_conv.shape, device=dy.device, dtype=torch.float32)
+        dwv = dw_conv.view(O, len(xs) * T, Cc)
+        dxs = []
+        for i, x in enumerate(xs):
+            contract_raw("xo,xtc->otc", dh, x, out=dwv[:, i * T:(i + 1) * T])
+            dxs.append(contract_raw("xo,otc->xtc", dh, wv[:, i * T:(i + 1) * T]) if ctx.needs_input_grad[4 + i] else None)
+        return (dw_conv, db_conv, dw_fc, db_fc, *dxs)

@@ -40,14 +40,17 @@ ALIGN = 32      # floats: members of a flat bucket start on 128-byte boundaries
 
 
 class GradBuckets:
-    """Flat per-block gradient storage + overlapped averaging all-reduce.
+    """Flat per-block gradient storage + overlapped all-reduce.
 
-    ``p.grad`` of every live parameter is a view into its bucket's flat buffer.  The reference loop
-    calls ``optimizer.zero_grad()`` (train_DSTAGNN_my.py:154), whose default ``set_to_none=True``
-    DETACHES those views; the buckets therefore check the attachment whenever they are about to reduce
-    (and in ``zero()``): a gradient that autograd allocated afresh is copied into its slot and
-    re-attached, a gradient that is still ``None`` leaves a zero slot.  Either calling convention --
-    ``buckets.zero()`` or ``optimizer.zero_grad()`` at the top of the step -- gives the same result.
+    At the top of a step the live parameters' ``.grad`` are set to ``None`` (``zero()`` -- or the reference
+    loop's own ``optimizer.zero_grad()``, train_DSTAGNN_my.py:154: both work), so autograd simply hands every
+    gradient tensor over instead of launching one accumulation kernel per parameter.  When the last gradient of
+    a bucket has arrived (post-accumulate hooks; blocks finish their backward in reverse order) the bucket's
+    gradients are COLLECTED into its flat buffer by one kernel (``dstag_gather_flat``), the flat buffer is
+    all-reduced in place -- overlapping NVLink traffic with the remaining backward kernels -- and each ``p.grad``
+    is pointed at its slice of the reduced buffer, so any optimizer that reads ``p.grad`` sees the averaged
+    gradients.  ``average=False`` leaves the SUM over ranks in the buckets (``step.FlatAdam`` folds 1 / world
+    into its gradient read instead of a separate scaling kernel).
     """
 
     def __init__(self, net, process_group=None, overlap: bool = True, average: bool = True):
@@ -60,6 +63,7 @@ class GradBuckets:
         self._views: Dict[str, List[torch.Tensor]] = {}
         self._offsets: Dict[str, List[int]] = {}
         self._pending: Dict[str, int] = {}
+        self._done: Dict[str, bool] = {}
         self._works = []
         groups: Dict[str, List] = {}
         for name, p in live_parameters(net).items():
@@ -72,77 +76,81 @@ class GradBuckets:
                 offs.append(n)
                 n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
             flat = torch.zeros(n, device=items[0][1].device, dtype=items[0][1].dtype)
-            views = []
-            for (_, p), off in zip(items, offs):
-                v = flat[off:off + p.numel()].view_as(p)
-                p.grad = v
-                views.append(v)
             self.buckets[b] = flat
             self._members[b] = [p for _, p in items]
-            self._views[b] = views
+            self._views[b] = [flat[off:off + p.numel()].view_as(p) for (_, p), off in zip(items, offs)]
             self._offsets[b] = offs
             self._pending[b] = len(items)
-        if self.overlap:
-            for b, ps in self._members.items():
-                for p in ps:
-                    p.register_post_accumulate_grad_hook(self._make_hook(b))
+            self._done[b] = False
+        for b, ps in self._members.items():
+            for p in ps:
+                p.grad = None
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
         self.numel = sum(p.numel() for ps in self._members.values() for p in ps)      # without the alignment padding
 
     def _make_hook(self, b):
         def hook(_p):
             if self._pending[b] <= 0:          # a new step began without zero(): re-arm
                 self._pending[b] = len(self._members[b])
+                self._done[b] = False
             self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch(b)
+            if self._pending[b] == 0 and self.overlap:
+                self._reduce(b)
         return hook
 
-    def _attach(self, b, copy: bool):
-        """Make every ``p.grad`` of bucket b a view of the flat buffer again.  ``copy``: gradients found in
-        foreign storage are copied into their slot first (they were produced by this step's backward);
-        a gradient that is ``None`` gets a zeroed slot."""
-        for p, v in zip(self._members[b], self._views[b]):
+    def _collect(self, b):
+        """Gather the bucket's gradients into its flat buffer (slots of parameters without a gradient are
+        zeroed) and re-point every ``p.grad`` at its slice."""
+        flat, views = self.buckets[b], self._views[b]
+        srcs, offs, sizes = [], [], []
+        for p, v, off in zip(self._members[b], views, self._offsets[b]):
             g = p.grad
             if g is None:
-                if copy:
-                    v.zero_()
-            elif g.data_ptr() != v.data_ptr() or g.shape != v.shape or not g.is_contiguous():
-                if copy:
-                    v.copy_(g)
-            else:
-                continue
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                srcs.append(g), offs.append(off), sizes.append(g.numel())
+        if srcs:
+            if flat.is_cuda:
+                import ctypes as C
+
+                from . import _lib
+                n = len(srcs)
+                _lib.check(_lib.load().dstag_gather_flat((C.c_void_p * n)(*[g.data_ptr() for g in srcs]),
+                                                         (C.c_int64 * n)(*offs), (C.c_int64 * n)(*sizes), n,
+                                                         flat.data_ptr(), _lib.stream_ptr(flat)), "dstag_gather_flat")
+            else:                                  # CPU tensors (gloo tests of the bucket logic)
+                for g, off, sz in zip(srcs, offs, sizes):
+                    flat[off:off + sz].copy_(g.reshape(-1))
+        for p, v in zip(self._members[b], views):
             p.grad = v
 
-    def _launch(self, b):
-        self._attach(b, copy=True)
-        flat = self.buckets[b]
-        if self.average:
-            flat.mul_(1.0 / self.world)
-        self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+    def _reduce(self, b):
+        self._collect(b)
+        self._done[b] = True
+        if self.world > 1:
+            flat = self.buckets[b]
+            if self.average:
+                flat.mul_(1.0 / self.world)
+            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero(self):
-        """Start of a step: clear the flat buffers and (re-)attach the ``.grad`` views."""
-        for b, flat in self.buckets.items():
-            flat.zero_()
-            self._attach(b, copy=False)
-            self._pending[b] = len(self._members[b])
+        """Start of a step: drop the gradients (``.grad = None``: no kernel runs)."""
+        for b, ps in self._members.items():
+            for p in ps:
+                p.grad = None
+            self._pending[b] = len(ps)
+            self._done[b] = False
         self._works = []
 
     def finish(self):
-        """After ``loss.backward()``: make sure every bucket is averaged across ranks (and, also at
-        world size 1, that every gradient lives in its bucket again)."""
-        if self.world == 1:
-            for b in self.buckets:
-                self._attach(b, copy=True)
-            return
-        if not self.overlap:
-            for b in self.buckets:
-                self._launch(b)
-        else:
-            for b, n in self._pending.items():
-                if n > 0:          # a parameter got no gradient this step; reduce what there is
-                    self._launch(b)
-                    self._pending[b] = 0
+        """After ``loss.backward()``: every bucket collected (and averaged across ranks)."""
+        for b in self.buckets:
+            if not self._done[b]:
+                self._reduce(b)
         for w in self._works:
             w.wait()
         self._works = []
+        for b in self.buckets:
+            self._pending[b] = 0

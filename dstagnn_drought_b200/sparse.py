@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .contraction import _check, contract_raw
+from .contraction import _check, contract_raw, zeros
 
 SPARSE_MAX_DENSITY = 0.05
 SHORT_CHAIN = int(os.environ.get("DSTAG_SHORT_CHAIN", "64"))
@@ -164,7 +164,7 @@ class SparseChebConv(torch.autograd.Function):
                                          1.0 / math.sqrt(dk), st), "dstag_dqk_combine")
         dbias = None
         if ctx.needs_input_grad[1]:
-            dbias = torch.zeros((K, N, ld), device=dev, dtype=torch.float32)
+            dbias = zeros((K, N, ld), dev)
             npa = g["pa_j"].numel()
             if npa:
                 _lib.check(lib.dstag_dbias_sparse(P.data_ptr(), h.data_ptr(), r.data_ptr(), g["pa_j"].data_ptr(),

@@ -22,7 +22,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib, ops
-from .contraction import _check
+from .contraction import _check, arm_zero_arena, disarm_zero_arena
 from .parallel import GradBuckets
 
 
@@ -159,6 +159,9 @@ class TrainStep:
         dev = next(iter(self.buckets.buckets.values())).device
         self.counters = StepCounters(dev)
         self.opt = FlatAdam(net, self.buckets, lr, counters=self.counters)
+        # zero-initialised accumulators of the backward (bias / LayerNorm / table / mask-bias gradients) come out
+        # of one arena that is cleared once per step
+        self.arena = arm_zero_arena(dev, int(1.25 * self.buckets.numel) + (1 << 20))
         self.want_graph = graph and self.world == 1
         self.warmup = warmup
         self._graph = None
@@ -167,7 +170,12 @@ class TrainStep:
         self.kernels_per_replay = 0      # kernels of this library inside the captured graph
         self.replays = 0
 
+    def close(self):
+        self.counters.close()
+        disarm_zero_arena(self.counters.t.device)
+
     def _eager(self, x, y):
+        self.arena.reset()
         self.buckets.zero()
         loss = smooth_l1_loss(self.net(x), y)
         loss.backward()

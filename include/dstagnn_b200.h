@@ -258,6 +258,25 @@ int dstag_smooth_l1_bwd(const float* pred, const float* target, const float* gou
 int dstag_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                     float eps, float grad_scale, const uint64_t* step_dev, uint64_t step_host, void* stream);
 
+/* flat[offsets[t] + i] = srcs[t][i], i < sizes[t], for t < n: collects the step's parameter gradients (separate
+ * device tensors; srcs / offsets / sizes are HOST arrays, passed to the kernel by value) into the flat bucket that
+ * the gradient all-reduce (train_DSTAGNN_my.py:148,158) and dstag_adam_step consume. */
+int dstag_gather_flat(const float* const* srcs, const int64_t* offsets, const int64_t* sizes, int32_t n, float* flat,
+                      void* stream);
+
+/* n strided copies of <= 4-D fp32 blocks in one launch per 16 (element strides, may be negative: a flipped
+ * axis): the per-step re-layouts of small parameter tensors -- packed [W_Q | W_K | W_V] rows, stacked Theta_k, the
+ * GTU conv matrices and their flipped transposes (model/DSTAGNN_my.py:62-63, 92-94, 112-113, 190) -- and the
+ * un-packing of their gradients.  copies: HOST array (passed to the kernel by value). */
+typedef struct {
+  const void* src;
+  void* dst;
+  int32_t n[4];            /* extents, outermost first; unused leading extents = 1 */
+  int64_t src_stride[4];
+  int64_t dst_stride[4];
+} dstag_copy_t;
+int dstag_multi_copy(const dstag_copy_t* copies, int32_t n, void* stream);
+
 /* counters[i] += 1 for i < n (n <= 32): the device-resident step counters (dropout key, Adam step). */
 int dstag_tick(uint64_t* counters, int32_t n, void* stream);
 

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 12
+        return 14
 
     def dstag_last_error(self):
         return self.err
@@ -355,6 +355,26 @@ def _emu_optim(cls):
         P[:] = P - (lr / (1 - b1 ** t)) * mm / (np.sqrt(vv) / math.sqrt(1 - b2 ** t) + eps)
         return 0
 
+    def dstag_gather_flat(self, srcs, offsets, sizes, n, flat, stream):
+        self.launches += 1
+        for t in range(n):
+            sz = int(sizes[t])
+            _arr(int(flat) + 4 * int(offsets[t]), sz)[:] = _arr(int(srcs[t]), sz)
+        return 0
+
+    def dstag_multi_copy(self, copies, n, stream):
+        self.launches += 1
+        for t in range(n):
+            c = copies[t]
+            idx = np.indices(tuple(c.n)).reshape(4, -1).astype(np.int64)
+            so = sum(idx[k] * c.src_stride[k] for k in range(4))
+            do = sum(idx[k] * c.dst_stride[k] for k in range(4))
+            lo_s, lo_d = int(so.min()), int(do.min())
+            src = _arr(int(c.src) + 4 * lo_s, int(so.max()) - lo_s + 1)
+            dst = _arr(int(c.dst) + 4 * lo_d, int(do.max()) - lo_d + 1)
+            dst[do - lo_d] = src[so - lo_s]
+        return 0
+
     def dstag_tick(self, counters, n, stream):
         self.launches += 1
         np.ctypeslib.as_array((C.c_int64 * int(n)).from_address(int(counters)))[:] += 1
@@ -378,8 +398,8 @@ def _emu_optim(cls):
             out[k] = pa * d[k, :, :N].T
         return 0
 
-    for f in (dstag_smooth_l1_fwd, dstag_smooth_l1_bwd, dstag_adam_step, dstag_tick, dstag_bias_transpose,
-              dstag_bias_transpose_bwd):
+    for f in (dstag_smooth_l1_fwd, dstag_smooth_l1_bwd, dstag_adam_step, dstag_gather_flat, dstag_multi_copy, dstag_tick,
+              dstag_bias_transpose, dstag_bias_transpose_bwd):
         setattr(cls, f.__name__, f)
     return cls
 

@@ -110,7 +110,7 @@ def test_graph_captured_step_equals_eager_step_and_torch_adam():
             if mode == "graph":
                 assert ts.replays == 6 and ts.kernels_per_replay > 50
         finally:
-            ts.counters.close()
+            ts.close()
     net, x, y = _net(dev, dropout=False)
     opt = torch.optim.Adam(list(live_parameters(net).values()), lr=1e-3)
     ref = []
@@ -139,4 +139,4 @@ def test_graph_replays_draw_fresh_dropout_masks():
         ts.counters.t[0] -= 1                                            # rewind the dropout counter by one step
         assert float(ts.step(x, y)) == vals[-1]
     finally:
-        ts.counters.close()
+        ts.close()
