@@ -138,7 +138,7 @@ def _k_order(pl: Plan, A, B):
     return rev if score(rev) > score(fwd) else fwd
 
 
-_FP32_SPECS = [t for t in os.environ.get("DSTAG_FP32_SPECS", "").split(",") if t]
+_FP32_SPECS = [t for t in os.environ.get("DSTAG_FP32_SPECS", "").split(";") if t]
 _desc_cache = {}
 _swap_cache = {}
 _dims_cache = {}

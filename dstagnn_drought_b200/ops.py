@@ -654,11 +654,16 @@ class Head(torch.autograd.Function):
         X, T, Cc = xs[0].shape
         O = w_conv.shape[0]
         wv = w_conv.view(O, len(xs) * T, Cc)
-        h = torch.empty((X, O), device=xs[0].device, dtype=torch.float32)
+        # one partial product per block (each free to split its reduction: at T = 144 a chain of T*C = 4608
+        # terms in the tensor core's truncating accumulator cost 1e-4 of the downstream gradients), summed in a
+        # fixed order
+        parts = torch.empty((len(xs), X, O), device=xs[0].device, dtype=torch.float32)
         for i, x in enumerate(xs):
-            contract_raw("xtc,otc->xo", x, wv[:, i * T:(i + 1) * T], out=h,
-                         c_add=("o", b_conv) if i == 0 else None, accumulate=ACC_STORE if i == 0 else ACC_ADD,
-                         split_k=1)
+            contract_raw("xtc,otc->xo", x, wv[:, i * T:(i + 1) * T], out=parts[i],
+                         c_add=("o", b_conv) if i == 0 else None, reproducible=True)
+        h = torch.empty((X, O), device=xs[0].device, dtype=torch.float32)
+        _lib.check(_lib.load().dstag_sum_slices(parts.data_ptr(), parts.stride(0), len(xs), h.data_ptr(), X, O, O,
+                                                _stream(h)), "dstag_sum_slices")
         y = contract_raw("xo,po->xp", h, w_fc, c_add=("p", b_fc), reproducible=True)
         ctx.save_for_backward(w_conv, w_fc, h, *xs)
         return y

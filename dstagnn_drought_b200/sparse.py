@@ -24,6 +24,7 @@ from .contraction import _check, contract_raw, zeros
 
 SPARSE_MAX_DENSITY = 0.05
 SHORT_CHAIN = int(os.environ.get("DSTAG_SHORT_CHAIN", "64"))
+EXACT_BELOW = 128                # graphs up to this many nodes: P Qc and P^T (r K) on the exact fp32 engine
 
 
 def choose_path(cheb_polynomials: Sequence, d_k: int) -> str:
@@ -155,8 +156,11 @@ class SparseChebConv(torch.autograd.Function):
         # the only dense work of the backward: two N x N x d_k products with the (non-negative) softmax maps
         # (accumulated in chains of 64 terms: the tensor core's accumulator truncates, and the bias of a chain
         #  of N terms reached 1e-3 of the projection-bias gradients at N = 4096)
-        O = contract_raw("bkji,bikd->bjkd", Pv, Qc, tag="sat_PQ", chain=SHORT_CHAIN)     # (B, N, K, dk)
-        W = contract_raw("bkji,bjkd->bikd", Pv, rK, tag="sat_PtrK", chain=SHORT_CHAIN)   # (B, N, K, dk)
+        # Small graphs take the exact fp32 engine: the products are tiny there, and with one or two edges per row the
+        # edge half of the key gradient is exact while a 3xTF32 P Qc is not -- their difference showed at 1.2e-4.
+        prec = _lib.PREC_FP32 if N <= EXACT_BELOW else None
+        O = contract_raw("bkji,bikd->bjkd", Pv, Qc, tag="sat_PQ", chain=SHORT_CHAIN, precision=prec)     # (B, N, K, dk)
+        W = contract_raw("bkji,bjkd->bikd", Pv, rK, tag="sat_PtrK", chain=SHORT_CHAIN, precision=prec)   # (B, N, K, dk)
         dqk = torch.empty_like(qk)
         _lib.check(lib.dstag_dqk_combine(qk.data_ptr(), Qc.data_ptr(), h.data_ptr(), r.data_ptr(), O.data_ptr(), W.data_ptr(),
                                          g["rowptr"].data_ptr(), g["col"].data_ptr(), g["t_rowptr"].data_ptr(),
