@@ -219,7 +219,8 @@ class DSTAGNN_block(nn.Module):
         # 7. gated temporal convolutions                                             (lines 237-242)
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
                                  self.gtu5.con2out.weight, self.gtu5.con2out.bias,
-                                 self.gtu7.con2out.weight, self.gtu7.con2out.bias)       # (B*N, 3T-12, C)
+                                 self.gtu7.con2out.weight, self.gtu7.con2out.bias,
+                                 torch.is_grad_enabled())                               # (B*N, 3T-12, C)
         # 8-11. fcmy over the concatenated time axis, combine, residual, LayerNorm over channels
         #       (lines 243-252); one fused kernel for the PEMS shapes, GEMM + tail kernel otherwise
         lin = self.fcmy[0]

@@ -460,14 +460,37 @@ class GtuStack(torch.autograd.Function):
         return g.as_strided((X, T - ks + 1, ks * Cc), (T * Cc, Cc, 1))
 
     @staticmethod
-    def forward(ctx, g, w3, b3, w5, b5, w7, b7):
+    def _fused(lib, Cc, T, backward):
+        return os.environ.get("DSTAG_GTU", "fused") != "gemm" and all(
+            lib.dstag_gtu_tc_supported(Cc, T, ks, 1 if backward else 0) for ks in GtuStack.KS)
+
+    @staticmethod
+    def forward(ctx, g, w3, b3, w5, b5, w7, b7, *save):
+        # (save: optional flag, False when the caller runs under no_grad -- grad mode is not visible in here)
         lib = _lib.load()
         _check(g, "g")
+        ctx.extra = len(save)
         g = g.contiguous()
         X, T, Cc = g.shape
         widths = [T - ks + 1 for ks in GtuStack.KS]
         total = sum(widths)
         out = torch.empty((X, total, Cc), device=g.device, dtype=torch.float32)
+        need_bwd = any(ctx.needs_input_grad) and (not save or bool(save[0]))
+        ctx.fused = GtuStack._fused(lib, Cc, T, need_bwd)
+        if ctx.fused:
+            # one tcgen05 kernel per kernel size: convolution + bias + gate + concatenation; the conv output stays
+            # on chip and only the gate factors [tanh(p) | sigmoid(q)] are kept for the backward
+            svs, off = [], 0
+            for ks, w, b, tp in zip(GtuStack.KS, (w3, w5, w7), (b3, b5, b7), widths):
+                w, b = w.contiguous(), b.contiguous()
+                sv = torch.empty((X, tp, 2 * Cc), device=g.device, dtype=torch.float32) if need_bwd else None
+                _lib.check(lib.dstag_gtu_conv_gate_fwd(g.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), _p(sv),
+                                                       X, Cc, T, ks, total, off, _stream(g)), "dstag_gtu_conv_gate_fwd")
+                svs.append(sv)
+                off += tp
+            if need_bwd:
+                ctx.save_for_backward(g, w3, w5, w7, *svs)
+            return out
         # conv kernels (2C, C, 1, ks) -> K-contiguous GEMM operands (o, (d, c)): all three in one launch
         wks = [torch.empty((2 * Cc, ks, Cc), device=g.device, dtype=torch.float32) for ks in GtuStack.KS]
         multi_copy([(wk, w[:, :, 0, :].permute(0, 2, 1)) for wk, w in zip(wks, (w3, w5, w7))])
@@ -484,7 +507,37 @@ class GtuStack(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _backward_fused(ctx, dout):
+        lib = _lib.load()
+        g, w3, w5, w7, sv3, sv5, sv7 = ctx.saved_tensors
+        X, T, Cc = g.shape
+        dout = dout.contiguous()
+        total = dout.shape[1]
+        # (the kernel always produces the input gradient: it shares its pass over dcat with du)
+        dg = torch.empty_like(g)
+        dwks, grads, off = [], [], 0
+        with _lib.on_device(_stream(g)):
+            ws_rows = lib.dstag_gtu_bwd_ws_rows()
+        for i, (ks, w, sv) in enumerate(zip(GtuStack.KS, (w3, w5, w7), (sv3, sv5, sv7))):
+            tp = T - ks + 1
+            du = torch.empty((X, tp, 2 * Cc), device=g.device, dtype=torch.float32)
+            ws = zeros((ws_rows, 2 * Cc), g.device)          # per-warp partial column sums of du
+            _lib.check(lib.dstag_gtu_gate_conv_bwd(sv.data_ptr(), dout.data_ptr(), w.contiguous().data_ptr(), du.data_ptr(),
+                                                   dg.data_ptr(), ws.data_ptr(), X, Cc, T, ks, total, off,
+                                                   0 if i == 0 else 1, _stream(g)), "dstag_gtu_gate_conv_bwd")
+            db = colsum(ws, ws_rows, 2 * Cc)
+            dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
+            dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)
+            dwks.append((dw[:, :, 0, :], dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1)))     # (o, c, d) <- (o, d, c)
+            grads += [dw, db]
+            off += tp
+        multi_copy(dwks)
+        return (dg if ctx.needs_input_grad[0] else None, *grads, *([None] * ctx.extra))
+
+    @staticmethod
     def backward(ctx, dout):
+        if ctx.fused:
+            return GtuStack._backward_fused(ctx, dout)
         lib = _lib.load()
         g, w3, w5, w7, u3, u5, u7 = ctx.saved_tensors
         X, T, Cc = g.shape
@@ -520,7 +573,7 @@ class GtuStack(torch.autograd.Function):
             grads += [dw, db]
             off += tp
         multi_copy(dwks)
-        return (dg, *grads)
+        return (dg, *grads, *([None] * ctx.extra))
 
 
 # ----------------------------------------------------------------------------------------

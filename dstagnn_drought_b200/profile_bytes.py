@@ -35,6 +35,9 @@ ALGO_BYTES = {
     "dstag_tattn_bwd": lambda a: _tattn(a, True),
     "dstag_gtu_gate_fwd": lambda a: 4 * a[2] * a[4] * 3 * a[3],
     "dstag_gtu_gate_bwd": lambda a: 4 * a[4] * a[5] * (3 * a[6] + 2 * (a[6] + 2 * a[7])),
+    # fused GTU: g in, cat (+ saved gate factors) out; saved factors + dcat in, du + dg out
+    "dstag_gtu_conv_gate_fwd": lambda a: 4 * a[5] * a[6] * (a[7] + (a[7] - a[8] + 1) * (1 + (2 if a[4] else 0))),
+    "dstag_gtu_gate_conv_bwd": lambda a: 4 * a[6] * a[7] * ((a[8] - a[9] + 1) * 5 + a[8] * (2 if a[12] else 1)),
     "dstag_outer_sum": lambda a: 4 * a[4] * (a[5] + a[6]) * a[7],
     "dstag_tail_fwd": lambda a: 4 * a[9] * a[10] * a[11] * (3 + (1 if a[1] else 0)),
     "dstag_tail_bwd": lambda a: 4 * a[12] * a[13] * a[14] * (5 + (2 if a[2] else 0)),
@@ -55,6 +58,24 @@ ALGO_BYTES = {
     "dstag_dbias_sparse": lambda a: 4 * a[12] * a[8] * (a[7] + 1),
     "dstag_tick": lambda a: 16 * a[1],
 }
+
+
+# multiply-add = 2 flops; only the entry points that run on the tensor cores outside dstag_gemm
+ALGO_FLOPS = {
+    "dstag_gtu_conv_gate_fwd": lambda a: 2 * a[5] * (a[7] - a[8] + 1) * 2 * a[6] * a[8] * a[6],
+    "dstag_gtu_gate_conv_bwd": lambda a: 2 * a[6] * (a[8] - a[9] + 1) * 2 * a[7] * a[9] * a[7],
+}
+
+
+def algo_flops(name, args):
+    f = ALGO_FLOPS.get(name)
+    if f is None:
+        return 0
+    try:
+        vals = [(x.value if hasattr(x, "value") else x) for x in args]
+        return int(f([0 if v is None else v for v in vals]))
+    except Exception:
+        return 0
 
 
 def algo_bytes(name, args):

@@ -200,6 +200,27 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
 int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C,
                        int32_t Tp, int32_t pad, int32_t S, int32_t off, void* stream);
 
+/* Fused GTU kernels on the tcgen05 tensor cores (csrc/gtu_tc.cu), C = 32 channels, ks in {3, 5, 7}:
+ *   dstag_gtu_conv_gate_fwd: Conv2d(C -> 2C, (1, ks)) over time + bias + tanh * sigmoid gate + torch.cat
+ *     (model/DSTAGNN_my.py:192-196, 238-242) in one kernel.  g (X, T, C) channels-last, w (2C, C, 1, ks) and
+ *     bias (2C) as nn.Conv2d stores them; writes rows off .. off + T - ks of cat (X, S, C) and, when sv is not
+ *     NULL, sv (X, T - ks + 1, 2C) = [tanh(p) | sigmoid(q)] for the backward.  The conv output never reaches HBM.
+ *   dstag_gtu_gate_conv_bwd: autograd of the above w.r.t. g, plus the gradient of the conv output:
+ *     du (X, T - ks + 1, 2C) = gate'(sv) * dcat[:, off .., :] (the operand of the weight gradient; its column
+ *     sums -- partial sums per warp in db_ws, see below -- are the bias gradient) and dg (X, T, C) (+)= the transposed convolution of du with w (`accumulate`
+ *     != 0 adds to dg: the three kernel sizes share one input).  Deterministic (no atomics).
+ *   dstag_gtu_tc_supported(C, T, ks, backward) tells whether a shape is covered (T - ks + 1 <= 128 rows per
+ *     node in the backward); other shapes take dstag_gemm + the gate kernels above. */
+int dstag_gtu_tc_supported(int32_t C, int32_t T, int32_t ks, int32_t backward);
+int dstag_gtu_conv_gate_fwd(const float* g, const float* w, const float* bias, float* cat, float* sv, int64_t X,
+                            int32_t C, int32_t T, int32_t ks, int32_t S, int32_t off, void* stream);
+int dstag_gtu_gate_conv_bwd(const float* sv, const float* dcat, const float* w, float* du, float* dg, float* db_ws,
+                            int64_t X, int32_t C, int32_t T, int32_t ks, int32_t S, int32_t off, int32_t accumulate,
+                            void* stream);
+/* rows of the (rows, 2C) workspace db_ws (nullable; ZEROED by the caller): every producer warp of the kernel leaves
+ * its partial column sums of du there; their column sum (dstag_colsum) is the conv bias gradient */
+int dstag_gtu_bwd_ws_rows(void);
+
 /* out[m, n] += sum_x sum_c a[x, m, c] * b[x, n, c];  asum[m] += sum_x sum_c a[x, m, c] (nullable).
  * a (X, m, C), b (X, n, C) channels-last, 16-byte aligned; out / asum zeroed by the caller.
  * The fcmy weight and bias gradients (autograd of model/DSTAGNN_my.py:243): a T x (3T-12) result

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 14
+        return 15
 
     def dstag_last_error(self):
         return self.err
@@ -235,6 +235,45 @@ class FakeLib:
         U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
         O = _arr(out, X * S * Cc).reshape(X, S, Cc)                                   # channels-last
         O[:, off:off + Tp, :] = np.tanh(U[:, :, :Cc]) / (1 + np.exp(-U[:, :, Cc:]))
+        return 0
+
+    def dstag_gtu_tc_supported(self, Cc, T, ks, backward):
+        return int(Cc == 32 and ks in (3, 5, 7) and T >= ks and (not backward or T - ks + 1 <= 128))
+
+    def dstag_gtu_conv_gate_fwd(self, g, w, bias, cat, sv, X, Cc, T, ks, S, off, stream):
+        self.launches += 1
+        Tp = T - ks + 1
+        G = _arr(g, X * T * Cc).reshape(X, T, Cc).astype(np.float64)
+        W = _arr(w, 2 * Cc * Cc * ks).reshape(2 * Cc, Cc, ks).astype(np.float64)
+        win = np.stack([G[:, j:j + Tp, :] for j in range(ks)], 3)                         # (X, Tp, C, ks)
+        U = np.einsum("xtcj,ocj->xto", win, W) + _arr(bias, 2 * Cc).astype(np.float64)
+        th, sg = np.tanh(U[:, :, :Cc]), 1 / (1 + np.exp(-U[:, :, Cc:]))
+        _arr(cat, X * S * Cc).reshape(X, S, Cc)[:, off:off + Tp, :] = th * sg
+        if sv:
+            SV = _arr(sv, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc)
+            SV[:, :, :Cc], SV[:, :, Cc:] = th, sg
+        return 0
+
+    def dstag_gtu_bwd_ws_rows(self):
+        return 8
+
+    def dstag_gtu_gate_conv_bwd(self, sv, dcat, w, du, dg, db_ws, X, Cc, T, ks, S, off, accumulate, stream):
+        self.launches += 1
+        Tp = T - ks + 1
+        SV = _arr(sv, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
+        th, sg = SV[:, :, :Cc], SV[:, :, Cc:]
+        d = _arr(dcat, X * S * Cc).reshape(X, S, Cc)[:, off:off + Tp, :].astype(np.float64)
+        DU = np.concatenate([d * sg * (1 - th * th), d * th * sg * (1 - sg)], 2)          # (X, Tp, 2C)
+        _arr(du, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc)[:] = DU
+        if db_ws:
+            _arr(db_ws, 8 * 2 * Cc).reshape(8, 2 * Cc)[0] = DU.reshape(-1, 2 * Cc).sum(0)
+        W = _arr(w, 2 * Cc * Cc * ks).reshape(2 * Cc, Cc, ks).astype(np.float64)
+        Y = np.einsum("xto,ocj->xtjc", DU, W)
+        DG = np.zeros((X, T, Cc))
+        for j in range(ks):
+            DG[:, j:j + Tp, :] += Y[:, :, j, :]
+        out = _arr(dg, X * T * Cc).reshape(X, T, Cc)
+        out[:] = (out + DG) if accumulate else DG
         return 0
 
     def dstag_outer_sum_supported(self, m, n, Cc):

@@ -280,7 +280,8 @@ def test_sparse_cheb_conv_matches_dense_formula(dev, precision, cfg):
     assert float((gr[1][..., :N] * (1 - keep)).abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144)])
+@pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144), (1531, 32, 12), (40, 32, 7),
+                                 (9, 32, 130)])
 def test_gtu_stack(dev, precision, cfg):
     from dstagnn_drought_b200.ops import GtuStack
     X, Cc, T = cfg
@@ -304,6 +305,30 @@ def test_gtu_stack(dev, precision, cfg):
     assert rel_err(out, ref) < TOL
     for got, want in zip(gr, rr):
         assert rel_err(got, want) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [(257, 32, 12), (11, 32, 144)])
+def test_gtu_fused_forward_without_grad_matches_gemm_path(dev, cfg, monkeypatch):
+    """Inference (no saved gate factors; any T, also the T' > 128 rows per node of the drought configuration)
+    through the fused tcgen05 kernel against the contraction-engine + gate-kernel path."""
+    from dstagnn_drought_b200.ops import GtuStack
+    X, Cc, T = cfg
+    torch.manual_seed(18)
+    g = torch.randn(X, T, Cc, device=dev)
+    ws = [torch.randn(2 * Cc, Cc, 1, ks, device=dev) * 0.2 for ks in (3, 5, 7)]
+    bs = [torch.randn(2 * Cc, device=dev) for _ in range(3)]
+    args = [g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2]]
+    with torch.no_grad():
+        fused = GtuStack.apply(*args, False)
+        monkeypatch.setenv("DSTAG_GTU", "gemm")
+        plain = GtuStack.apply(*args, False)
+    xc = g.double().permute(2, 0, 1).unsqueeze(0)
+    outs = []
+    for w, b in zip(ws, bs):
+        u = torch.nn.functional.conv2d(xc, w.double(), b.double())
+        outs.append(torch.tanh(u[:, :Cc]) * torch.sigmoid(u[:, -Cc:]))
+    ref = torch.cat(outs, dim=-1)[0].permute(1, 2, 0)
+    assert rel_err(fused, ref) < TOL and rel_err(plain, ref) < TOL
 
 
 @pytest.mark.parametrize("cfg", [(3, 32, 12, True), (500, 32, 12, False), (37, 32, 12, True), (9, 32, 144, True),
