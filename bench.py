@@ -231,7 +231,7 @@ def needs_l2_flush(args, w):
 
 
 def workload_config(args, w, batch):
-    graphed = args.impl == "ours" and args.gpus <= 1 and not args.no_graph
+    graphed = args.impl == "ours" and not args.no_graph and (args.gpus <= 1 or os.environ.get("DSTAG_GRAPH_MULTI", "1") != "0")
     what = (f"train step (zero_grad+fwd+SmoothL1+bwd{'+allreduce' if args.gpus > 1 else ''}+Adam)"
             if args.mode == "train" else "inference (eval, no_grad forward)") + (", CUDA graph" if graphed else "")
     return {"workload": f"{args.workload}: N={w['N']} T={w['T']} K={w['K']} H={w['H']} d_model={w['D']} "
@@ -246,15 +246,30 @@ def workload_config(args, w, batch):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def ncu_traffic(w, args, B):
-    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/r01_ncu_cheb_final.md); only valid for the configuration it was taken on."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_cheb_traffic.json")
+def kernel_family(tag):
+    """Kernel FUNCTION behind a profiler tag: every contraction runs gemm_tc_kernel<> (gemm_simt_kernel<> below 2^19
+    MACs / K < 8); the other entry points are one kernel each."""
+    if tag.startswith("gemm:") or tag.startswith("cheb_") or tag.startswith("sat_P") or (tag.startswith("gtu") and "_" in tag) \
+            or tag in ("fcmy_dw",):
+        return "contraction engine: gemm_tc_kernel<> (tcgen05 / TMEM / TMA), all contractions of the step"
+    return {"dstag_gtu_conv_gate_fwd": "gtu_fwd_tc_kernel<> (fused GTU forward, tcgen05)",
+            "dstag_gtu_gate_conv_bwd": "gtu_bwd_tc_kernel<> (fused GTU backward, tcgen05)"}.get(tag, tag)
+
+
+def ncu_traffic(w, args, B, fam):
+    """DRAM bytes (read + write) per launch of the dominant kernel function, from the committed ncu capture of one
+    step (profiles/r02_ncu_traffic.json: {family: mean bytes per launch}); only valid for the configuration it was
+    taken on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_traffic.json")
     if (args.workload != "pems07" or args.precision != "tf32x3" or B != 64 or args.mode != "train"
             or not os.path.exists(path)):
         return None
     with open(path) as f:
-        return json.load(f)["mean_bytes_per_launch"]
+        d = json.load(f)
+    for key, v in d.items():
+        if key != "_meta" and key.split(":")[0] in fam:
+            return v
+    return None
 
 
 def run_ours(args, w):
@@ -271,6 +286,9 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not args.no_graph:
+            from dstagnn_drought_b200.step import multi_gpu_graph_env
+            multi_gpu_graph_env()
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     set_precision(args.precision)
@@ -284,7 +302,8 @@ def run_ours(args, w):
         net.train()
     else:
         net.eval()
-    use_graph = not args.no_graph and world == 1
+    # (multi-rank steps are captured too, NCCL all-reduces included, unless DSTAG_GRAPH_MULTI=0)
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("DSTAG_GRAPH_MULTI", "1") != "0")
 
     def barrier():
         if world > 1:
@@ -421,20 +440,42 @@ def run_ours(args, w):
 
         pk = peaks()
         gemm_ms = sum(v[1] for v in prof.values()) / prof_steps
-        cheb = {t: prof[t] for t in ("cheb_fwd", "cheb_bwd_dx", "cheb_bwd_dmap") if t in prof}
-        # dominant kernel family: the Chebyshev contraction (forward + its two backward products)
-        c_calls = sum(v[0] for v in cheb.values())
-        c_ms = sum(v[1] for v in cheb.values())
-        c_flops = sum(v[2] for v in cheb.values())
-        achieved = c_flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
-        roofline = {"bound": "tensor",
-                    "kernel": "Chebyshev contraction (" + " + ".join(sorted(cheb)) + ")",
-                    "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                    "peak_source": f"{pk['src']} dense bf16 (sustained); fp32-grade 3xTF32 issues 6 bf16-equivalent "
-                                   "MMA passes per algorithmic flop, so its ceiling is peak/6",
-                    "traffic": ncu_traffic(w, args, B), "launches_per_step": c_calls / prof_steps,
-                    "avg_launch_ms": c_ms / max(c_calls, 1), "share_of_step": (c_ms / prof_steps) / (ms / args.steps),
-                    "precision": args.precision}
+        # ---- roofline of the dominant kernel FUNCTION of this step (the one with the most device time) ----
+        fams = {}
+        for tag, v in prof.items():
+            fams.setdefault(kernel_family(tag), []).append(v)
+        fam, rows = max(fams.items(), key=lambda kv: sum(v[1] for v in kv[1]))
+        f_calls = sum(v[0] for v in rows)
+        f_ms = sum(v[1] for v in rows)
+        f_flops = sum(v[2] for v in rows)
+        f_bytes = sum(v[3] for v in rows)
+        # which roof binds: per launch group the larger of flops / tensor peak and bytes / HBM peak
+        t_tensor = sum(v[2] / (pk["tensor"] * 1e12) for v in rows)
+        t_hbm = sum(v[3] / (pk["hbm"] * 1e9) for v in rows)
+        floor_ms = 1e3 * sum(max(v[2] / (pk["tensor"] * 1e12), v[3] / (pk["hbm"] * 1e9)) for v in rows)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        if bound == "tensor":
+            achieved, peak, unit = f_flops / (f_ms * 1e-3) / 1e12, pk["tensor"], "TFLOP/s"
+            src = (f"{pk['src']} dense bf16 (sustained); the path computes fp32-grade 3xTF32 products: 3 TF32 MMAs (each at half "
+                   "the bf16 rate) per algorithmic flop, so its ceiling is peak/6 -- cuBLAS TF32 measured at "
+                   "740 TFLOP/s on this pool (profiles/r02_tf32_peak.json) puts that ceiling at 247 TFLOP/s")
+        else:
+            achieved, peak, unit = f_bytes / (f_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+            src = f"{pk['src']} HBM copy bandwidth (MEASURED_PEAKS.json)"
+        roofline = {"bound": bound, "kernel": fam, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "peak_source": src, "traffic": ncu_traffic(w, args, B, fam),
+                    "launches_per_step": f_calls / prof_steps, "avg_launch_ms": f_ms / max(f_calls, 1),
+                    "share_of_step": (f_ms / prof_steps) / (ms / args.steps), "precision": args.precision,
+                    "algorithmic_gflop_per_step": f_flops / prof_steps / 1e9,
+                    "algorithmic_gb_per_step": f_bytes / prof_steps / 1e9,
+                    # both roofs together: sum over the family's launches of max(flops / tensor peak, bytes / HBM peak)
+                    "mixed_floor_ms_per_step": floor_ms / prof_steps,
+                    "mixed_frac": floor_ms / f_ms if f_ms > 0 else 0.0}
+        # step roofline = sum over ALL kernels of max(flops_k / tensor peak, bytes_k / HBM peak) / step time
+        step_floor = 1e3 * sum(max(v[2] / (pk["tensor"] * 1e12), v[3] / (pk["hbm"] * 1e9)) for v in prof.values()) / prof_steps
+        step_roofline = {"floor_ms": step_floor, "frac": step_floor / (ms / args.steps),
+                         "tflops_per_step": sum(v[2] for v in prof.values()) / prof_steps / 1e12,
+                         "gb_per_step": sum(v[3] for v in prof.values()) / prof_steps / 1e9}
         breakdown = {t: {"calls_per_step": v[0] / prof_steps, "ms_per_step": round(v[1] / prof_steps, 4),
                          "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 2),
                          "gbs": round(v[3] / max(v[1], 1e-9) / 1e6, 1)} for t, v in
@@ -454,7 +495,8 @@ def run_ours(args, w):
                 "config": workload_config(args, w, B),
                 "e2e": {"value": B * n * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
+                "cpu_baseline": cpu,
                 "precision": args.precision, "final_loss" if train else "mean_abs_prediction": final,
                 "kernel_ms_per_step_profiled": round(gemm_ms, 3)}
         print(json.dumps(line), flush=True)
@@ -472,7 +514,8 @@ def run_ours(args, w):
     for i, B in enumerate(batches):
         measure(B, with_cpu=(i == 0))
     if world > 1:
-        dist.destroy_process_group()
+        from dstagnn_drought_b200.step import shutdown_process_group
+        shutdown_process_group(graphs_captured=use_graph)
 
 
 def main():

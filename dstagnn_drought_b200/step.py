@@ -17,6 +17,7 @@ never receive a gradient in the reference either, so Adam never touches them the
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -28,6 +29,31 @@ from .parallel import GradBuckets
 
 def _st(t):
     return _lib.stream_ptr(t)
+
+
+def shutdown_process_group(graphs_captured: bool):
+    """End of a multi-rank run.  A process that captured NCCL collectives in CUDA graphs must not go through
+    ``destroy_process_group`` / interpreter teardown (observed on B200, torch 2.11 + NCCL 2.28: the communicator
+    abort waits forever on work that only exists inside the graphs): synchronise, barrier, flush and leave."""
+    import sys
+
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if graphs_captured:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    dist.destroy_process_group()
+
+
+def multi_gpu_graph_env():
+    """Call BEFORE ``init_process_group`` when multi-rank training steps are to be captured in CUDA graphs."""
+    if os.environ.get("DSTAG_GRAPH_MULTI", "1") != "0":
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -145,8 +171,11 @@ class TrainStep:
     """``step(x, y) -> loss`` (a 0-d device tensor): zero-grad, forward, SmoothL1, backward, gradient
     averaging across ranks, Adam -- train_DSTAGNN_my.py:154-158 -- with every kernel of this library.
 
-    ``graph=True`` captures the step in a CUDA graph after ``warmup`` eager steps (single-GPU only: the
-    bucketed NCCL all-reduce is launched from autograd hooks and is kept eager).  A captured step reads its
+    ``graph=True`` captures the step in a CUDA graph after ``warmup`` eager steps.  With more than one rank the
+    bucketed NCCL all-reduces (launched from the autograd hooks, on NCCL's own stream) are captured with it --
+    NCCL >= 2.9.6 supports stream capture; the process group must be created with
+    ``TORCH_NCCL_ASYNC_ERROR_HANDLING=0`` (the watchdog's event queries are illegal during a capture), which
+    ``multi_gpu_graph_env()`` sets; ``DSTAG_GRAPH_MULTI=0`` keeps multi-rank steps eager.  A captured step reads its
     batch from static buffers: ``step`` copies the caller's tensors into them (device-to-device, or
     host-to-device from pinned memory) before the replay."""
 
@@ -162,7 +191,7 @@ class TrainStep:
         # zero-initialised accumulators of the backward (bias / LayerNorm / table / mask-bias gradients) come out
         # of one arena that is cleared once per step
         self.arena = arm_zero_arena(dev, int(1.25 * self.buckets.numel) + (1 << 20))
-        self.want_graph = graph and self.world == 1
+        self.want_graph = graph and (self.world == 1 or os.environ.get("DSTAG_GRAPH_MULTI", "1") != "0")
         self.warmup = warmup
         self._graph = None
         self._seen = 0

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import argparse
 import configparser
+import json
 import os
 import random
 import sys
@@ -317,6 +318,8 @@ def main(argv=None):
     device = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        from .step import multi_gpu_graph_env
+        multi_gpu_graph_env()                  # the captured step contains the NCCL all-reduces
         dist.init_process_group("nccl", device_id=device)
     if (args.config is None) == (args.dataset is None):
         raise SystemExit("give exactly one of --config FILE or --dataset NAME")
@@ -337,7 +340,10 @@ def main(argv=None):
     summary = fit(cfg, device, args.out, args.epochs, args.max_batches, rank, world, precision=args.precision,
                   cuda_graph=not args.no_cuda_graph)
     if world > 1:
-        dist.destroy_process_group()
+        from .step import shutdown_process_group
+        if rank == 0:
+            print(json.dumps({k: v for k, v in summary.items() if isinstance(v, (int, float, str))}), flush=True)
+        shutdown_process_group(graphs_captured=not args.no_cuda_graph)
     return summary
 
 
