@@ -604,6 +604,32 @@ def reduce_to(sub_out: str, grad: torch.Tensor, sub_keep: str) -> torch.Tensor:
     return red
 
 
+def _gram_weight_grad(spec, A, dC, B, am, alpha):
+    """Weight gradients whose reduction runs over the rows of two row-contiguous activations take the tall-skinny
+    Gram kernel (csrc/gram_tc.cu) instead of a split-K contraction.  Today: the Theta mix of cheb_conv_withSAt,
+    dTheta[k, f, c] = sum_{x,t} Z[k, x, t, f] dG[x, t, c] (model/DSTAGNN_my.py:131) with 32 features and channels.
+    Returns None when the shape is not covered."""
+    if spec != "kxtf,kfc->xtc" or am is not None or alpha != 1.0 or os.environ.get("DSTAG_GRAM", "1") == "0":
+        return None
+    if get_precision() == "fp32" or not (A.is_contiguous() and dC.is_contiguous()):
+        return None
+    K, X, T, Fin = A.shape
+    Cc = dC.shape[-1]
+    lib = _lib.load()
+    if Fin != 32 or Cc != 32 or K * Fin > 128 or X * T * 32 >= 2 ** 31 - 64 or not lib.dstag_gram_supported(K, Cc):
+        return None
+    st = _lib.stream_ptr(A)
+    with _lib.on_device(st):
+        slices = lib.dstag_gram_slices()
+    part = torch.empty((slices, 128, Cc), device=A.device, dtype=torch.float32)
+    _lib.check(lib.dstag_gram_rows(A.data_ptr(), dC.data_ptr(), part.data_ptr(), X * T, 1, 1, K, X * T * Fin, Cc, st),
+               "dstag_gram_rows")
+    dt = torch.empty((128, Cc), device=A.device, dtype=torch.float32)
+    _lib.check(lib.dstag_sum_slices(part.data_ptr(), part.stride(0), slices, dt.data_ptr(), 128, Cc, Cc, st),
+               "dstag_sum_slices")
+    return dt[:K * Fin].view(K, Fin, Cc)
+
+
 class _Contract(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, cadd, amul, spec, cadd_sub, amul_sub, alpha, relu, pad_rows):
@@ -632,8 +658,10 @@ class _Contract(torch.autograd.Function):
             dA = empty_like_rows(A)        # gradients keep the (row-padded) layout of their tensors
             contract_raw(f"{pl.c},{pl.b}->{pl.a}", dC, B, out=dA, c_mul=am, alpha=ctx.alpha)
         if ctx.needs_input_grad[1]:
-            dB = empty_like_rows(B)
-            contract_raw(f"{pl.a},{pl.c}->{pl.b}", A, dC, out=dB, a_mul=am, alpha=ctx.alpha)
+            dB = _gram_weight_grad(ctx.spec, A, dC, B, am, ctx.alpha)
+            if dB is None:
+                dB = empty_like_rows(B)
+                contract_raw(f"{pl.a},{pl.c}->{pl.b}", A, dC, out=dB, a_mul=am, alpha=ctx.alpha)
         if ctx.has_cadd and ctx.needs_input_grad[2]:
             dadd = reduce_to(pl.c, dC.contiguous(), ctx.cadd_sub)
         return dA, dB, dadd, None, None, None, None, None, None, None

@@ -461,7 +461,8 @@ class GtuStack(torch.autograd.Function):
 
     @staticmethod
     def _fused(lib, Cc, T, backward):
-        return os.environ.get("DSTAG_GTU", "fused") != "gemm" and all(
+        from .contraction import get_precision
+        return os.environ.get("DSTAG_GTU", "fused") != "gemm" and get_precision() != "fp32" and all(
             lib.dstag_gtu_tc_supported(Cc, T, ks, 1 if backward else 0) for ks in GtuStack.KS)
 
     @staticmethod
@@ -518,6 +519,7 @@ class GtuStack(torch.autograd.Function):
         dwks, grads, off = [], [], 0
         with _lib.on_device(_stream(g)):
             ws_rows = lib.dstag_gtu_bwd_ws_rows()
+            gram = lib.dstag_gram_slices() if (os.environ.get("DSTAG_GRAM", "1") != "0" and Cc == 32) else 0
         for i, (ks, w, sv) in enumerate(zip(GtuStack.KS, (w3, w5, w7), (sv3, sv5, sv7))):
             tp = T - ks + 1
             du = torch.empty((X, tp, 2 * Cc), device=g.device, dtype=torch.float32)
@@ -526,9 +528,21 @@ class GtuStack(torch.autograd.Function):
                                                    dg.data_ptr(), ws.data_ptr(), X, Cc, T, ks, total, off,
                                                    0 if i == 0 else 1, _stream(g)), "dstag_gtu_gate_conv_bwd")
             db = colsum(ws, ws_rows, 2 * Cc)
-            dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
             dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)
-            dwks.append((dw[:, :, 0, :], dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1)))     # (o, c, d) <- (o, d, c)
+            if gram:
+                # dW[o, c, 0, j] = sum_{x,t'} du[(x,t'), o] g[x, t'+j, c]: the tall-skinny Gram kernel (one partial per
+                # CTA, added in a fixed order)
+                mrows = 128 * ((ks + 3) // 4)
+                part = torch.empty((gram, mrows, 2 * Cc), device=g.device, dtype=torch.float32)
+                _lib.check(lib.dstag_gram_rows(g.data_ptr(), du.data_ptr(), part.data_ptr(), X, T, tp, ks, Cc, 2 * Cc,
+                                               _stream(g)), "dstag_gram_rows")
+                dt = torch.empty((mrows, 2 * Cc), device=g.device, dtype=torch.float32)
+                _lib.check(lib.dstag_sum_slices(part.data_ptr(), part.stride(0), gram, dt.data_ptr(), mrows, 2 * Cc, 2 * Cc,
+                                                _stream(g)), "dstag_sum_slices")
+                dwks.append((dw[:, :, 0, :], dt.view(mrows // Cc, Cc, 2 * Cc)[:ks].permute(2, 1, 0)))   # (o, c, j) <- ((j, c), o)
+            else:
+                dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
+                dwks.append((dw[:, :, 0, :], dwk.view(2 * Cc, ks, Cc).permute(0, 2, 1)))     # (o, c, d) <- (o, d, c)
             grads += [dw, db]
             off += tp
         multi_copy(dwks)

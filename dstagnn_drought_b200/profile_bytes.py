@@ -38,6 +38,7 @@ ALGO_BYTES = {
     # fused GTU: g in, cat (+ saved gate factors) out; saved factors + dcat in, du + dg out
     "dstag_gtu_conv_gate_fwd": lambda a: 4 * a[5] * a[6] * (a[7] + (a[7] - a[8] + 1) * (1 + (2 if a[4] else 0))),
     "dstag_gtu_gate_conv_bwd": lambda a: 4 * a[6] * a[7] * ((a[8] - a[9] + 1) * 5 + a[8] * (2 if a[12] else 1)),
+    "dstag_gram_rows": lambda a: 4 * a[3] * (a[4] * 32 + a[5] * a[8]),
     "dstag_outer_sum": lambda a: 4 * a[4] * (a[5] + a[6]) * a[7],
     "dstag_tail_fwd": lambda a: 4 * a[9] * a[10] * a[11] * (3 + (1 if a[1] else 0)),
     "dstag_tail_bwd": lambda a: 4 * a[12] * a[13] * a[14] * (5 + (2 if a[2] else 0)),
@@ -62,6 +63,7 @@ ALGO_BYTES = {
 
 # multiply-add = 2 flops; only the entry points that run on the tensor cores outside dstag_gemm
 ALGO_FLOPS = {
+    "dstag_gram_rows": lambda a: 2 * a[3] * a[5] * a[6] * 32 * a[8],
     "dstag_gtu_conv_gate_fwd": lambda a: 2 * a[5] * (a[7] - a[8] + 1) * 2 * a[6] * a[8] * a[6],
     "dstag_gtu_gate_conv_bwd": lambda a: 2 * a[6] * (a[8] - a[9] + 1) * 2 * a[7] * a[9] * a[7],
 }

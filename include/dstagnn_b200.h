@@ -221,6 +221,18 @@ int dstag_gtu_gate_conv_bwd(const float* sv, const float* dcat, const float* w, 
  * its partial column sums of du there; their column sum (dstag_colsum) is the conv bias gradient */
 int dstag_gtu_bwd_ws_rows(void);
 
+/* Tall-skinny Gram product on the tcgen05 tensor cores (csrc/gram_tc.cu) -- the weight-gradient shapes:
+ *   D[(j, c), n] = sum_r A_j[r, c] * B[r, n],   j < taps <= 8, c < 32, n < NB in {32, 64}, r < X * Tp,
+ *   A_j[r, :] = the 32 floats at  a + ((r / Tp) * T + r % Tp) * 32 + j * tap_stride,   B (X * Tp, NB) contiguous.
+ * GTU conv weight gradient (autograd of model/DSTAGNN_my.py:193): a = g (X, T, 32), tap_stride = 32 (the next time
+ * step), b = du (X, Tp, 64), D[(j, c), o] = dW[o, c, 0, j].
+ * Every CTA (dstag_gram_slices() of them) writes ONE partial result: partial (slices, 128 * ceil(taps / 4), NB); the
+ * caller adds them in a fixed order with dstag_sum_slices (rows (j, c) with j >= taps are zero). */
+int dstag_gram_slices(void);
+int dstag_gram_supported(int32_t taps, int32_t NB);
+int dstag_gram_rows(const float* a, const float* b, float* partial, int64_t X, int32_t T, int32_t Tp, int32_t taps,
+                    int64_t tap_stride, int32_t NB, void* stream);
+
 /* out[m, n] += sum_x sum_c a[x, m, c] * b[x, n, c];  asum[m] += sum_x sum_c a[x, m, c] (nullable).
  * a (X, m, C), b (X, n, C) channels-last, 16-byte aligned; out / asum zeroed by the caller.
  * The fcmy weight and bias gradients (autograd of model/DSTAGNN_my.py:243): a T x (3T-12) result

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 15
+        return 16
 
     def dstag_last_error(self):
         return self.err
@@ -252,6 +252,26 @@ class FakeLib:
         if sv:
             SV = _arr(sv, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc)
             SV[:, :, :Cc], SV[:, :, Cc:] = th, sg
+        return 0
+
+    def dstag_gram_slices(self):
+        return 3
+
+    def dstag_gram_supported(self, taps, NB):
+        return int(1 <= taps <= 8 and NB in (32, 64))
+
+    def dstag_gram_rows(self, a, b, partial, X, T, Tp, taps, tap_stride, NB, stream):
+        self.launches += 1
+        MT = 1 if taps <= 4 else 2
+        Bm = _arr(b, X * Tp * NB).reshape(X * Tp, NB).astype(np.float64)
+        P = _arr(partial, 3 * MT * 128 * NB).reshape(3, MT * 128, NB)
+        P[:] = 0
+        rows = (np.arange(X)[:, None] * T + np.arange(Tp)[None, :]).reshape(-1)
+        span = int(rows.max()) * 32 + (taps - 1) * tap_stride + 32
+        A = _arr(a, span).astype(np.float64)
+        for j in range(taps):
+            Aj = A[(rows[:, None] * 32 + j * tap_stride + np.arange(32)[None, :])]          # (R, 32)
+            P[1, 32 * j:32 * j + 32, :] = Aj.T @ Bm
         return 0
 
     def dstag_gtu_bwd_ws_rows(self):
