@@ -420,6 +420,31 @@ sat_softmax_mma_kernel(const float* __restrict__ qk, const float* __restrict__ b
   }
   cp_async_wait<0>();
   __syncthreads();
+  if (TP == nullptr) {
+    // P only (the sparse Chebyshev path): the strip's 16 rows are assembled in the row buffer (free since the bias
+    // rows were consumed) and leave as ONE bulk copy per row (cp.async.bulk shared -> global): the fragment layout
+    // gives a store instruction eight 32-byte sectors of eight different rows, which kept the LSU pipe at 72 %
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 s0 = *reinterpret_cast<const float4*>(&red[1][g + 8 * h][0]);
+      const float4 s1 = *reinterpret_cast<const float4*>(&red[1][g + 8 * h][4]);
+      const float inv = 1.f / (((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w)));
+      float* srow = rows_s + (g + 8 * h) * PITCH + cw;
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (cw + 64 * t < ld) *reinterpret_cast<float2*>(srow + 64 * t) = make_float2(acc[t][2 * h] * inv, acc[t][2 * h + 1] * inv);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk copy
+    __syncthreads();
+    if (tid < kSatMmaRows && j0 + tid < N) {
+      float* dst = P + (((long long)b * K + k) * N + j0 + tid) * ld;
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows_s + tid * PITCH);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(ld * 4) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the CTA's shared memory must outlive the read
+    }
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j = j0 + g + 8 * h;

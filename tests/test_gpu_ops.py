@@ -307,6 +307,48 @@ def test_gtu_stack(dev, precision, cfg):
         assert rel_err(got, want) < 5e-5
 
 
+@pytest.mark.parametrize("cfg", [
+    # (X, T, Tp, taps, planes, NB): GTU conv weight gradients (taps = consecutive time steps) ...
+    (5, 12, 10, 3, False, 64), (301, 12, 8, 5, False, 64), (1531, 12, 6, 7, False, 64), (77, 20, 14, 7, False, 64),
+    (40, 7, 1, 7, False, 64), (3, 12, 10, 3, False, 32),
+    # ... and the Theta gradient (every tap a plane of its own, identity rows)
+    (5000, 1, 1, 3, True, 32), (37, 1, 1, 2, True, 32), (129, 1, 1, 8, True, 64)])
+def test_gram_rows_kernel(dev, cfg):
+    """csrc/gram_tc.cu through the C ABI: D[(j, c), n] = sum_r A_j[r, c] B[r, n] against fp64, ragged row counts,
+    both tap layouts, one and two M tiles; the per-CTA partials are added by dstag_sum_slices."""
+    from dstagnn_drought_b200 import _lib
+    lib = _lib.load()
+    X, T, Tp, taps, planes, NB = cfg
+    torch.manual_seed(21)
+    R = X * Tp
+    if planes:
+        a = torch.randn(taps, R, 32, device=dev)
+        tap_stride = R * 32
+        Aj = [a[j].double() for j in range(taps)]
+    else:
+        a = torch.randn(X, T, 32, device=dev)
+        tap_stride = 32
+        Aj = [a[:, j:j + Tp, :].reshape(R, 32).double() for j in range(taps)]
+    b = torch.randn(R, NB, device=dev)
+    slices = lib.dstag_gram_slices()
+    mrows = 128 * ((taps + 3) // 4)
+    part = torch.full((slices, mrows, NB), float("nan"), device=dev)
+    st = _lib.stream_ptr(a)
+    _lib.check(lib.dstag_gram_rows(a.data_ptr(), b.data_ptr(), part.data_ptr(), X, T, Tp, taps, tap_stride, NB, st),
+               "dstag_gram_rows")
+    out = torch.empty((mrows, NB), device=dev)
+    _lib.check(lib.dstag_sum_slices(part.data_ptr(), part.stride(0), slices, out.data_ptr(), mrows, NB, NB, st),
+               "dstag_sum_slices")
+    ref = torch.cat([A.t() @ b.double() for A in Aj], 0)                          # ((j, c), n)
+    assert rel_err(out[:taps * 32], ref) < 2e-5
+    assert float(out[taps * 32:].abs().max() if taps * 32 < mrows else 0.0) == 0.0   # rows of absent taps are zero
+    # run-to-run reproducible
+    part2 = torch.empty_like(part)
+    _lib.check(lib.dstag_gram_rows(a.data_ptr(), b.data_ptr(), part2.data_ptr(), X, T, Tp, taps, tap_stride, NB, st),
+               "dstag_gram_rows")
+    assert torch.equal(part, part2)
+
+
 @pytest.mark.parametrize("cfg", [(257, 32, 12), (11, 32, 144)])
 def test_gtu_fused_forward_without_grad_matches_gemm_path(dev, cfg, monkeypatch):
     """Inference (no saved gate factors; any T, also the T' > 128 rows per node of the drought configuration)
