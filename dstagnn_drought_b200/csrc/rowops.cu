@@ -306,8 +306,10 @@ __device__ __forceinline__ void ld4_guard(float (&o)[4], const float* __restrict
   for (int j = 0; j < 4; ++j) o[j] = (c + j < L) ? __ldg(p + c + j) : 0.f;
 }
 
+// gamma / beta sit in shared memory, not in registers: with them the NV = 7 instantiation (rows of 883 nodes) held
+// 202 registers, one 8-warp CTA per SM was resident (12 % of the warp slots) and the kernel ran at 1.8 TB/s
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 4 ? 4 : 3)
 ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __restrict__ tab, int tab_mod,
                    long long tab_ld, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ y, long long y_ld, float* __restrict__ mean, float* __restrict__ rstd, int rows,
@@ -317,12 +319,12 @@ ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __r
   const int nw = gridDim.x * (blockDim.x >> 5);
   const float invL = 1.f / (float)L;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float gm[NV][4], bt[NV][4];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    ld4_guard(gm[i], gamma, 4 * (lane + 32 * i), L);
-    ld4_guard(bt[i], beta, 4 * (lane + 32 * i), L);
+  __shared__ __align__(16) float gs[128 * NV], bs[128 * NV];
+  for (int c = threadIdx.x; c < 128 * NV; c += blockDim.x) {
+    gs[c] = c < L ? __ldg(gamma + c) : 0.f;
+    bs[c] = c < L ? __ldg(beta + c) : 0.f;
   }
+  __syncthreads();
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
     const float* ap = a + (long long)r * a_ld;
     const float* tp = tab ? tab + (long long)(r % tab_mod) * tab_ld : nullptr;
@@ -369,8 +371,10 @@ ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __r
             for (int j = 0; j < 4; ++j) dm[j] = dropout_scale(e0 + j, seed, drop_p, inv_keep);
           }
         }
+        const float4 g4 = *reinterpret_cast<const float4*>(gs + c), b4 = *reinterpret_cast<const float4*>(bs + c);
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaf((v[i][j] - mu) * rs, gm[i][j], bt[i][j]) * dm[j];
+        for (int j = 0; j < 4; ++j) o[j] = fmaf((v[i][j] - mu) * rs, gm[j], bt[j]) * dm[j];
         *reinterpret_cast<float4*>(yp + c) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -382,27 +386,28 @@ ln_fwd_warp_kernel(const float* __restrict__ a, long long a_ld, const float* __r
 // NV = 4), and 4-warp CTAs pack 3 per SM (12 warps) where 8-warp CTAs fit once.
 constexpr int kLnBwdThreads = 128;
 template <int NV>
-__global__ void __launch_bounds__(kLnBwdThreads, NV <= 4 ? 3 : 2)
+__global__ void __launch_bounds__(kLnBwdThreads, NV <= 4 ? 4 : 3)
 ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ a, long long a_ld,
                    const float* __restrict__ tab, int tab_mod, long long tab_ld, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dpre,
                    long long dpre_ld, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int L,
                    float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
   seed = fold_seed(seed, seed_dev);
-  extern __shared__ float sm[];          // [2][128 * NV] CTA-level d gamma / d beta accumulators
+  extern __shared__ __align__(16) float sm[];   // [3][128 * NV]: CTA-level d gamma / d beta accumulators, gamma
   constexpr int W = 128 * NV;
   float* sg = sm;
   float* sb = sm + W;
+  float* gs = sm + 2 * W;
   for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) sm[c] = 0.f;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) gs[c] = c < L ? __ldg(gamma + c) : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (blockDim.x >> 5);
   const float invL = 1.f / (float)L;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float gm[NV][4], ag[NV][4], ab[NV][4];
+  float ag[NV][4], ab[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    ld4_guard(gm[i], gamma, 4 * (lane + 32 * i), L);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
   }
@@ -427,6 +432,8 @@ ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* _
       }
       const float xv[4] = {x.x, x.y, x.z, x.w};
       const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float4 g4 = *reinterpret_cast<const float4*>(gs + c);
+      const float gmv[4] = {g4.x, g4.y, g4.z, g4.w};
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop_p > 0.f && c < L) {
         const unsigned long long e0 = (unsigned long long)r * L + c;
@@ -442,7 +449,7 @@ ln_bwd_warp_kernel(const float* __restrict__ dy, long long dy_ld, const float* _
         const bool ok = c + j < L;
         const float d = ok ? dv[j] * dm[j] : 0.f;
         const float xn = ok ? (xv[j] - mu) * rs : 0.f;
-        const float g = d * gm[i][j];
+        const float g = d * gmv[j];
         xh[i][j] = xn;
         gg[i][j] = g;
         ag[i][j] = fmaf(d, xn, ag[i][j]);
@@ -607,9 +614,9 @@ int dstag_layernorm_bwd(const float* dy, int64_t dy_ld, const float* a, int64_t 
   if (al && nv <= 8) {
     const int wpc = kLnBwdThreads / 32;
     const int blocks = (rows + wpc - 1) / wpc;
-    const int resident = kNumSMs * (nv <= 4 ? 3 : 2);
+    const int resident = kNumSMs * (nv <= 4 ? 4 : 3);
     const int grid = blocks < resident ? blocks : resident;
-    const size_t sm_bytes = (size_t)2 * 128 * nv * sizeof(float);
+    const size_t sm_bytes = (size_t)3 * 128 * nv * sizeof(float);
 #define DSTAG_LN_BWD(NV_)                                                                                        \
   case NV_:                                                                                                      \
     ln_bwd_warp_kernel<NV_><<<grid, kLnBwdThreads, sm_bytes, (cudaStream_t)stream>>>(                                      \
