@@ -284,6 +284,37 @@ sum_slices_kernel(const float* __restrict__ ws, long long slice_stride, int nsli
   }
 }
 
+// Small results with many slices (a 128 x 32 Gram result summed over 148 per-CTA partials, a weight gradient over 64
+// batch slices): one thread per output walked the slices one dependent-latency step at a time on a handful of CTAs
+// (25-33 us for a few MB).  Here 8 lanes share one float4 of the result: lane u adds the slices u, u + 8, ... in
+// ascending order and the 8 partial sums are combined by a fixed xor tree -- still a run-to-run reproducible order.
+__global__ void __launch_bounds__(256)
+sum_slices_par_kernel(const float* __restrict__ ws, long long slice_stride, int nslices, float* __restrict__ out,
+                      long long rows, long long cols, long long out_ld) {
+  const long long c4 = cols >> 2, n4 = rows * c4;
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);          // the 8 lanes of this group (groups may leave the loop apart)
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n4; i += stride) {
+    const long long r = i / c4, c = (i - r * c4) << 2;
+    const float* src = ws + r * cols + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = sub; s < nslices; s += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * slice_stride));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      a.x += __shfl_xor_sync(gmask, a.x, o);
+      a.y += __shfl_xor_sync(gmask, a.y, o);
+      a.z += __shfl_xor_sync(gmask, a.z, o);
+      a.w += __shfl_xor_sync(gmask, a.w, o);
+    }
+    if (sub == 0) *reinterpret_cast<float4*>(out + r * out_ld + c) = a;
+  }
+}
+
 __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                 float* __restrict__ dx, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -648,7 +679,11 @@ int dstag_sum_slices(const float* ws, int64_t slice_stride, int32_t nslices, flo
   const long long n = vec ? rows * (cols / 4) : rows * cols;
   long long blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  if (vec)
+  if (vec && nslices >= 16 && n * 8 <= (long long)kNumSMs * 8 * 256 * 4) {
+    long long pb = (n * 8 + 255) / 256;
+    if (pb > kNumSMs * 8) pb = kNumSMs * 8;
+    sum_slices_par_kernel<<<(unsigned)pb, 256, 0, (cudaStream_t)stream>>>(ws, slice_stride, nslices, out, rows, cols, out_ld);
+  } else if (vec)
     sum_slices_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ws, slice_stride, nslices, out, rows, cols, out_ld);
   else
     sum_slices_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ws, slice_stride, nslices, out, rows, cols, out_ld);
