@@ -134,7 +134,7 @@ spmm_reduce_kernel(const float* __restrict__ src, const float* __restrict__ a, c
 // warp per (b, j) looping over the orders (the X rows of one order are L1 hits for the next); the row of dZ
 // stays in registers when L <= 32 * 4 * kDotRegs
 constexpr int kDotRegs = 4;     // float4 per lane kept in registers: rows of up to 512 floats
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 edge_dots_kernel(const float* __restrict__ dZ, const float* __restrict__ X, const float* __restrict__ a,
                  const int* __restrict__ rowptr, const int* __restrict__ col, float* __restrict__ h,
                  float* __restrict__ r, int B, int K, int N, int L, int E) {
