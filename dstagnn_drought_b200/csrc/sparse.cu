@@ -54,7 +54,7 @@ struct EdgeBatch {
 // (per-order outputs from an order-free source: the forward product Z_k = A_k^T X with the row CSR)
 // warp per (b, n, 128-float chunk of the row) looping over the orders k: T_1, T_2, ... share the adjacency's
 // pattern, so the rows gathered for one order are L1 hits for the next.  lane = one float4.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 spmm_expand_kernel(const float* __restrict__ src, const float* __restrict__ a, const int* __restrict__ rowptr,
                    const int* __restrict__ col, const int* __restrict__ eid, float* __restrict__ dst, int B, int K,
                    int N, int L, int E, int chunks) {
@@ -93,7 +93,7 @@ spmm_expand_kernel(const float* __restrict__ src, const float* __restrict__ a, c
 
 // dst[b, n, chunk] = sum_k sum_{e in row (k, n)} a[b, eid ? eid[e] : e] * src[k, b, col[e], chunk]
 // (an order-free result from per-order sources: the input gradient dX = sum_k A_k dZ_k with the column CSR)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 spmm_reduce_kernel(const float* __restrict__ src, const float* __restrict__ a, const int* __restrict__ rowptr,
                    const int* __restrict__ col, const int* __restrict__ eid, float* __restrict__ dst, int B, int K,
                    int N, int L, int E, int chunks) {
