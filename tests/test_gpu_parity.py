@@ -67,7 +67,7 @@ def test_net_matches_reference_golden(name, precision, path, monkeypatch):
 
 
 # Oracle-only shapes: (shape, data seed, conditioned).
-# conditioned = True: the seed was found offline by tools/find_conditioned_seed.py using ONLY the fp64 oracle
+# conditioned = True: the seed was found offline by tests/tools/find_conditioned_seed.py using ONLY the fp64 oracle
 #   (tests/helpers.conditioned_case: no ReLU pre-activation within ~1e-6 of its kink); the test re-verifies
 #   that before it trusts the seed, and holds every gradient to max(1e-4, 3 x fp32-oracle error).
 # conditioned = False: shapes with so many ReLU units (8 M at PEMS07, 59 M at GAMBIA) that no input avoids the

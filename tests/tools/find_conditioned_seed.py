@@ -2,7 +2,7 @@
 """Find, with the fp64 CPU oracle ONLY, a well-conditioned data seed for each oracle-only parity case of
 tests/test_gpu_parity.py (ORACLE_CASES).
 
-    python tools/find_conditioned_seed.py [case ...]
+    python tests/tools/find_conditioned_seed.py [case ...]
 
 "Well conditioned" = the fp64 gradients move by < 5e-5 (relative to each tensor's maximum) when all weights
 and the input are perturbed by 1e-6: no ReLU pre-activation sits within rounding distance of its kink, so the
@@ -13,7 +13,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

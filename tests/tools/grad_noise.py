@@ -1,11 +1,11 @@
 """Run-to-run spread of the parameter gradients at the GAMBIA-layout test shape (N=37, T=144) against the fp64
 oracle, and the tooling that traced its one discrete outlier to a ReLU kink rather than to a kernel fault.
 
-    python tools/grad_noise.py 40 quiet            # per repetition: worst gradient error; outliers listed
-    python tools/grad_noise.py 40 quiet check      # + every contraction issued twice, results compared
-    python tools/grad_noise.py 40 quiet trace      # + element-wise comparison of every autograd Function's
+    python tests/tools/grad_noise.py 40 quiet            # per repetition: worst gradient error; outliers listed
+    python tests/tools/grad_noise.py 40 quiet check      # + every contraction issued twice, results compared
+    python tests/tools/grad_noise.py 40 quiet trace      # + element-wise comparison of every autograd Function's
                                                    #   outputs against a good repetition, ReLU sign flips
-    python tools/grad_noise.py 40 quiet fp32       # CUDA-core GEMMs (no atomically summed slices)
+    python tests/tools/grad_noise.py 40 quiet fp32       # CUDA-core GEMMs (no atomically summed slices)
 
 Finding (B200, round 1): in ~10 % of the repetitions one of the 340 992 outputs of block 1's Theta contraction
 (relu fused) is 0 instead of 3.4e-9 -- the forward sums its K-outer slices atomically, the pre-activation is
@@ -17,7 +17,9 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import dstagnn_oracle as O  # noqa: E402
 from dstagnn_drought_b200 import make_model  # noqa: E402
 
