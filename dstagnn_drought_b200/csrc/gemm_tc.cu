@@ -56,6 +56,7 @@ struct TcParams {
   int chunk_kb;              // > 0: accumulate at most this many k-blocks per TMEM pass (see "short chains")
   int a_rt;                  // output rows per M tile: 128, or fewer when the A tile is a ragged TMA box
   int a_rag_d1;              // > 0: A rows are (x, t) windows loaded by a rank-3 box (32 k, d1 t, a_rt / d1 x)
+  int epi_coalesce;          // row-contiguous outputs leave through the 32 x 32 transposing path (whole lines per store)
 };
 
 struct alignas(64) TcMaps {
@@ -799,7 +800,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                    (!Ca || (reinterpret_cast<uintptr_t>(Ca + n0) & 15) == 0) &&
                    (!Cm || (reinterpret_cast<uintptr_t>(Cm + n0) & 15) == 0);
         vec = __all_sync(0xffffffffu, vec || !mok);
-        if (vec) {
+        const bool b4ok = c_quad && full && __all_sync(0xffffffffu, ((c_ro | ca_ro | cm_ro) & 3) == 0);
+        if (vec && !(p.epi_coalesce && b4ok)) {
           if (mok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -818,7 +820,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               *dst = o;
             }
           }
-        } else if (c_quad && full && __all_sync(0xffffffffu, ((c_ro | ca_ro | cm_ro) & 3) == 0)) {
+        } else if (b4ok) {
           // (b4) columns contiguous in 16-byte aligned runs of a multiple of 4 (e.g. n = (x, t), t innermost):
           //      transpose the 32 x 32 block through shared memory; every lane then stores float4s,
           //      8 lanes covering the 32 columns of one row, 4 rows per instruction
@@ -1177,6 +1179,14 @@ int gemm_tc(const dstag_gemm_t* g_in, cudaStream_t stream) {
   p.a_bdim[0] = p.a_bdim[1] = p.b_bdim[0] = p.b_bdim[1] = 0;
   p.a_rt = TC_BM;
   p.a_rag_d1 = 0;
+  {
+    // long reductions (the epilogue hides behind the next tile's main loop): whole-line stores through the transposing
+    // path are 4-12 % faster than a thread streaming its own row (32 lines per store instruction); short-K launches are
+    // epilogue bound and keep the cheaper per-thread path.  DSTAG_TC_EPI = 0 / 1 forces either.
+    static int epi = -1;
+    if (epi < 0) { const char* e = getenv("DSTAG_TC_EPI"); epi = e ? (e[0] == '1' ? 1 : 0) : 2; }
+    p.epi_coalesce = epi == 2 ? (g->K >= 256 ? 1 : 0) : epi;
+  }
   p.a_tma = (!am && make_tmap(&maps.a, p.a_bdim, g->A, g->A.col, g->A.row, p.a_mode, g->K, g->M, g->batch, TC_BM)) ? 1 : 0;
   static int mn_tma = -1;
   if (mn_tma < 0) { const char* e = getenv("DSTAG_TC_TMA_MN"); mn_tma = (e && e[0] == '0') ? 0 : 1; }
