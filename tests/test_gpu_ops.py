@@ -349,6 +349,23 @@ def test_gram_rows_kernel(dev, cfg):
     assert torch.equal(part, part2)
 
 
+@pytest.mark.parametrize("cfg", [(148, 128, 32), (64, 512, 384), (17, 5, 12), (3, 7, 6), (295, 96, 32), (20, 1000, 64)])
+def test_sum_slices_fixed_order(dev, cfg):
+    """dstag_sum_slices (serial and slice-parallel kernels): the sum of the slices, identical from run to run."""
+    from dstagnn_drought_b200 import _lib
+    lib = _lib.load()
+    ns, rows, cols = cfg
+    torch.manual_seed(5)
+    ws = torch.randn(ns, rows, cols, device=dev)
+    out = torch.full((rows, cols), float("nan"), device=dev)
+    st = _lib.stream_ptr(ws)
+    _lib.check(lib.dstag_sum_slices(ws.data_ptr(), ws.stride(0), ns, out.data_ptr(), rows, cols, cols, st), "dstag_sum_slices")
+    assert rel_err(out, ws.double().sum(0)) < 2e-6
+    out2 = torch.empty_like(out)
+    _lib.check(lib.dstag_sum_slices(ws.data_ptr(), ws.stride(0), ns, out2.data_ptr(), rows, cols, cols, st), "dstag_sum_slices")
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("cfg", [(257, 32, 12), (11, 32, 144)])
 def test_gtu_fused_forward_without_grad_matches_gemm_path(dev, cfg, monkeypatch):
     """Inference (no saved gate factors; any T, also the T' > 128 rows per node of the drought configuration)
