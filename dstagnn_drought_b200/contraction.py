@@ -616,7 +616,7 @@ def _gram_weight_grad(spec, A, dC, B, am, alpha):
     K, X, T, Fin = A.shape
     Cc = dC.shape[-1]
     lib = _lib.load()
-    if Fin != 32 or Cc != 32 or K * Fin > 128 or X * T * 32 >= 2 ** 31 - 64 or not lib.dstag_gram_supported(K, Cc):
+    if Fin != 32 or Cc != 32 or K * Fin > 128 or X * T * 32 >= 2 ** 31 - 64 or not lib.dstag_gram_supported(K, Cc, 1, 1):
         return None
     st = _lib.stream_ptr(A)
     with _lib.on_device(st):

@@ -10,7 +10,7 @@
 // Both operands are row-contiguous, i.e. the reduction index is the SLOW index of both: the contraction engine
 // stages such operands MN-major through shared memory and splits the reduction 150-300 ways with a second pass; these
 // were its slowest launches (19-60 TFLOP/s).  Here:
-//   * rows are the K dimension, 32 per k-block.  A (M = (tap, channel), 128 lanes per 4 taps) goes through TENSOR
+//   * rows are the K dimension: a k-block is G = floor(32 / Tp) whole nodes (up to 32 rows, the rest zero).  A (M = (tap, channel), 128 lanes per 4 taps) goes through TENSOR
 //     MEMORY: producer thread (tap j, channel c) reads its column of the k-block with 32 coalesced 4-byte loads (a warp
 //     = one tap reads one whole 128-byte row per instruction; the taps' windows overlap in L1), splits it into the
 //     3xTF32 hi / lo terms and stores them with tcgen05.st -- no shared memory, no transposition;
@@ -41,10 +41,11 @@ struct GramParams {
   const float* a;           // rows of 32 floats
   const float* b;           // (R, NB)
   float* partial;           // (gridDim.x, MT * 128, NB)
-  int R, T, Tp;             // GEMM row r -> (x = r / Tp, tp = r % Tp) -> A row x * T + tp   (Tp == T: identity)
+  int X, T, Tp;             // X nodes of Tp GEMM rows each; GEMM row (x, tp) reads A row x * T + tp
+  int G;                    // nodes per k-block: G * Tp <= 32 rows (the other rows of the block are zero rows)
   int taps;
   long long tap_stride;     // floats from tap j to tap j + 1 of the same GEMM row
-  int nkb;                  // k-blocks of 32 rows
+  int nkb;                  // k-blocks = ceil(X / G)
   long long* trace;         // optional per-warp cycle counters (DSTAG_GRAM_TRACE), normally NULL
 };
 
@@ -72,7 +73,11 @@ struct GramCfg {
   static constexpr int A_TM = 128;                     // first column of the A slots
 };
 
-template <int MT, int NB>
+// TPC: Tp known at compile time (the GTU kernel sizes at T = 12: 10, 8, 6; the Theta gradient: 1) or 0 = run time.
+// A k-block is G whole nodes, so with a constant Tp every load of the block is `LDG [node base + immediate]`: ONE
+// instruction.  The producers are instruction-issue bound (ncu: 55 % issue active, 5 500 warp instructions per
+// k-block); walking the rows with a running (node, time) pair cost 13 instructions per load.
+template <int MT, int NB, int TPC>
 __global__ void __launch_bounds__(GR_THREADS, 1) gram_tc_kernel(const __grid_constant__ GramParams p) {
   using Cfg = GramCfg<MT, NB>;
   extern __shared__ uint8_t smem_raw[];
@@ -124,23 +129,40 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_tc_kernel(const __grid_con
     const float* abase = p.a + (long long)tap * p.tap_stride + lane;
     // the 32 loads of the NEXT k-block are in flight while the current one is split and stored (one exposed global
     // latency per k-block otherwise: the whole CTA works on the same k-block)
+    const int Tp = TPC > 0 ? TPC : p.Tp;
+    const int G = TPC > 0 ? 32 / TPC : p.G;
+    const long long node_stride = (long long)p.T * 32;
     auto load_block = [&](int i, uint32_t (&v)[32]) {
-      const int r0 = (kb0 + i) * 32;
       if (live) {
-        // the 32 GEMM rows r0 .. r0 + 31 map to A rows x * T + tp: consecutive, with a jump of T - Tp at node ends
-        // (selects, not branches; handing the offsets round by shuffle was 10-30 % slower)
-        const int x = r0 / p.Tp;
-        int tp = r0 - x * p.Tp;
-        const float* ptr = abase + ((long long)x * p.T + tp) * 32;
-        const int step_wrap = 32 * (1 + p.T - p.Tp);
-        const int nvalid = p.R - r0;
+        const int x0 = (kb0 + i) * G;
+        const int nlast = min(G, p.X - x0) - 1;            // nodes beyond it re-read the last one: their B rows are zero
+        const float* bp = abase + (long long)x0 * node_stride;
+        if (TPC == 1 && nlast == 31) {
+          // (this instantiation is dispatched for T == Tp == 1 only: the 32 rows of the block are consecutive)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          v[k] = k < nvalid ? __float_as_uint(__ldg(ptr)) : 0u;
-          ++tp;
-          const bool wrap = tp == p.Tp;
-          tp = wrap ? 0 : tp;
-          ptr += wrap ? step_wrap : 32;
+          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__ldg(bp + k * 32));
+        } else if (TPC > 0) {
+          constexpr int GC = TPC > 0 ? 32 / TPC : 1, TC = TPC > 0 ? TPC : 1;
+          const bool whole = nlast == GC - 1;               // (a partial last block clamps the node index)
+#pragma unroll
+          for (int n = 0; n < GC; ++n) {
+            const float* np = bp + (long long)(whole ? n : min(n, nlast)) * node_stride;
+#pragma unroll
+            for (int t = 0; t < TC; ++t) v[n * TC + t] = __float_as_uint(__ldg(np + t * 32));
+          }
+#pragma unroll
+          for (int k = GC * TC; k < 32; ++k) v[k] = 0u;
+        } else {
+          int n = 0, t = 0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const bool in = n < G;
+            v[k] = in ? __float_as_uint(__ldg(bp + (long long)min(n, nlast) * node_stride + t * 32)) : 0u;
+            ++t;
+            const bool wrap = t == Tp;
+            t = wrap ? 0 : t;
+            n += wrap ? 1 : 0;
+          }
         }
       } else {
 #pragma unroll
@@ -221,10 +243,12 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_tc_kernel(const __grid_con
       __syncwarp();
       if (p.trace) w_wait += clock64() - t0; }
       const uint32_t dst = smem_u32(smem + s * Cfg::B_STAGE);
-      const long long r0 = (long long)(kb0 + i) * 32;
+      const int x0 = (kb0 + i) * p.G;
+      const int nvalid = min(p.G, p.X - x0) * p.Tp;          // the block's rows are contiguous in B; the rest are zero rows
+      const long long r0 = (long long)x0 * p.Tp;
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
-        const bool ok = r0 + krow[u] < p.R;
+        const bool ok = krow[u] < nvalid;
         cp_async16(dst + doff[u], ok ? (const void*)(p.b + (r0 + krow[u]) * NB + 4 * kch[u]) : (const void*)p.b, ok ? 16u : 0u);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -314,7 +338,7 @@ int gram_sms(int dev) {
   return sms[dev];
 }
 
-template <int MT, int NB>
+template <int MT, int NB, int TPC>
 int launch_gram(const GramParams& p, cudaStream_t stream) {
   using Cfg = GramCfg<MT, NB>;
   int dev = 0;
@@ -322,14 +346,14 @@ int launch_gram(const GramParams& p, cudaStream_t stream) {
   if (dev < 0 || dev >= kMaxDevG) dev = 0;
   static bool configured[kMaxDevG] = {false};
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<MT, NB, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("dstag_gram_rows: cudaFuncSetAttribute(%d) failed: %s", Cfg::SMEM, cudaGetErrorString(e));
       return (int)e;
     }
     configured[dev] = true;
   }
-  gram_tc_kernel<MT, NB><<<gram_sms(dev), GR_THREADS, Cfg::SMEM, stream>>>(p);
+  gram_tc_kernel<MT, NB, TPC><<<gram_sms(dev), GR_THREADS, Cfg::SMEM, stream>>>(p);
   DSTAG_RETURN_LAUNCH("dstag_gram_rows");
 }
 
@@ -346,24 +370,33 @@ int dstag_gram_slices(void) {
   return dstag::gram_sms(dev);
 }
 
-int dstag_gram_supported(int32_t taps, int32_t NB) { return (taps >= 1 && taps <= 8 && (NB == 32 || NB == 64)) ? 1 : 0; }
+int dstag_gram_supported(int32_t taps, int32_t NB, int32_t T, int32_t Tp) {
+  return (taps >= 1 && taps <= 8 && (NB == 32 || NB == 64) && Tp >= 1 && Tp <= T && Tp <= 32) ? 1 : 0;
+}
 
 int dstag_gram_rows(const float* a, const float* b, float* partial, int64_t X, int32_t T, int32_t Tp, int32_t taps,
                     int64_t tap_stride, int32_t NB, void* stream) {
   DSTAG_CHECK_ARG(a && b && partial && X > 0, "dstag_gram_rows: null pointer or empty problem");
-  DSTAG_CHECK_ARG(dstag_gram_supported(taps, NB), "dstag_gram_rows: unsupported shape taps=%d NB=%d", taps, NB);
-  DSTAG_CHECK_ARG(Tp >= 1 && Tp <= T, "dstag_gram_rows: need 1 <= Tp <= T (got Tp=%d T=%d)", Tp, T);
+  DSTAG_CHECK_ARG(dstag_gram_supported(taps, NB, T, Tp), "dstag_gram_rows: unsupported shape taps=%d NB=%d T=%d Tp=%d", taps,
+                  NB, T, Tp);
   DSTAG_CHECK_ARG(X * T * 32 < (1ll << 31) - 64, "dstag_gram_rows: too many rows");
   DSTAG_CHECK_ARG(((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0,
                   "dstag_gram_rows: b and partial must be 16-byte aligned");
   dstag::GramParams p;
   p.a = a; p.b = b; p.partial = partial;
-  p.R = (int)(X * Tp); p.T = T; p.Tp = Tp; p.taps = taps; p.tap_stride = tap_stride;
-  p.nkb = (p.R + 31) / 32;
+  p.X = (int)X; p.T = T; p.Tp = Tp; p.G = 32 / Tp; p.taps = taps; p.tap_stride = tap_stride;
+  p.nkb = (int)((X + p.G - 1) / p.G);
   { const char* e = getenv("DSTAG_GRAM_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (taps <= 4) return NB == 64 ? dstag::launch_gram<1, 64>(p, st) : dstag::launch_gram<1, 32>(p, st);
-  return NB == 64 ? dstag::launch_gram<2, 64>(p, st) : dstag::launch_gram<2, 32>(p, st);
+  const bool two = taps > 4;
+  // instantiations with a compile-time Tp for the shapes of the shipped configurations (T = 12, ks = 3 / 5 / 7; the
+  // Theta gradient), the run-time walk for everything else
+  if (NB == 64 && !two && Tp == 10) return dstag::launch_gram<1, 64, 10>(p, st);
+  if (NB == 64 && two && Tp == 8) return dstag::launch_gram<2, 64, 8>(p, st);
+  if (NB == 64 && two && Tp == 6) return dstag::launch_gram<2, 64, 6>(p, st);
+  if (NB == 32 && !two && Tp == 1 && T == 1) return dstag::launch_gram<1, 32, 1>(p, st);
+  if (!two) return NB == 64 ? dstag::launch_gram<1, 64, 0>(p, st) : dstag::launch_gram<1, 32, 0>(p, st);
+  return NB == 64 ? dstag::launch_gram<2, 64, 0>(p, st) : dstag::launch_gram<2, 32, 0>(p, st);
 }
 
 }  // extern "C"

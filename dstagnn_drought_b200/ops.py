@@ -529,7 +529,7 @@ class GtuStack(torch.autograd.Function):
                                                    0 if i == 0 else 1, _stream(g)), "dstag_gtu_gate_conv_bwd")
             db = colsum(ws, ws_rows, 2 * Cc)
             dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)
-            if gram:
+            if gram and lib.dstag_gram_supported(ks, 2 * Cc, T, tp):
                 # dW[o, c, 0, j] = sum_{x,t'} du[(x,t'), o] g[x, t'+j, c]: the tall-skinny Gram kernel (one partial per
                 # CTA, added in a fixed order)
                 mrows = 128 * ((ks + 3) // 4)

@@ -227,9 +227,10 @@ int dstag_gtu_bwd_ws_rows(void);
  * GTU conv weight gradient (autograd of model/DSTAGNN_my.py:193): a = g (X, T, 32), tap_stride = 32 (the next time
  * step), b = du (X, Tp, 64), D[(j, c), o] = dW[o, c, 0, j].
  * Every CTA (dstag_gram_slices() of them) writes ONE partial result: partial (slices, 128 * ceil(taps / 4), NB); the
- * caller adds them in a fixed order with dstag_sum_slices (rows (j, c) with j >= taps are zero). */
+ * caller adds them in a fixed order with dstag_sum_slices (rows (j, c) with j >= taps are zero).  Rows are taken in
+ * k-blocks of floor(32 / Tp) whole nodes. */
 int dstag_gram_slices(void);
-int dstag_gram_supported(int32_t taps, int32_t NB);
+int dstag_gram_supported(int32_t taps, int32_t NB, int32_t T, int32_t Tp);   /* Tp <= 32: a k-block is whole nodes */
 int dstag_gram_rows(const float* a, const float* b, float* partial, int64_t X, int32_t T, int32_t Tp, int32_t taps,
                     int64_t tap_stride, int32_t NB, void* stream);
 

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 16
+        return 17
 
     def dstag_last_error(self):
         return self.err
@@ -257,8 +257,8 @@ class FakeLib:
     def dstag_gram_slices(self):
         return 3
 
-    def dstag_gram_supported(self, taps, NB):
-        return int(1 <= taps <= 8 and NB in (32, 64))
+    def dstag_gram_supported(self, taps, NB, T, Tp):
+        return int(1 <= taps <= 8 and NB in (32, 64) and 1 <= Tp <= min(T, 32))
 
     def dstag_gram_rows(self, a, b, partial, X, T, Tp, taps, tap_stride, NB, stream):
         self.launches += 1

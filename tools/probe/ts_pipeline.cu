@@ -35,7 +35,8 @@ __device__ __forceinline__ void st32(uint32_t t, const uint32_t (&r)[32]) { asm 
 
 constexpr int SLOTS = 6;
 // flags: 1 = no MMAs (wait + commit only), 2 = MMA warp spins with nanosleep back-off, 4 = two producer teams,
-//        8 = producers skip tcgen05.st, 16 = N = 128 instead of 64, 32 = 4 MMAs per k-block instead of 12
+//        8 = producers skip tcgen05.st, 16 = N = 128 instead of 64, 32 = 4 MMAs per k-block instead of 12,
+//        64 = producers also write shared memory and issue fence.proxy.async every iteration
 __global__ void __launch_bounds__(416, 1) k(long long* out, int iters, int flags) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -71,6 +72,10 @@ __global__ void __launch_bounds__(416, 1) k(long long* out, int iters, int flags
       const long long b0 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ta = base + 128 + s * 64 + ((uint32_t)(32 * q) << 16);
+      if (flags & 64) {                                   // a shared-memory write that the tensor core must see
+        *reinterpret_cast<float4*>(smem + 32768 + threadIdx.x * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
       if (!(flags & 8)) { st32(ta, r); st32(ta + 32, r); }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -118,9 +123,9 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   const int iters = 4000;
   const char* names[] = {"full pipeline", "no MMAs (wait + commit)", "MMA warp backs off", "two producer teams", "two teams, no MMAs", "producers skip tcgen05.st", "N = 128",
-                         "4 MMAs per k-block", "two teams, 4 MMAs", "two teams, N = 128"};
-  const int fl[] = {0, 1, 2, 4, 5, 8, 16, 32, 36, 20};
-  for (int v = 0; v < 10; ++v) {
+                         "4 MMAs per k-block", "two teams, 4 MMAs", "two teams, N = 128", "+ st.shared + fence.proxy.async", "same, two teams"};
+  const int fl[] = {0, 1, 2, 4, 5, 8, 16, 32, 36, 20, 64, 68};
+  for (int v = 0; v < 12; ++v) {
     k<<<148, 416, 128 * 1024>>>(d, 100, fl[v]);
     k<<<148, 416, 128 * 1024>>>(d, iters, fl[v]);
     cudaError_t e = cudaDeviceSynchronize();
