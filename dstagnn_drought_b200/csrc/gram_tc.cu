@@ -380,6 +380,8 @@ int dstag_gram_rows(const float* a, const float* b, float* partial, int64_t X, i
   DSTAG_CHECK_ARG(dstag_gram_supported(taps, NB, T, Tp), "dstag_gram_rows: unsupported shape taps=%d NB=%d T=%d Tp=%d", taps,
                   NB, T, Tp);
   DSTAG_CHECK_ARG(X * T * 32 < (1ll << 31) - 64, "dstag_gram_rows: too many rows");
+  DSTAG_CHECK_ARG(tap_stride != 32 || Tp + taps - 1 <= T,
+                  "dstag_gram_rows: taps that are consecutive rows need Tp + taps - 1 <= T (got Tp=%d taps=%d T=%d)", Tp, taps, T);
   DSTAG_CHECK_ARG(((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0,
                   "dstag_gram_rows: b and partial must be 16-byte aligned");
   dstag::GramParams p;
