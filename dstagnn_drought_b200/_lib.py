@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -75,6 +75,10 @@ SIGNATURES = {
     "dstag_gram_slices": (C.c_int, []),
     "dstag_gram_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
     "dstag_gram_rows": (C.c_int, [_F, _F, _F, _i64, _i32, _i32, _i32, _i64, _i32, _F]),
+    "dstag_thin_supported": (C.c_int, [_i32, _i32]),
+    "dstag_thin_slices": (C.c_int, []),
+    "dstag_thin_expand": (C.c_int, [_F, _i64, _i32, _i32, _F, _i64, _i64, _F, _F, _i64, _i32, _i32, _F]),
+    "dstag_thin_bwd": (C.c_int, [_F, _i64, _i32, _i32, _F, _i64, _i64, _F, _F, _F, _F, _i64, _i32, _F]),
     "dstag_outer_sum_supported": (C.c_int, [_i32, _i32, _i32]),
     "dstag_outer_sum": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _F]),
     "dstag_tail_fwd": (C.c_int, [_F, _F, _F, _F, _F, _f32, _F, _F, _F, _i64, _i32, _i32, _f32, _u64, _F, _F]),
@@ -137,7 +141,7 @@ class _Profiled:
     _PLAIN = ("dstag_abi_version", "dstag_last_error", "dstag_launch_count", "dstag_reset_launch_count",
               "dstag_gemm", "dstag_gemm_uses_tensor_cores", "dstag_tail_fused_supported",
               "dstag_outer_sum_supported", "dstag_gtu_tc_supported", "dstag_gtu_bwd_ws_rows", "dstag_gram_slices",
-              "dstag_gram_supported")
+              "dstag_gram_supported", "dstag_thin_supported", "dstag_thin_slices")
 
     def __init__(self, lib):
         self._cdll = lib

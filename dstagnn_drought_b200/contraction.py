@@ -630,9 +630,76 @@ def _gram_weight_grad(spec, A, dC, B, am, alpha):
     return dt[:K * Fin].view(K, Fin, Cc)
 
 
+def _thin_args(spec, A, B, amul, alpha, cadd, cadd_sub, pad_rows):
+    """Operands of the thin-feature kernels (csrc/thin.cu) for the first block's Theta mix and 1x1 residual conv
+    (model/DSTAGNN_my.py:131, 228 with in_channels = 1): (a_plane, taps, F, w strides, R, C), or None when the
+    contraction is not one of them (the engine takes it then)."""
+    if amul is not None or alpha != 1.0 or pad_rows or os.environ.get("DSTAG_THIN", "1") == "0":
+        return None
+    if cadd is not None and cadd_sub != "c":
+        return None
+    if not (A.is_contiguous() and A.dtype == torch.float32 and B.dtype == torch.float32):
+        return None
+    if spec == "kxtf,kfc->xtc" and B.is_contiguous():
+        K, X, T, Fin = A.shape
+        Cc = B.shape[-1]
+        args = (X * T * Fin, K, Fin, Cc, 1, X * T, Cc)
+    elif spec == "xtf,cf->xtc":
+        X, T, Fin = A.shape
+        Cc = B.shape[0]
+        args = (0, 1, Fin, B.stride(1), B.stride(0), X * T, Cc)
+    else:
+        return None
+    if not _lib.load().dstag_thin_supported(args[1] * args[2], Cc):
+        return None
+    return args
+
+
+def _thin_forward(args, A, B, cadd, relu):
+    a_plane, taps, Fin, w_js, w_cs, R, Cc = args
+    out = torch.empty(A.shape[-3:-1] + (Cc,), device=A.device, dtype=torch.float32)
+    _lib.check(_lib.load().dstag_thin_expand(A.data_ptr(), a_plane, taps, Fin, B.data_ptr(), w_js, w_cs,
+                                             cadd.data_ptr() if cadd is not None else 0, out.data_ptr(), R, Cc,
+                                             int(relu), _lib.stream_ptr(A)), "dstag_thin_expand")
+    return out
+
+
+def _thin_backward(args, A, B, dC, y, need_dA, need_dB, need_dadd):
+    """One pass over dC: relu mask, dA (thin planes), and per-CTA partials of dB / the bias gradient."""
+    a_plane, taps, Fin, w_js, w_cs, R, Cc = args
+    J = taps * Fin
+    lib = _lib.load()
+    st = _lib.stream_ptr(A)
+    dA = torch.empty_like(A) if need_dA else None
+    part = None
+    if need_dB or need_dadd:
+        part = torch.empty((lib.dstag_thin_slices(), J + 1, Cc), device=A.device, dtype=torch.float32)
+    _lib.check(lib.dstag_thin_bwd(A.data_ptr(), a_plane, taps, Fin, B.data_ptr(), w_js, w_cs, dC.data_ptr(),
+                                  y.data_ptr() if y is not None else 0, dA.data_ptr() if need_dA else 0,
+                                  part.data_ptr() if part is not None else 0, R, Cc, st), "dstag_thin_bwd")
+    dB = dadd = None
+    if part is not None:
+        dt = torch.empty((J + 1, Cc), device=A.device, dtype=torch.float32)
+        _lib.check(lib.dstag_sum_slices(part.data_ptr(), part.stride(0), part.shape[0], dt.data_ptr(), J + 1, Cc, Cc,
+                                        st), "dstag_sum_slices")
+        if need_dB:
+            # (K, F, C) as stored; the conv weight is (C, F): a view when F == 1
+            dB = dt[:J].view(B.shape) if (B.dim() == 3 or Fin == 1) else dt[:J].t().contiguous()
+        if need_dadd:
+            dadd = dt[J]
+    return dA, dB, dadd
+
+
 class _Contract(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, cadd, amul, spec, cadd_sub, amul_sub, alpha, relu, pad_rows):
+        ctx.thin = _thin_args(spec, A, B, amul, alpha, cadd, cadd_sub, pad_rows)
+        if ctx.thin is not None:
+            out = _thin_forward(ctx.thin, A, B, cadd, relu)
+            ctx.spec, ctx.cadd_sub, ctx.amul_sub, ctx.alpha, ctx.relu = spec, cadd_sub, amul_sub, alpha, relu
+            ctx.has_cadd = cadd is not None
+            ctx.save_for_backward(A, B, amul, out if relu else None)
+            return out
         out = None
         if pad_rows:
             assert not relu
@@ -650,6 +717,11 @@ class _Contract(torch.autograd.Function):
         A, B, amul, out = ctx.saved_tensors
         pl = plan(ctx.spec)
         dC = dense_rows(dC)
+        if ctx.thin is not None:
+            dA, dB, dadd = _thin_backward(ctx.thin, A, B, dC.contiguous(), out if ctx.relu else None,
+                                          ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                          ctx.has_cadd and ctx.needs_input_grad[2])
+            return dA, dB, dadd, None, None, None, None, None, None, None
         if ctx.relu:
             dC = relu_bwd(out, dC)
         dA = dB = dadd = None

@@ -91,6 +91,9 @@ gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
 // through shared memory at the end.
 // ---------------------------------------------------------------------------------------
 constexpr int kOsNodes = 8;            // nodes per slab
+// MR rows of `a` per thread: with one row a thread issues 5 shared-memory float4 loads per 16 FMAs and the kernel is
+// bound by the shared-memory pipe (ncu: issue active 68 %, 2.1 TB/s); three rows share the four `b` loads (7 per 48).
+template <int MR>
 __global__ void __launch_bounds__(256)
 outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                  float* __restrict__ asum, long long X, int m, int n, int C, int phases) {
@@ -98,13 +101,15 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
   const int Cp = C + 4;                    // padded row: rows that differ in m / n hit different banks
   float* as = sm;                          // kOsNodes x m x Cp
   float* bs = sm + kOsNodes * m * Cp;      // kOsNodes x n x Cp
-  const int nq = n >> 2, per = m * nq;     // output quads
+  const int nq = n >> 2, per = (m / MR) * nq;     // threads per phase: (row group, output quad)
   const int ph = threadIdx.x / per, id = threadIdx.x - ph * per;
   const bool active = ph < phases;
-  const int mi = id / nq, q = id - mi * nq;
+  const int mi = (id / nq) * MR, q = id - (id / nq) * nq;
   const int c4n = C >> 2;                  // float4 groups per row
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float accs = 0.f;
+  float acc[MR][4];
+  float accs[MR];
+#pragma unroll
+  for (int r = 0; r < MR; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; accs[r] = 0.f; }
   const long long nslab = (X + kOsNodes - 1) / kOsNodes;
   for (long long sl = blockIdx.x; sl < nslab; sl += gridDim.x) {
     const long long x0 = sl * kOsNodes;
@@ -124,36 +129,52 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
       // phase ph takes the (node, channel group) pairs ph, ph + phases, ...
       for (int e = ph; e < nx * c4n; e += phases) {
         const int xl = e / c4n, cg = e - xl * c4n;
-        const float4 av = *reinterpret_cast<const float4*>(as + (xl * m + mi) * Cp + 4 * cg);
+        float4 av[MR];
+#pragma unroll
+        for (int r = 0; r < MR; ++r) av[r] = *reinterpret_cast<const float4*>(as + (xl * m + mi + r) * Cp + 4 * cg);
         // the thread's four outputs are n = q, q + nq, q + 2 nq, q + 3 nq: for a fixed j the lanes of a
         // quarter warp read consecutive padded rows (stride 36 floats = 4 banks): conflict-free float4 loads
         const float* bp = bs + (xl * n + q) * Cp + 4 * cg;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 bv = *reinterpret_cast<const float4*>(bp + j * nq * Cp);
-          acc[j] = fmaf(av.x, bv.x, fmaf(av.y, bv.y, fmaf(av.z, bv.z, fmaf(av.w, bv.w, acc[j]))));
+#pragma unroll
+          for (int r = 0; r < MR; ++r)
+            acc[r][j] = fmaf(av[r].x, bv.x, fmaf(av[r].y, bv.y, fmaf(av[r].z, bv.z, fmaf(av[r].w, bv.w, acc[r][j]))));
         }
-        if (q == 0) accs += (av.x + av.y) + (av.z + av.w);
+        if (q == 0) {
+#pragma unroll
+          for (int r = 0; r < MR; ++r) accs[r] += (av[r].x + av[r].y) + (av[r].z + av[r].w);
+        }
       }
     }
   }
   __syncthreads();
-  float* red = sm;                         // [256][5]
+  constexpr int RW = 5 * MR;               // floats per thread in the fold buffer
+  float* red = sm;                         // [256][RW]
   if (active) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[threadIdx.x * 5 + j] = acc[j];
-    red[threadIdx.x * 5 + 4] = accs;
+    for (int r = 0; r < MR; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[threadIdx.x * RW + 5 * r + j] = acc[r][j];
+      red[threadIdx.x * RW + 5 * r + 4] = accs[r];
+    }
   }
   __syncthreads();
   if (threadIdx.x < per) {
-    float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float t[RW];
+#pragma unroll
+    for (int j = 0; j < RW; ++j) t[j] = 0.f;
     for (int p2 = 0; p2 < phases; ++p2)
 #pragma unroll
-      for (int j = 0; j < 5; ++j) t[j] += red[(p2 * per + threadIdx.x) * 5 + j];
-    float* dst = out + mi * n + q;
+      for (int j = 0; j < RW; ++j) t[j] += red[(p2 * per + threadIdx.x) * RW + j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dst + j * nq, t[j]);
-    if (asum && q == 0) atomicAdd(asum + mi, t[4]);
+    for (int r = 0; r < MR; ++r) {
+      float* dst = out + (mi + r) * n + q;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dst + j * nq, t[5 * r + j]);
+      if (asum && q == 0) atomicAdd(asum + mi + r, t[5 * r + 4]);
+    }
   }
 }
 
@@ -323,14 +344,20 @@ int dstag_outer_sum(const float* a, const float* b, float* out, float* asum, int
   DSTAG_CHECK_ARG(dstag_outer_sum_supported(m, n, C), "dstag_outer_sum: unsupported shape m=%d n=%d C=%d", m, n, C);
   DSTAG_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0,
                   "dstag_outer_sum: operands must be 16-byte aligned");
-  const int per = m * (n / 4);
+  // three rows per thread when the fold buffer (15 floats per thread) fits in the slab's shared memory
+  const bool three = m % 3 == 0 && (size_t)kOsNodes * (m + n) * (C + 4) >= 256 * 15;
+  const int per = (three ? m / 3 : m) * (n / 4);
   const int phases = 256 / per;
   const size_t smem = (size_t)kOsNodes * (m + n) * (C + 4) * sizeof(float);
-  int rc = opt_in_smem((const void*)outer_sum_kernel, smem, "dstag_outer_sum");
+  int rc = three ? opt_in_smem((const void*)outer_sum_kernel<3>, smem, "dstag_outer_sum")
+                 : opt_in_smem((const void*)outer_sum_kernel<1>, smem, "dstag_outer_sum");
   if (rc) return rc;
   const long long nslab = (X + kOsNodes - 1) / kOsNodes;
   const int grid = (int)(nslab < kNumSMs * 4 ? nslab : kNumSMs * 4);
-  outer_sum_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, out, asum, X, m, n, C, phases);
+  if (three)
+    outer_sum_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, out, asum, X, m, n, C, phases);
+  else
+    outer_sum_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, out, asum, X, m, n, C, phases);
   DSTAG_RETURN_LAUNCH("dstag_outer_sum");
 }
 

@@ -39,6 +39,9 @@ ALGO_BYTES = {
     "dstag_gtu_conv_gate_fwd": lambda a: 4 * a[5] * a[6] * (a[7] + (a[7] - a[8] + 1) * (1 + (2 if a[4] else 0))),
     "dstag_gtu_gate_conv_bwd": lambda a: 4 * a[6] * a[7] * ((a[8] - a[9] + 1) * 5 + a[8] * (2 if a[12] else 1)),
     "dstag_gram_rows": lambda a: 4 * a[3] * (a[4] * 32 + a[5] * a[8]),
+    # thin contractions: the (R, C) tensor once (+ the relu mask), the J thin planes once
+    "dstag_thin_expand": lambda a: 4 * a[9] * (a[10] + a[2] * a[3]),
+    "dstag_thin_bwd": lambda a: 4 * a[11] * (a[12] * (2 if a[8] else 1) + a[2] * a[3] * ((1 if a[10] else 0) + (1 if a[9] else 0))),
     "dstag_outer_sum": lambda a: 4 * a[4] * (a[5] + a[6]) * a[7],
     "dstag_tail_fwd": lambda a: 4 * a[9] * a[10] * a[11] * (3 + (1 if a[1] else 0)),
     "dstag_tail_bwd": lambda a: 4 * a[12] * a[13] * a[14] * (5 + (2 if a[2] else 0)),

@@ -242,6 +242,22 @@ int dstag_outer_sum_supported(int32_t m, int32_t n, int32_t C);
 int dstag_outer_sum(const float* a, const float* b, float* out, float* asum, int64_t X, int32_t m, int32_t n,
                     int32_t C, void* stream);
 
+/* Thin-feature contractions (csrc/thin.cu): J = taps * F <= 4 input values per row, C output channels (C / 4 a power
+ * of two <= 32).  The first block's Theta mix (model/DSTAGNN_my.py:131 with in_channels = 1) and 1x1 residual_conv
+ * (line 228) -- streaming kernels that move the (R, C) tensor once instead of one-k-block tensor-core tiles.
+ *   a_j[r] = a[(j / F) * a_plane + r * F + j % F]  (taps planes of (R, F) rows);   w[j, c] = w[j * w_js + c * w_cs]
+ *   expand: out[r, c] = act(bias[c] + sum_j a_j[r] w[j, c])          out (R, C) contiguous; bias nullable; relu flag
+ *   bwd:    d' = d * [y > 0] (y nullable: the forward output of a relu expand)
+ *           dz (nullable, laid out like a):   dz_j[r] = sum_c d'[r, c] w[j, c]
+ *           partial (nullable): (dstag_thin_slices(), J + 1, C) per-CTA partials of dw[j, c] = sum_r a_j[r] d'[r, c]
+ *           and (row J) db[c] = sum_r d'[r, c]; the caller adds them in a fixed order with dstag_sum_slices. */
+int dstag_thin_supported(int32_t J, int32_t C);
+int dstag_thin_slices(void);
+int dstag_thin_expand(const float* a, int64_t a_plane, int32_t taps, int32_t F, const float* w, int64_t w_js,
+                      int64_t w_cs, const float* bias, float* out, int64_t R, int32_t C, int32_t relu, void* stream);
+int dstag_thin_bwd(const float* a, int64_t a_plane, int32_t taps, int32_t F, const float* w, int64_t w_js, int64_t w_cs,
+                   const float* d, const float* y, float* dz, float* partial, int64_t R, int32_t C, void* stream);
+
 /* Unfused tail (model/DSTAGNN_my.py:243-252) for any T and C <= 256:
  *   tc' = dropout(tc) ; tco = relu(tc' [+ g]) ; out = LN_C(relu(r + tco)) over the channel axis
  *   tc, g (NULL in block 0, line 245), r, out: (X, T, C);  mean/rstd: (X, T) saved statistics.

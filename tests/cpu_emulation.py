@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 17
+        return 18
 
     def dstag_last_error(self):
         return self.err
@@ -294,6 +294,54 @@ class FakeLib:
             DG[:, j:j + Tp, :] += Y[:, :, j, :]
         out = _arr(dg, X * T * Cc).reshape(X, T, Cc)
         out[:] = (out + DG) if accumulate else DG
+        return 0
+
+    # ---- thin-feature contractions (csrc/thin.cu) ----
+    def dstag_thin_supported(self, J, Cc):
+        Q = Cc // 4
+        return int(1 <= J <= 4 and Cc % 4 == 0 and 1 <= Q <= 32 and Q & (Q - 1) == 0)
+
+    def dstag_thin_slices(self):
+        return 3
+
+    @staticmethod
+    def _thin_operands(a, a_plane, taps, F, w, w_js, w_cs, R, Cc):
+        J = taps * F
+        span_a = (taps - 1) * a_plane + R * F
+        A = _arr(a, span_a)
+        idx = [(j // F) * a_plane + np.arange(R) * F + j % F for j in range(J)]
+        Wm = _arr(w, (J - 1) * w_js + (Cc - 1) * w_cs + 1)
+        W = np.array([[Wm[j * w_js + c * w_cs] for c in range(Cc)] for j in range(J)], dtype=np.float64)
+        return A, idx, W
+
+    def dstag_thin_expand(self, a, a_plane, taps, F, w, w_js, w_cs, bias, out, R, Cc, relu, stream):
+        self.launches += 1
+        A, idx, W = self._thin_operands(a, a_plane, taps, F, w, w_js, w_cs, R, Cc)
+        Z = np.stack([A[i] for i in idx], 1).astype(np.float64)                  # (R, J)
+        O = Z @ W
+        if bias:
+            O = O + _arr(bias, Cc).astype(np.float64)
+        _arr(out, R * Cc).reshape(R, Cc)[:] = np.maximum(O, 0) if relu else O
+        return 0
+
+    def dstag_thin_bwd(self, a, a_plane, taps, F, w, w_js, w_cs, d, y, dz, partial, R, Cc, stream):
+        self.launches += 1
+        J = taps * F
+        A, idx, W = self._thin_operands(a, a_plane, taps, F, w, w_js, w_cs, R, Cc)
+        D = _arr(d, R * Cc).reshape(R, Cc).astype(np.float64)
+        if y:
+            D = D * (_arr(y, R * Cc).reshape(R, Cc) > 0)
+        if dz:
+            DZ = _arr(dz, (taps - 1) * a_plane + R * F)
+            P = D @ W.T                                                          # (R, J)
+            for j, i in enumerate(idx):
+                DZ[i] = P[:, j]
+        if partial:
+            Pm = _arr(partial, 3 * (J + 1) * Cc).reshape(3, J + 1, Cc)
+            Pm[:] = 0
+            Z = np.stack([A[i] for i in idx], 1).astype(np.float64)
+            Pm[1, :J] = Z.T @ D
+            Pm[1, J] = D.sum(0)
         return 0
 
     def dstag_outer_sum_supported(self, m, n, Cc):

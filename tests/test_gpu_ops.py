@@ -349,6 +349,62 @@ def test_gram_rows_kernel(dev, cfg):
     assert torch.equal(part, part2)
 
 
+@pytest.mark.parametrize("cfg", [(3, 5, 12, 1, 32), (3, 1531, 12, 1, 32), (1, 77, 3, 1, 8), (2, 40, 12, 2, 128), (4, 9, 7, 1, 64),
+                                 (2, 301, 12, 1, 16)])
+def test_thin_theta_mix(dev, monkeypatch, cfg):
+    """Theta mix of the first block (K * F_in <= 4 values per row): streaming kernels vs fp64, and the same result as
+    the contraction engine they replace (DSTAG_THIN=0)."""
+    from dstagnn_drought_b200 import contract
+    K, X, T, Fin, Cc = cfg
+    torch.manual_seed(4)
+    Z, th = torch.randn(K, X, T, Fin, device=dev), torch.randn(K, Fin, Cc, device=dev)
+    dout = torch.randn(X, T, Cc, device=dev)
+    fn = lambda z, t: contract("kxtf,kfc->xtc", z, t, relu=True)
+    from dstagnn_drought_b200 import _lib
+    before = _lib.launch_count()
+    out, (dZ, dT) = _grads(fn, [Z, th], dout)
+    assert _lib.launch_count() - before == 3            # expand; one backward pass; fixed-order fold of its partials
+    ref, (rZ, rT) = _grads(lambda z, t: torch.relu(torch.einsum("kxtf,kfc->xtc", z, t)), [Z.double(), th.double()],
+                           dout.double())
+    for got, want in ((out, ref), (dZ, rZ), (dT, rT)):
+        assert rel_err(got, want) < TOL
+    monkeypatch.setenv("DSTAG_THIN", "0")
+    out2, (dZ2, dT2) = _grads(fn, [Z, th], dout)
+    for got, want in ((out2, ref), (dZ2, rZ), (dT2, rT)):
+        assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(5, 12, 1, 32), (1531, 12, 1, 32), (64, 7, 3, 64), (33, 12, 4, 8)])
+def test_thin_residual_conv(dev, cfg):
+    """1x1 residual convolution of the first block: out = x w^T + b with w (C, F_in); x needs no gradient."""
+    from dstagnn_drought_b200 import contract
+    X, T, Fin, Cc = cfg
+    torch.manual_seed(5)
+    x, w, b = torch.randn(X, T, Fin, device=dev), torch.randn(Cc, Fin, device=dev), torch.randn(Cc, device=dev)
+    dout = torch.randn(X, T, Cc, device=dev)
+    out, (dx, dw, db) = _grads(lambda x_, w_, b_: contract("xtf,cf->xtc", x_, w_, c_add=("c", b_)), [x, w, b], dout)
+    ref, (rx, rw, rb) = _grads(lambda x_, w_, b_: torch.einsum("xtf,cf->xtc", x_, w_) + b_,
+                               [x.double(), w.double(), b.double()], dout.double())
+    for got, want in ((out, ref), (dx, rx), (dw, rw), (db, rb)):
+        assert got.shape == want.shape and rel_err(got, want) < TOL
+    wd = w.detach().clone().requires_grad_(True)
+    contract("xtf,cf->xtc", x, wd).backward(dout)          # weight gradient alone (no dz, no bias)
+    assert rel_err(wd.grad, rw) < TOL
+
+
+@pytest.mark.parametrize("cfg", [(3, 12, 36, 32), (1531, 12, 36, 32), (37, 20, 60, 32), (64, 3, 4, 8), (501, 6, 12, 16),
+                                 (9, 7, 24, 64)])
+def test_fcmy_param_grads(dev, cfg):
+    """Streaming T x S reduction (one and three rows of `a` per thread, ragged node slabs) against fp64 einsum."""
+    from dstagnn_drought_b200.ops import fcmy_param_grads
+    X, T, S, Cc = cfg
+    torch.manual_seed(21)
+    dtc, cat = torch.randn(X, T, Cc, device=dev), torch.randn(X, S, Cc, device=dev)
+    dw, db = fcmy_param_grads(dtc, cat)
+    assert rel_err(dw, torch.einsum("xtc,xsc->ts", dtc.double(), cat.double())) < TOL
+    assert rel_err(db, dtc.double().sum((0, 2))) < TOL
+
+
 @pytest.mark.parametrize("cfg", [(148, 128, 32), (64, 512, 384), (17, 5, 12), (3, 7, 6), (295, 96, 32), (20, 1000, 64)])
 def test_sum_slices_fixed_order(dev, cfg):
     """dstag_sum_slices (serial and slice-parallel kernels): the sum of the slices, identical from run to run."""
