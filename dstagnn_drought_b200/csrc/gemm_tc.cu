@@ -42,6 +42,9 @@ constexpr int TC_A_WARPS = 8, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue wa
 constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
 constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;         // one thread issues the TMA bulk-tensor loads
 constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // 576
+#ifndef TC_STAGE_LIMIT
+#define TC_STAGE_LIMIT 6                              // (-DTC_STAGE_LIMIT=n: pipeline-depth experiments)
+#endif
 constexpr int TC_SMEM_BUDGET = 196 * 1024;            // operand stages
 constexpr int TC_EPI_SMEM = TC_EPI_WARPS * 32 * 36 * 4;   // per-warp 32 x 32 transpose buffers (row stride 33 or 36)
 
@@ -301,7 +304,7 @@ struct TcCfg {
   static constexpr int STAGE = A_PLANES * A_PLANE + PLANES * B_PLANE;
   static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE;
   static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 6;    // 64 TMEM columns (hi + lo) per stage
-  static constexpr int STAGES_CAP = STAGES_TM < 6 ? STAGES_TM : 6;
+  static constexpr int STAGES_CAP = STAGES_TM < TC_STAGE_LIMIT ? STAGES_TM : TC_STAGE_LIMIT;
   static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
   static constexpr int BAR_OFF = STAGES * STAGE;
   static constexpr int EPI_OFF = BAR_OFF + 512;

@@ -49,6 +49,9 @@ def main():
         ("sat_scores", "bjkd,bikd->bkji", qk[:, :, 1], qk[:, :, 0], dict(out=dS[..., :N], alpha=1 / math.sqrt(dk))),
         ("sat_dq", "bkji,bjkd->bikd", dS[..., :N], qk[:, :, 1], {}),
         ("sat_dk", "bkji,bikd->bjkd", dS[..., :N], qk[:, :, 0], {}),
+        # the sparse path's two dense products with the softmax maps (chains of 64 terms, dstagnn_drought_b200/sparse.py)
+        ("sat_PQ", "bkji,bikd->bjkd", P[..., :N], r(B, N, K, dk), dict(chain=64)),
+        ("sat_PtrK", "bkji,bjkd->bikd", P[..., :N], r(B, N, K, dk), dict(chain=64)),
         ("qkv", "rn,on->ro", E, Wqkv, {}),
         ("qkv_dx", "ro,on->rn", r(B * FT, 3 * H * dk), Wqkv, dict(out=rp(B * FT, N))),
         ("qkv_dw", "ro,rn->on", r(B * FT, 3 * H * dk), E, dict(out=rp(3 * H * dk, N))),
