@@ -351,10 +351,17 @@ struct PosIter {
 // Measured on B200: weight-gradient shapes 7-20 % faster; not used with a Hadamard factor or narrower
 // B tiles, where the coupling of the two groups costs more than the balance gains.
 // A through tensor memory: thread (warp w, lane l) owns row 32 (w % 4) + l of the raw tile and the k half w / 4.
-template <class Cfg>
+// In team mode (TEAMS: B tiles narrower than 128 rows) the A warps form two teams of four that take alternate
+// k-blocks and split BOTH k halves of their row: the chain wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive
+// is latency-bound per warp (ncu on sat_PQ: 1400 cycles per k-block with the TMA data two stages ahead), and two
+// teams keep two k-blocks in that chain at once.
+template <class Cfg, bool TEAMS>
 __device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_major, bool plain, uint32_t tmem_slot, int t) {
   const int lane = t & 31, w = t >> 5;
-  const int r = 32 * (w & 3) + lane, kh = w >> 2;
+  const int r = 32 * (w & 3) + lane;
+#pragma unroll
+  for (int half = 0; half < (TEAMS ? 2 : 1); ++half) {
+  const int kh = TEAMS ? half : (w >> 2);
   uint32_t hi[16], lo[16];
   if (!mn_major) {
 #pragma unroll
@@ -385,9 +392,14 @@ __device__ __forceinline__ void finish_a_tmem(const uint8_t* a_raw, bool mn_majo
   const uint32_t ta = tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + 16 * kh;
   tmem_st16(ta, hi);
   tmem_st16(ta + 32, lo);
+  }
   tmem_st_wait();
   tc_fence_before();
 }
+
+// Two A-warp teams on alternate k-blocks: A through tensor memory and the B split left to the B warps.
+template <class Cfg, int BN, bool IS_A>
+struct TcTeams { static constexpr bool value = Cfg::ATM && BN < 128 && IS_A; };
 
 template <class Cfg, int BN, bool X3, bool AMUL, bool IS_A>
 __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uint64_t* rawb, uint32_t ph, bool has_mul,
@@ -400,7 +412,7 @@ __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uin
     if (IS_A) {
       if (lane == 0) mbar_wait(rawa, ph, 0);
       __syncwarp();
-      finish_a_tmem<Cfg>(stage, a_mn, a_plain, tmem_slot, t);
+      finish_a_tmem<Cfg, TcTeams<Cfg, BN, IS_A>::value>(stage, a_mn, a_plain, tmem_slot, t);
       if (!SHARE_B) return;
     }
     if (lane == 0) mbar_wait(rawb, ph, 0);
@@ -480,12 +492,18 @@ __device__ __forceinline__ void transform_all(const TcParams& p, uint8_t* smem, 
   const bool a_mn = p.a_mode == MODE_MVEC;
   PosIter pos;
   uint32_t it = 0;
+  constexpr bool TEAMS = TcTeams<Cfg, BN, IS_A>::value;
+  const uint32_t team = (uint32_t)(t >> 7);             // A warps 0-3 / 4-7
   for (bool ok = pos.init(p); ok; ok = pos.next(p), ++it) {
+    if (TEAMS && (it & 1) != team) continue;
     const int s = it % Cfg::STAGES;
     finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (it / Cfg::STAGES) & 1,
                                           has_mul, t, pt, lane, tmem_base + Cfg::A_TM + s * 64, a_mn, a_mn && p.a_tma);
     __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar + s);
+    if (lane == 0) {
+      mbar_arrive(full_bar + s);
+      if (TEAMS) mbar_arrive(full_bar + s);             // (the barrier counts all eight A warps)
+    }
   }
 }
 
@@ -541,12 +559,19 @@ __device__ __forceinline__ void produce_async(const TcParams& p, uint8_t* smem, 
     ++ni;
   };
   for (int d = 0; d < STAGES - 1 && oki; ++d) issue_one();
+  constexpr bool TEAMS = TcTeams<Cfg, BN, IS_A>::value;
+  const uint32_t team = (uint32_t)(t >> 7);
   while (okx) {
     const int s = nx % STAGES;
-    finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (nx / STAGES) & 1, has_mul,
-                                          t, pt, lane, tmem_base + Cfg::A_TM + s * 64, p.a_mode == MODE_MVEC, false);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar + s);
+    if (!TEAMS || (nx & 1) == team) {
+      finish_stage<Cfg, BN, X3, AMUL, IS_A>(smem + s * Cfg::STAGE, rawa_bar + s, rawb_bar + s, (nx / STAGES) & 1, has_mul,
+                                            t, pt, lane, tmem_base + Cfg::A_TM + s * 64, p.a_mode == MODE_MVEC, false);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(full_bar + s);
+        if (TEAMS) mbar_arrive(full_bar + s);
+      }
+    }
     okx = px.next(p);
     ++nx;
     if (oki) issue_one();
