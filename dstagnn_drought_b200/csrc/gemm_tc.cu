@@ -42,6 +42,9 @@ constexpr int TC_A_WARPS = 8, TC_B_WARPS = 4, TC_EPI_WARPS = 4;   // epilogue wa
 constexpr int TC_MMA_WARP = TC_A_WARPS + TC_B_WARPS + TC_EPI_WARPS;
 constexpr int TC_TMA_WARP = TC_MMA_WARP + 1;         // one thread issues the TMA bulk-tensor loads
 constexpr int TC_THREADS = (TC_TMA_WARP + 1) * 32;   // 576
+#ifndef TC_DBG_SKIP
+#define TC_DBG_SKIP 0                                 // timing experiments only (results are wrong): 1 = no A split,
+#endif                                                // 2 = no B split, 4 = one MMA per k-step instead of three
 #ifndef TC_STAGE_LIMIT
 #define TC_STAGE_LIMIT 6                              // (-DTC_STAGE_LIMIT=n: pipeline-depth experiments)
 #endif
@@ -412,11 +415,16 @@ __device__ __forceinline__ void finish_stage(uint8_t* stage, uint64_t* rawa, uin
     if (IS_A) {
       if (lane == 0) mbar_wait(rawa, ph, 0);
       __syncwarp();
+#if !(TC_DBG_SKIP & 1)
       finish_a_tmem<Cfg, TcTeams<Cfg, BN, IS_A>::value>(stage, a_mn, a_plain, tmem_slot, t);
+#endif
       if (!SHARE_B) return;
     }
     if (lane == 0) mbar_wait(rawb, ph, 0);
     __syncwarp();
+#if TC_DBG_SKIP & 2
+    return;
+#endif
     uint8_t* b_hi = stage + Cfg::B_OFF;
     constexpr int B_CH = BN * 8;
     constexpr int NTB = SHARE_B ? (TC_A_WARPS + TC_B_WARPS) * 32 : TC_B_WARPS * 32;
@@ -726,9 +734,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const uint32_t first = (kb == c0 && kk == 0) ? 0u : 1u;
             if constexpr (Cfg::ATM) {
               const uint32_t ta = tmem_base + Cfg::A_TM + s * 64 + 8 * kk;     // hi columns; lo at +32
+#if TC_DBG_SKIP & 4
+              umma_tf32_ts(d_tmem, ta, b_hi + ba, idesc_ts, first);
+#else
               umma_tf32_ts(d_tmem, ta + 32, b_hi + ba, idesc_ts, first);
               umma_tf32_ts(d_tmem, ta, b_lo + ba, idesc_ts, 1u);
               umma_tf32_ts(d_tmem, ta, b_hi + ba, idesc_ts, 1u);
+#endif
             } else if (X3) {
               umma_tf32(d_tmem, a_lo + aa, b_hi + ba, idesc, first);
               umma_tf32(d_tmem, a_hi + aa, b_lo + ba, idesc, 1u);
