@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdstagnn_b200.so")
 # A/B benchmarking of engine variants on the same box: DSTAG_LIB_PATH selects another build of the same ABI
 LIB_PATH = os.environ.get("DSTAG_LIB_PATH", LIB_PATH)
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 ACC_STORE, ACC_ADD, ACC_ATOMIC = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
@@ -68,6 +68,7 @@ SIGNATURES = {
     "dstag_tattn_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_fwd": (C.c_int, [_F, _F, _i64, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_bwd": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
+    "dstag_gtu_gate_bwd_sv": (C.c_int, [_F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_tc_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
     "dstag_gtu_conv_gate_fwd": (C.c_int, [_F, _F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _F]),
     "dstag_gtu_gate_conv_bwd": (C.c_int, [_F, _F, _F, _F, _F, _F, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _F]),

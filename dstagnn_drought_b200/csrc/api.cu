@@ -45,7 +45,7 @@ static int validate(const dstag_gemm_t* g) {
 
 extern "C" {
 
-int dstag_abi_version(void) { return 18; }
+int dstag_abi_version(void) { return 19; }
 const char* dstag_last_error(void) { return dstag::g_err; }
 int64_t dstag_launch_count(void) { return dstag::g_launches.load(); }
 void dstag_reset_launch_count(void) { dstag::g_launches.store(0); }

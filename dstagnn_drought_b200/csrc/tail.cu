@@ -32,6 +32,9 @@ gtu_gate_fwd_kernel(const float* __restrict__ u, float* __restrict__ out, long l
 }
 
 constexpr int kGateNC = 8;       // channels per lane kept in registers for the bias gradient (C <= 256)
+// FROM_SV: `u` holds the saved gate factors [tanh(p) | sigmoid(q)] of the fused forward kernel (csrc/gtu_tc.cu)
+// instead of the pre-activations.
+template <bool FROM_SV>
 __global__ void __launch_bounds__(256)
 gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout, float* __restrict__ dup,
                     float* __restrict__ db, long long X, int C, int Tp, int pad, int S, int off) {
@@ -55,7 +58,8 @@ gtu_gate_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dout,
       for (int i = 0; i < kGateNC; ++i) {
         const int c = lane + 32 * i;
         if (c < C) {
-          const float th = tanhf_(__ldg(up + c)), sg = sigmoidf_(__ldg(up + C + c));
+          const float th = FROM_SV ? __ldg(up + c) : tanhf_(__ldg(up + c));
+          const float sg = FROM_SV ? __ldg(up + C + c) : sigmoidf_(__ldg(up + C + c));
           const float d = __ldg(dp + c);
           const float rp = d * sg * (1.f - th * th), rq = d * th * sg * (1.f - sg);
           o[c] = rp;
@@ -320,16 +324,29 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
   DSTAG_RETURN_LAUNCH("dstag_gtu_gate_fwd");
 }
 
-int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C, int32_t Tp,
-                       int32_t pad, int32_t S, int32_t off, void* stream) {
+static int gate_bwd(const char* name, bool from_sv, const float* u, const float* dout, float* dup, float* db, int64_t X,
+                    int32_t C, int32_t Tp, int32_t pad, int32_t S, int32_t off, void* stream) {
   DSTAG_CHECK_ARG(u && dout && dup && X > 0 && C > 0 && Tp > 0 && pad >= 0 && off >= 0 && off + Tp <= S,
-                  "dstag_gtu_gate_bwd: bad arguments");
-  DSTAG_CHECK_ARG(C <= 32 * kGateNC, "dstag_gtu_gate_bwd: at most %d channels", 32 * kGateNC);
+                  "%s: bad arguments", name);
+  DSTAG_CHECK_ARG(C <= 32 * kGateNC, "%s: at most %d channels", name, 32 * kGateNC);
   long long blocks = (X + 7) / 8;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   const size_t smem = db ? (size_t)8 * 2 * C * sizeof(float) : 0;
-  gtu_gate_bwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(u, dout, dup, db, X, C, Tp, pad, S, off);
-  DSTAG_RETURN_LAUNCH("dstag_gtu_gate_bwd");
+  if (from_sv)
+    gtu_gate_bwd_kernel<true><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(u, dout, dup, db, X, C, Tp, pad, S, off);
+  else
+    gtu_gate_bwd_kernel<false><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(u, dout, dup, db, X, C, Tp, pad, S, off);
+  DSTAG_RETURN_LAUNCH(name);
+}
+
+int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C, int32_t Tp,
+                       int32_t pad, int32_t S, int32_t off, void* stream) {
+  return gate_bwd("dstag_gtu_gate_bwd", false, u, dout, dup, db, X, C, Tp, pad, S, off, stream);
+}
+
+int dstag_gtu_gate_bwd_sv(const float* sv, const float* dout, float* dup, float* db, int64_t X, int32_t C, int32_t Tp,
+                          int32_t pad, int32_t S, int32_t off, void* stream) {
+  return gate_bwd("dstag_gtu_gate_bwd_sv", true, sv, dout, dup, db, X, C, Tp, pad, S, off, stream);
 }
 
 int dstag_outer_sum_supported(int32_t m, int32_t n, int32_t C) {

@@ -478,7 +478,10 @@ class GtuStack(torch.autograd.Function):
         out = torch.empty((X, total, Cc), device=g.device, dtype=torch.float32)
         need_bwd = any(ctx.needs_input_grad) and (not save or bool(save[0]))
         ctx.fused = GtuStack._fused(lib, Cc, T, need_bwd)
-        if ctx.fused:
+        # more than 128 output steps per node (the drought configuration, T = 144): the fused forward covers the shape,
+        # the fused backward does not -- forward fused, backward through the contraction engine from the saved factors
+        ctx.from_sv = not ctx.fused and need_bwd and GtuStack._fused(lib, Cc, T, False)
+        if ctx.fused or ctx.from_sv:
             # one tcgen05 kernel per kernel size: convolution + bias + gate + concatenation; the conv output stays
             # on chip and only the gate factors [tanh(p) | sigmoid(q)] are kept for the backward
             svs, off = [], 0
@@ -572,8 +575,9 @@ class GtuStack(torch.autograd.Function):
             tpad = tp + 2 * pad
             dup = torch.empty((X, tpad, 2 * Cc), device=g.device, dtype=torch.float32)
             db = zeros((2 * Cc,), g.device)                                          # bias gradient, fused
-            _lib.check(lib.dstag_gtu_gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), db.data_ptr(), X, Cc,
-                                              tp, pad, total, off, _stream(g)), "dstag_gtu_gate_bwd")
+            gate_bwd = lib.dstag_gtu_gate_bwd_sv if ctx.from_sv else lib.dstag_gtu_gate_bwd
+            _lib.check(gate_bwd(u.data_ptr(), dout.data_ptr(), dup.data_ptr(), db.data_ptr(), X, Cc,
+                                tp, pad, total, off, _stream(g)), "dstag_gtu_gate_bwd")
             du = dup[:, pad:pad + tp, :]                                             # valid rows (view)
             dwk = contract_raw("xto,xtk->ok", du, GtuStack._views(g, ks), tag=f"gtu{ks}_dw")
             dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)

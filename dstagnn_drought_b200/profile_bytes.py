@@ -35,6 +35,7 @@ ALGO_BYTES = {
     "dstag_tattn_bwd": lambda a: _tattn(a, True),
     "dstag_gtu_gate_fwd": lambda a: 4 * a[2] * a[4] * 3 * a[3],
     "dstag_gtu_gate_bwd": lambda a: 4 * a[4] * a[5] * (3 * a[6] + 2 * (a[6] + 2 * a[7])),
+    "dstag_gtu_gate_bwd_sv": lambda a: 4 * a[4] * a[5] * (3 * a[6] + 2 * (a[6] + 2 * a[7])),
     # fused GTU: g in, cat (+ saved gate factors) out; saved factors + dcat in, du + dg out
     "dstag_gtu_conv_gate_fwd": lambda a: 4 * a[5] * a[6] * (a[7] + (a[7] - a[8] + 1) * (1 + (2 if a[4] else 0))),
     "dstag_gtu_gate_conv_bwd": lambda a: 4 * a[6] * a[7] * ((a[8] - a[9] + 1) * 5 + a[8] * (2 if a[12] else 1)),

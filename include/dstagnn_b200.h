@@ -199,6 +199,10 @@ int dstag_gtu_gate_fwd(const float* u, float* out, int64_t X, int32_t C, int32_t
  * gradient (column sums of dup) is ACCUMULATED into it. */
 int dstag_gtu_gate_bwd(const float* u, const float* dout, float* dup, float* db, int64_t X, int32_t C,
                        int32_t Tp, int32_t pad, int32_t S, int32_t off, void* stream);
+/* the same from the gate factors sv = [tanh(p) | sigmoid(q)] (X, Tp, 2C) that dstag_gtu_conv_gate_fwd saves: shapes whose
+ * forward runs fused but whose backward does not (more than 128 output steps per node: the drought configuration) */
+int dstag_gtu_gate_bwd_sv(const float* sv, const float* dout, float* dup, float* db, int64_t X, int32_t C,
+                          int32_t Tp, int32_t pad, int32_t S, int32_t off, void* stream);
 
 /* Fused GTU kernels on the tcgen05 tensor cores (csrc/gtu_tc.cu), C = 32 channels, ks in {3, 5, 7}:
  *   dstag_gtu_conv_gate_fwd: Conv2d(C -> 2C, (1, ks)) over time + bias + tanh * sigmoid gate + torch.cat

@@ -44,7 +44,7 @@ class FakeLib:
 
     # ---- plumbing ----
     def dstag_abi_version(self):
-        return 18
+        return 19
 
     def dstag_last_error(self):
         return self.err
@@ -356,11 +356,14 @@ class FakeLib:
             _arr(asum, m)[:] += A.sum((0, 2))
         return 0
 
-    def dstag_gtu_gate_bwd(self, u, dout, dup, db, X, Cc, Tp, pad, S, off, stream):
+    def dstag_gtu_gate_bwd_sv(self, sv, dout, dup, db, X, Cc, Tp, pad, S, off, stream):
+        return self.dstag_gtu_gate_bwd(sv, dout, dup, db, X, Cc, Tp, pad, S, off, stream, from_sv=True)
+
+    def dstag_gtu_gate_bwd(self, u, dout, dup, db, X, Cc, Tp, pad, S, off, stream, from_sv=False):
         self.launches += 1
         U = _arr(u, X * Tp * 2 * Cc).reshape(X, Tp, 2 * Cc).astype(np.float64)
         d = _arr(dout, X * S * Cc).reshape(X, S, Cc)[:, off:off + Tp, :].astype(np.float64)   # (X, Tp, C)
-        th, sg = np.tanh(U[:, :, :Cc]), 1 / (1 + np.exp(-U[:, :, Cc:]))
+        th, sg = (U[:, :, :Cc], U[:, :, Cc:]) if from_sv else (np.tanh(U[:, :, :Cc]), 1 / (1 + np.exp(-U[:, :, Cc:])))
         D = _arr(dup, X * (Tp + 2 * pad) * 2 * Cc).reshape(X, Tp + 2 * pad, 2 * Cc)
         D[:] = 0
         D[:, pad:pad + Tp, :Cc] = d * sg * (1 - th * th)

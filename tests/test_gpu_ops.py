@@ -281,7 +281,7 @@ def test_sparse_cheb_conv_matches_dense_formula(dev, precision, cfg):
 
 
 @pytest.mark.parametrize("cfg", [(5, 32, 12), (300, 32, 12), (7, 32, 20), (6, 8, 144), (1531, 32, 12), (40, 32, 7),
-                                 (9, 32, 130)])
+                                 (9, 32, 130), (5, 32, 144)])   # (last: fused forward, engine backward from the gate factors)
 def test_gtu_stack(dev, precision, cfg):
     from dstagnn_drought_b200.ops import GtuStack
     X, Cc, T = cfg
