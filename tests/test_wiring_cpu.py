@@ -45,3 +45,42 @@ def test_block_stack_wiring_matches_reference(name, path, monkeypatch):
             assert p.grad is not None, k
             assert rel_err(p.grad, g[k]) < 5e-5, k
     assert fake.launches > 50
+
+
+@pytest.mark.parametrize("T", [12, 140])
+def test_gtu_stack_modes_against_conv2d(T, monkeypatch):
+    """Host logic of the three GTU modes through the emulated ABI: fused forward + fused backward (T = 12), and the long
+    series (T = 140: more than 128 output steps per node) whose forward runs fused and whose backward goes through the
+    contraction engine from the saved gate factors (dstag_gtu_gate_bwd_sv)."""
+    from dstagnn_drought_b200.ops import GtuStack
+    fake = cpu_emulation.install(monkeypatch)
+    calls = []
+    for name in ("dstag_gtu_conv_gate_fwd", "dstag_gtu_gate_conv_bwd", "dstag_gtu_gate_bwd_sv", "dstag_gtu_gate_bwd"):
+        orig = getattr(type(fake), name)
+        monkeypatch.setattr(type(fake), name, (lambda o, n: lambda self, *a, **k: (calls.append(n), o(self, *a, **k))[1])(orig, name))
+    torch.manual_seed(3)
+    X, Cc = 2, 32
+    g = torch.randn(X, T, Cc)
+    ws = [torch.randn(2 * Cc, Cc, 1, ks) * 0.2 for ks in (3, 5, 7)]
+    bs = [torch.randn(2 * Cc) for _ in range(3)]
+    leaves = [t.clone().requires_grad_(True) for t in (g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+    out = GtuStack.apply(*leaves, True)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    ref_leaves = [t.double().clone().requires_grad_(True) for t in (g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+    xc = ref_leaves[0].permute(2, 0, 1).unsqueeze(0)
+    outs = []
+    for i in range(3):
+        u = torch.nn.functional.conv2d(xc, ref_leaves[1 + 2 * i], ref_leaves[2 + 2 * i])
+        outs.append(torch.tanh(u[:, :Cc]) * torch.sigmoid(u[:, -Cc:]))
+    ref = torch.cat(outs, dim=-1)[0].permute(1, 2, 0)
+    ref.backward(dout.double())
+    assert rel_err(out.detach(), ref.detach()) < 2e-5
+    for a, b in zip(leaves, ref_leaves):
+        assert rel_err(a.grad, b.grad) < 5e-5
+    assert calls.count("dstag_gtu_conv_gate_fwd") == 3
+    if T == 12:
+        assert calls.count("dstag_gtu_gate_conv_bwd") == 3 and "dstag_gtu_gate_bwd_sv" not in calls
+        assert "dstag_gtu_gate_bwd" not in calls
+    else:       # (the emulation's _sv entry point forwards to its gate_bwd with the factors given)
+        assert calls.count("dstag_gtu_gate_bwd_sv") == 3 and "dstag_gtu_gate_conv_bwd" not in calls
