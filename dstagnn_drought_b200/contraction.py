@@ -636,7 +636,7 @@ def _thin_args(spec, A, B, amul, alpha, cadd, cadd_sub, pad_rows):
     contraction is not one of them (the engine takes it then)."""
     if amul is not None or alpha != 1.0 or pad_rows or os.environ.get("DSTAG_THIN", "1") == "0":
         return None
-    if cadd is not None and cadd_sub != "c":
+    if cadd is not None and (cadd_sub != "c" or not cadd.is_contiguous() or cadd.data_ptr() % 16):
         return None
     if not (A.is_contiguous() and A.dtype == torch.float32 and B.dtype == torch.float32):
         return None
@@ -670,6 +670,8 @@ def _thin_backward(args, A, B, dC, y, need_dA, need_dB, need_dadd):
     J = taps * Fin
     lib = _lib.load()
     st = _lib.stream_ptr(A)
+    if dC.data_ptr() % 16:                 # (an offset view: the kernel reads float4 rows)
+        dC = dC.clone()
     dA = torch.empty_like(A) if need_dA else None
     part = None
     if need_dB or need_dadd:
