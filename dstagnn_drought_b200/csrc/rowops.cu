@@ -202,6 +202,46 @@ transpose_kernel(const float* __restrict__ in, long long in_ld, float* __restric
   }
 }
 
+// 64 x 64 tiles moved as float4 on both sides.  The tile's rows are enumerated by OUTPUT position p (r = the input
+// row that lands there), so the stores of a row-permuting transpose (r_d > 1: the gradient's way back from the
+// (b, (f, t), n) order of the temporal attention) are contiguous too -- walking input rows, consecutive lanes wrote
+// R / r_d floats apart.  Needs in_ld, out_ld multiples of 4 with in_ld >= C rounded up to 4, 16-byte aligned bases.
+__global__ void __launch_bounds__(256)
+transpose64_kernel(const float* __restrict__ in, long long in_ld, float* __restrict__ out, long long out_ld, int R,
+                   int C, int r_d, int c_d) {
+  __shared__ float tile[64][65];
+  const long long ibase = (long long)blockIdx.z * R * in_ld, obase = (long long)blockIdx.z * C * out_ld;
+  const int c0 = blockIdx.x * 64, p0 = blockIdx.y * 64;
+  const int lo = threadIdx.x & 15, hi = threadIdx.x >> 4;
+  const int Rd = R / r_d, Cd = C / c_d;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pl = hi + 16 * j, p = p0 + pl, c = c0 + 4 * lo;
+    if (p < R && c < C) {
+      const int r = r_d > 1 ? (p % Rd) * r_d + p / Rd : p;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in + ibase + (long long)r * in_ld + c));
+      tile[pl][4 * lo] = v.x; tile[pl][4 * lo + 1] = v.y; tile[pl][4 * lo + 2] = v.z; tile[pl][4 * lo + 3] = v.w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cl = hi + 16 * j, c = c0 + cl, p = p0 + 4 * lo;
+    if (c < C && p < R) {
+      const int pc = c_d > 1 ? (c % c_d) * Cd + c / c_d : c;
+      float* dst = out + obase + (long long)pc * out_ld + p;
+      const float4 v = make_float4(tile[4 * lo][cl], tile[4 * lo + 1][cl], tile[4 * lo + 2][cl], tile[4 * lo + 3][cl]);
+      if (p + 3 < R) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        dst[0] = v.x;
+        if (p + 1 < R) dst[1] = v.y;
+        if (p + 2 < R) dst[2] = v.z;
+      }
+    }
+  }
+}
+
 // ======================================================================================
 // Row softmax (in place), padded columns zeroed.
 // ======================================================================================
@@ -726,6 +766,12 @@ int dstag_transpose(const float* in, int64_t in_ld, float* out, int64_t out_ld, 
                   "dstag_transpose: bad arguments");
   DSTAG_CHECK_ARG(r_d >= 1 && c_d >= 1 && R % r_d == 0 && C % c_d == 0, "dstag_transpose: bad permutation factors");
   DSTAG_CHECK_ARG(batch <= 65535 && (R + 31) / 32 <= 65535, "dstag_transpose: grid too large");
+  if (in_ld % 4 == 0 && out_ld % 4 == 0 && in_ld >= (C + 3) / 4 * 4 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (R + 63) / 64 <= 65535) {
+    const dim3 grid64((C + 63) / 64, (R + 63) / 64, batch);
+    transpose64_kernel<<<grid64, 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, R, C, r_d, c_d);
+    DSTAG_RETURN_LAUNCH("dstag_transpose");
+  }
   const dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, R, C, r_d, c_d);
   DSTAG_RETURN_LAUNCH("dstag_transpose");

@@ -504,6 +504,16 @@ def test_transpose_softmax_colsum_relu(dev):
     want = xc.view(Bz, N_, T_, F_).permute(0, 3, 2, 1).reshape(Bz, F_ * T_, N_)
     assert torch.equal(fwd, want)
     assert torch.equal(transpose_raw(fwd, r_d=T_), xc)
+    # float4 tile kernel (leading dimensions multiples of 4), both directions, ragged tiles, PEMS07's own shape
+    for Bz, N_, T_, F_ in ((2, 45, 4, 8), (3, 883, 12, 32), (1, 130, 17, 4), (2, 64, 1, 64)):
+        xc = torch.randn(Bz, N_, T_ * F_, device=dev)
+        fwd = transpose_raw(xc, pad_rows=True, c_d=F_)
+        assert fwd.stride(1) % 4 == 0
+        want = xc.view(Bz, N_, T_, F_).permute(0, 3, 2, 1).reshape(Bz, F_ * T_, N_)
+        assert torch.equal(fwd, want)
+        assert torch.equal(transpose_raw(fwd, r_d=T_), xc)
+        assert torch.equal(transpose_raw(xc), xc.transpose(1, 2).contiguous())
+        assert torch.equal(transpose_raw(xc, pad_rows=True), xc.transpose(1, 2))
     for rows, cols in ((7, 1), (1000, 64), (64, 5000), (33, 130)):
         m = torch.randn(rows, cols, device=dev)
         assert rel_err(colsum(m, rows, cols), m.double().sum(0)) < TOL
