@@ -217,10 +217,15 @@ class DSTAGNN_block(nn.Module):
         theta = ops.PackRows.apply(*self.cheb_conv_SAt.Theta).view(K, Fin, C)           # (K, F, C)
         g = contract("kxtf,kfc->xtc", zc.view(K, B * N, T, Fin), theta, relu=True)      # (B*N, T, C)
         # 7. gated temporal convolutions                                             (lines 237-242)
+        # (blocks whose tail also consumes g take it from the stack's alias output: the stack's backward kernels then
+        #  accumulate into the tail's gradient instead of autograd adding the two paths)
+        alias = Fin != 1 and torch.is_grad_enabled() and g.requires_grad
         cat = ops.GtuStack.apply(g, self.gtu3.con2out.weight, self.gtu3.con2out.bias,
                                  self.gtu5.con2out.weight, self.gtu5.con2out.bias,
                                  self.gtu7.con2out.weight, self.gtu7.con2out.bias,
-                                 torch.is_grad_enabled())                               # (B*N, 3T-12, C)
+                                 torch.is_grad_enabled(), alias)                        # (B*N, 3T-12, C)
+        if alias:
+            cat, g = cat
         # 8-11. fcmy over the concatenated time axis, combine, residual, LayerNorm over channels
         #       (lines 243-252); one fused kernel for the PEMS shapes, GEMM + tail kernel otherwise
         lin = self.fcmy[0]

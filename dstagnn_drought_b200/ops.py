@@ -467,10 +467,20 @@ class GtuStack(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, g, w3, b3, w5, b5, w7, b7, *save):
-        # (save: optional flag, False when the caller runs under no_grad -- grad mode is not visible in here)
+        # (save[0]: optional flag, False when the caller runs under no_grad -- grad mode is not visible in here;
+        #  save[1]: also return g itself as a second output.  A caller that feeds g to another consumer through that
+        #  alias (the block tail) gets its gradient accumulated by the backward kernels instead of a separate add.)
+        ctx.extra = len(save)
+        ctx.alias = len(save) > 1 and bool(save[1])
+        if ctx.alias:
+            ctx.set_materialize_grads(False)
+            return GtuStack._forward(ctx, g, w3, b3, w5, b5, w7, b7, *save), g
+        return GtuStack._forward(ctx, g, w3, b3, w5, b5, w7, b7, *save)
+
+    @staticmethod
+    def _forward(ctx, g, w3, b3, w5, b5, w7, b7, *save):
         lib = _lib.load()
         _check(g, "g")
-        ctx.extra = len(save)
         g = g.contiguous()
         X, T, Cc = g.shape
         widths = [T - ks + 1 for ks in GtuStack.KS]
@@ -511,14 +521,15 @@ class GtuStack(torch.autograd.Function):
         return out
 
     @staticmethod
-    def _backward_fused(ctx, dout):
+    def _backward_fused(ctx, dout, dg_in=None):
         lib = _lib.load()
         g, w3, w5, w7, sv3, sv5, sv7 = ctx.saved_tensors
         X, T, Cc = g.shape
         dout = dout.contiguous()
         total = dout.shape[1]
-        # (the kernel always produces the input gradient: it shares its pass over dcat with du)
-        dg = torch.empty_like(g)
+        # (the kernel always produces the input gradient: it shares its pass over dcat with du; a gradient that arrived
+        #  through the alias output is the buffer it accumulates into)
+        dg = dg_in if dg_in is not None else torch.empty_like(g)
         dwks, grads, off = [], [], 0
         with _lib.on_device(_stream(g)):
             ws_rows = lib.dstag_gtu_bwd_ws_rows()
@@ -529,7 +540,8 @@ class GtuStack(torch.autograd.Function):
             ws = zeros((ws_rows, 2 * Cc), g.device)          # per-warp partial column sums of du
             _lib.check(lib.dstag_gtu_gate_conv_bwd(sv.data_ptr(), dout.data_ptr(), w.contiguous().data_ptr(), du.data_ptr(),
                                                    dg.data_ptr(), ws.data_ptr(), X, Cc, T, ks, total, off,
-                                                   0 if i == 0 else 1, _stream(g)), "dstag_gtu_gate_conv_bwd")
+                                                   0 if (i == 0 and dg_in is None) else 1, _stream(g)),
+                       "dstag_gtu_gate_conv_bwd")
             db = colsum(ws, ws_rows, 2 * Cc)
             dw = torch.empty(w.shape, device=g.device, dtype=torch.float32)
             if gram and lib.dstag_gram_supported(ks, 2 * Cc, T, tp):
@@ -552,15 +564,20 @@ class GtuStack(torch.autograd.Function):
         return (dg if ctx.needs_input_grad[0] else None, *grads, *([None] * ctx.extra))
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *dalias):
+        dg_in = dalias[0] if dalias and dalias[0] is not None else None
+        if dg_in is not None and not (dg_in.is_contiguous() and dg_in.data_ptr() % 16 == 0):
+            dg_in = dg_in.contiguous().clone()
+        if dout is None:                                   # (only the alias was used downstream)
+            return (dg_in, *([None] * (6 + ctx.extra)))
         if ctx.fused:
-            return GtuStack._backward_fused(ctx, dout)
+            return GtuStack._backward_fused(ctx, dout, dg_in)
         lib = _lib.load()
         g, w3, w5, w7, u3, u5, u7 = ctx.saved_tensors
         X, T, Cc = g.shape
         dout = dout.contiguous()
         total = dout.shape[1]
-        dg = torch.empty_like(g) if ctx.needs_input_grad[0] else None
+        dg = (dg_in if dg_in is not None else torch.empty_like(g)) if ctx.needs_input_grad[0] else None
         wflips = None
         if dg is not None:
             # flipped, transposed kernels (c, (d', o)) = w[o, c, 0, ks-1-d'] for the input-gradient correlation:
@@ -569,7 +586,7 @@ class GtuStack(torch.autograd.Function):
             multi_copy([(wf, (w.data_ptr() + 4 * (ks - 1), (ks, -1, Cc * ks)))
                         for wf, w, ks in zip(wflips, (w3, w5, w7), GtuStack.KS)])
         dwks = []
-        grads, off, first = [], 0, True
+        grads, off, first = [], 0, dg_in is None
         for i, (ks, w, u) in enumerate(zip(GtuStack.KS, (w3, w5, w7), (u3, u5, u7))):
             tp, pad = T - ks + 1, ks - 1
             tpad = tp + 2 * pad
