@@ -84,3 +84,39 @@ def test_gtu_stack_modes_against_conv2d(T, monkeypatch):
         assert "dstag_gtu_gate_bwd" not in calls
     else:       # (the emulation's _sv entry point forwards to its gate_bwd with the factors given)
         assert calls.count("dstag_gtu_gate_bwd_sv") == 3 and "dstag_gtu_gate_conv_bwd" not in calls
+
+
+@pytest.mark.parametrize("T", [12, 140])
+def test_gtu_stack_alias_output_accumulates_gradient(T, monkeypatch):
+    """The alias output hands g on to a second consumer; the stack's backward accumulates into that consumer's
+    gradient (in the kernels' dg buffer) and the sum equals what autograd would have added."""
+    from dstagnn_drought_b200.ops import GtuStack
+    cpu_emulation.install(monkeypatch)
+    torch.manual_seed(8)
+    X, Cc = 3, 32
+    g = torch.randn(X, T, Cc)
+    ws = [torch.randn(2 * Cc, Cc, 1, ks) * 0.2 for ks in (3, 5, 7)]
+    bs = [torch.randn(2 * Cc) for _ in range(3)]
+    mix = torch.randn(X, T, Cc)
+
+    def run(alias):
+        leaves = [t.clone().requires_grad_(True) for t in (g, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])]
+        gin = leaves[0] * 1.0                     # (a non-leaf, as in the block)
+        if alias:
+            cat, g2 = GtuStack.apply(gin, *leaves[1:], True, True)
+        else:
+            cat, g2 = GtuStack.apply(gin, *leaves[1:], True), gin
+        loss = (cat ** 2).sum() + (g2 * mix).sum()
+        loss.backward()
+        return cat.detach(), [t.grad for t in leaves]
+
+    cat_a, grads_a = run(True)
+    cat_p, grads_p = run(False)
+    assert torch.equal(cat_a, cat_p)
+    for a, b in zip(grads_a, grads_p):
+        assert rel_err(a, b) < 1e-6
+    # only the alias used downstream: its gradient passes straight through
+    leaf = g.clone().requires_grad_(True)
+    _, g2 = GtuStack.apply(leaf * 1.0, *ws[:1], bs[0], ws[1], bs[1], ws[2], bs[2], True, True)
+    (g2 * mix).sum().backward()
+    assert torch.equal(leaf.grad, mix)
